@@ -1,0 +1,212 @@
+/*
+ * tlb200.h — C ABI of the B200-native TensorLy tenalg hot path.
+ *
+ * Every entry point takes plain device pointers, shapes and a CUDA stream
+ * (passed as void* so that this header needs no CUDA include).  The caller
+ * owns every buffer (inputs, output, workspace); the callee allocates nothing,
+ * never synchronises the device and launches only on `stream`.
+ *
+ * Return value: 0 on success, a negative tlb200_status otherwise.  The Python
+ * shim (tensorly_b200/_ops.py) maps TLB200_EINVAL to ValueError — the same
+ * exception the reference raises for shape mismatches — and everything else to
+ * RuntimeError.
+ *
+ * Each function cites the reference interface it replaces (paths relative to
+ * the tensorly/tensorly checkout, v0.9.0).
+ */
+#ifndef TLB200_H_
+#define TLB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TLB200_MAX_NDIM 8
+
+typedef enum {
+    TLB200_OK = 0,
+    TLB200_EINVAL = -1,    /* bad shape / mode / rank / dtype            */
+    TLB200_EWORKSPACE = -2,/* workspace too small                         */
+    TLB200_ECUDA = -3,     /* a CUDA runtime call or launch failed        */
+    TLB200_EUNSUPPORTED = -4
+} tlb200_status;
+
+typedef enum { TLB200_F32 = 0, TLB200_F64 = 1 } tlb200_dtype;
+
+/* Which kernel family a call may use.  AUTO picks the tcgen05 (tensor-core,
+ * 3xTF32 error-compensated) path when dtype/shape/alignment allow it and the
+ * SIMT path otherwise; both are hand-written sm_100a kernels, there is no
+ * host fallback. */
+typedef enum { TLB200_PATH_AUTO = 0, TLB200_PATH_SIMT = 1, TLB200_PATH_TCGEN05 = 2 } tlb200_path;
+
+/* Library / build introspection. */
+int         tlb200_version(void);
+const char* tlb200_build_arch(void);            /* "sm_100a" */
+const char* tlb200_status_string(int status);
+/* Name of the kernel family the last call on this host thread dispatched to
+ * ("simt", "tcgen05", "copy", ...).  Used by tests to prove which path ran. */
+const char* tlb200_last_path(void);
+
+/* ---------------------------------------------------------------------------
+ * unfold — replaces tensorly.base.unfold (tensorly/base.py:39-53):
+ *   out[i_mode, (i_0..i_{mode-1}, i_{mode+1}..i_{N-1})] = x[i_0..i_{N-1}]
+ * x: C-contiguous N-way tensor; out: C-contiguous (shape[mode], prod(others)).
+ * Pure data movement, bit-exact.
+ * ------------------------------------------------------------------------- */
+int tlb200_unfold(const void* x, const int64_t* shape, int ndim, int mode,
+                  int dtype, void* out, void* stream);
+
+/* fold — replaces tensorly.base.fold (tensorly/base.py:56-79); inverse of unfold.
+ * unfolded: C-contiguous (shape[mode], prod(others)); out: C-contiguous `shape`. */
+int tlb200_fold(const void* unfolded, const int64_t* shape, int ndim, int mode,
+                int dtype, void* out, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * khatri_rao — replaces tensorly.tenalg.core_tenalg.khatri_rao
+ * (tensorly/tenalg/core_tenalg/_khatri_rao.py:9-109).
+ *   out[(i_0,..,i_{m-1}), r] = (((w[r]*M_0[i_0,r]) * M_1[i_1,r]) * ...) * mask[row]
+ * evaluated as a left fold with one IEEE rounding per multiply (no FMA, no
+ * reassociation), so the result is bit-identical to the reference's chain of
+ * broadcast multiplies.  First matrix slowest, last fastest.
+ * mats[i] has rows[i] rows and `rank` columns, element (r,c) at
+ * mats[i][r*row_stride[i] + c*col_stride[i]] (strides in elements).
+ * weights (rank,) and mask (prod(rows),) may be NULL.  out: (prod(rows), rank)
+ * with row stride out_ld >= rank.
+ * ------------------------------------------------------------------------- */
+int tlb200_khatri_rao(const void* const* mats, const int64_t* rows,
+                      const int64_t* row_stride, const int64_t* col_stride,
+                      int nmats, int64_t rank, const void* weights,
+                      const void* mask, int dtype, void* out, int64_t out_ld,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------
+ * MTTKRP — replaces tensorly.tenalg.core_tenalg.unfolding_dot_khatri_rao
+ * (tensorly/tenalg/core_tenalg/mttkrp.py:9-50):
+ *   out[i_mode, r] = sum_{i_n, n != mode} x[i_0..i_{N-1}] * w[r] * prod_{n != mode} F_n[i_n, r]
+ * x: C-contiguous N-way tensor, streamed from HBM exactly once; the Khatri-Rao
+ * matrix and the unfolding are never materialised.  factors[n] is (shape[n], rank)
+ * with element strides; factors[mode] is ignored (may be NULL).  weights may be
+ * NULL.  out: (shape[mode], rank) with row stride out_ld.
+ * `workspace` must hold tlb200_mttkrp_workspace_bytes(...) bytes (256-byte aligned).
+ * ------------------------------------------------------------------------- */
+size_t tlb200_mttkrp_workspace_bytes(const int64_t* shape, int ndim, int mode,
+                                     int64_t rank, int dtype, int path);
+
+int tlb200_mttkrp(const void* x, const int64_t* shape, int ndim, int mode,
+                  const void* const* factors, const int64_t* f_row_stride,
+                  const int64_t* f_col_stride, int64_t rank, const void* weights,
+                  int dtype, void* out, int64_t out_ld, void* workspace,
+                  size_t workspace_bytes, int path, void* stream);
+
+/* The (A, J, B) streaming plan tlb200_mttkrp uses for a shape/mode: the tensor is
+ * viewed as X[a, j, b] with strides (sa, sj, sb) and the KR rows factor as
+ * P[a, :] * Q[b, :].  Host-only (no device work); exposed so the planning logic is
+ * testable without a GPU. */
+typedef struct {
+    int64_t A, J, B;          /* extents                                    */
+    int64_t sa, sj, sb;       /* element strides of the view                */
+    int     p_first, p_count; /* modes folded into the P table              */
+    int     q_first, q_count; /* modes folded into the Q table              */
+    int64_t rank_padded;      /* column count of the P/Q/partials tables    */
+    int64_t splits;           /* split-K factor (deterministic 2-pass sum)  */
+    int     path;             /* resolved tlb200_path                       */
+} tlb200_mttkrp_plan_t;
+
+int tlb200_mttkrp_plan(const int64_t* shape, int ndim, int mode, int64_t rank,
+                       int dtype, int path, tlb200_mttkrp_plan_t* plan);
+
+/* ---------------------------------------------------------------------------
+ * mode_dot — replaces tensorly.tenalg.core_tenalg.mode_dot for a matrix operand
+ * (tensorly/tenalg/core_tenalg/n_mode_product.py:5-76):
+ *   out[.., i, ..] = sum_j m[i, j] * x[.., j, ..]      (contracting `mode`)
+ * m is (rows_out, shape[mode]) addressed as m[i*m_row_stride + j*m_col_stride], so
+ * `transpose=True` in the reference is a stride swap on the caller's side.  A vector
+ * operand is rows_out == 1 (the caller drops the mode).  x and out are C-contiguous;
+ * out has shape[mode] replaced by rows_out.
+ * ------------------------------------------------------------------------- */
+size_t tlb200_mode_dot_workspace_bytes(const int64_t* shape, int ndim, int mode,
+                                       int64_t rows_out, int dtype, int path);
+
+int tlb200_mode_dot(const void* x, const int64_t* shape, int ndim, int mode,
+                    const void* m, int64_t rows_out, int64_t m_row_stride,
+                    int64_t m_col_stride, int dtype, void* out, void* workspace,
+                    size_t workspace_bytes, int path, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * multi_mode_dot — replaces tensorly.tenalg.core_tenalg.multi_mode_dot for matrix
+ * operands (tensorly/tenalg/core_tenalg/n_mode_product.py:79-135): the chain
+ *   x  x_{modes[0]} m_0  x_{modes[1]} m_1 ...
+ * over `nmats` DISTINCT, ascending modes (the caller has already applied `skip`,
+ * sorted by mode and resolved `transpose` into strides).  Intermediates live in
+ * `workspace`.  out is C-contiguous with each contracted extent replaced by
+ * rows_out[k].
+ * ------------------------------------------------------------------------- */
+size_t tlb200_multi_mode_dot_workspace_bytes(const int64_t* shape, int ndim,
+                                             const int* modes, const int64_t* rows_out,
+                                             int nmats, int dtype, int path);
+
+int tlb200_multi_mode_dot(const void* x, const int64_t* shape, int ndim,
+                          const int* modes, const void* const* mats,
+                          const int64_t* rows_out, const int64_t* m_row_stride,
+                          const int64_t* m_col_stride, int nmats, int dtype,
+                          void* out, void* workspace, size_t workspace_bytes,
+                          int path, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * CP-ALS normal equations — replaces the caller-side lines of
+ * tensorly.decomposition._cp.parafac (tensorly/decomposition/_cp.py:411-428):
+ *
+ * tlb200_gram: G = F^T F for F (rows, rank) [rank x rank, row-major, ld = rank].
+ *   Deterministic: per-block partial sums are written to workspace and summed in a
+ *   fixed order by the last block.
+ *
+ * tlb200_cp_update: V = (w w^T) o prod_{i != mode} G_i + l2_reg * I ;
+ *                   F_mode = solve(V^T, M^T)^T   (LU with partial pivoting, as
+ *                   numpy/torch `solve` does), for `rows` rows of the MTTKRP M.
+ *   grams: nmodes pointers to rank x rank Gram matrices (entry `mode` ignored).
+ *   out may alias m.
+ * ------------------------------------------------------------------------- */
+size_t tlb200_gram_workspace_bytes(int64_t rows, int64_t rank, int dtype);
+
+int tlb200_gram(const void* f, int64_t rows, int64_t rank, int64_t row_stride,
+                int64_t col_stride, int dtype, void* gram, void* workspace,
+                size_t workspace_bytes, void* stream);
+
+int tlb200_cp_update(const void* const* grams, int nmodes, int mode, int64_t rank,
+                     const void* weights, double l2_reg, const void* m, int64_t m_ld,
+                     int64_t rows, int dtype, void* out, int64_t out_ld, void* stream);
+
+/* Fast CP reconstruction error — replaces error_calc's MTTKRP shortcut
+ * (tensorly/decomposition/_cp.py:217-225 with cp_norm, tensorly/cp_tensor.py:614-644):
+ *   iprod = sum(M_last o F_last);  norm_cp^2 = sum_{r,s} w_r w_s prod_n G_n[r,s];
+ *   err_out[0] = sqrt(|norm_x2 + norm_cp^2 - 2 iprod|) / sqrt(norm_x2)
+ *   err_out[1] = iprod, err_out[2] = norm_cp^2.
+ * norm_x2 points to a device scalar holding ||X||^2.  err_out: 3 scalars of `dtype`. */
+int tlb200_cp_error(const void* const* grams, int nmodes, int64_t rank,
+                    const void* weights, const void* m_last, int64_t m_ld,
+                    const void* f_last, int64_t f_row_stride, int64_t f_col_stride,
+                    int64_t rows, const void* norm_x2, int dtype, void* err_out,
+                    void* stream);
+
+/* Sum of squares of a contiguous array (||X||^2) into a device scalar of `dtype`
+ * (accumulated in double).  Replaces tl.norm(tensor, 2)**2 at _cp.py:350. */
+size_t tlb200_sumsq_workspace_bytes(int64_t n, int dtype);
+int tlb200_sumsq(const void* x, int64_t n, int dtype, void* out, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+/* Non-negative CP multiplicative update — replaces
+ * tensorly/decomposition/_nn_cp.py:131-136:
+ *   F[i,r] <- F[i,r] * max(M[i,r], eps) / max((F V)[i,r], eps)
+ * with V = (w w^T) o prod_{i != mode} G_i formed exactly as in tlb200_cp_update.
+ * f is updated in place (row stride f_ld). */
+int tlb200_nncp_update(const void* const* grams, int nmodes, int mode, int64_t rank,
+                       const void* weights, const void* m, int64_t m_ld, void* f,
+                       int64_t f_ld, int64_t rows, double eps, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TLB200_H_ */

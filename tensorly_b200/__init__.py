@@ -1,0 +1,29 @@
+"""tensorly_b200 — a B200-native (sm_100a) backend for TensorLy's dense-decomposition hot path.
+
+Public surface (same names and signatures as the reference functions they replace):
+
+    unfold, fold                                   tensorly/base.py
+    khatri_rao, unfolding_dot_khatri_rao           tensorly/tenalg/core_tenalg
+    mode_dot, multi_mode_dot                       tensorly/tenalg/core_tenalg
+    parafac, non_negative_parafac                  tensorly/decomposition (own sweep loop,
+                                                   CUDA-graphed, optionally mode-sharded)
+    register(), use()                              plug the "b200" tenalg backend into an
+                                                   unmodified TensorLy
+
+All arithmetic runs in hand-written CUDA kernels behind the C ABI of include/tlb200.h;
+there is no CPU fallback — a missing libtlb200.so raises at first use.
+"""
+from ._ops import (cp_error, cp_update, fold, get_kernel_path, gram, khatri_rao, last_kernel_path, mode_dot,
+                   mttkrp_plan, multi_mode_dot, nncp_update, set_kernel_path, sumsq, unfold,
+                   unfolding_dot_khatri_rao)
+from .backend import BACKEND_NAME, import_tensorly, register, use
+from .cp_als import CPALS, CPResult, non_negative_parafac, parafac, shard_bounds
+
+__version__ = "0.1.0"
+__all__ = [
+    "unfold", "fold", "khatri_rao", "unfolding_dot_khatri_rao", "mode_dot", "multi_mode_dot",
+    "parafac", "non_negative_parafac", "CPALS", "CPResult", "shard_bounds",
+    "gram", "cp_update", "nncp_update", "cp_error", "sumsq", "mttkrp_plan",
+    "set_kernel_path", "get_kernel_path", "last_kernel_path",
+    "register", "use", "import_tensorly", "BACKEND_NAME",
+]

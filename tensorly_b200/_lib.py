@@ -1,0 +1,120 @@
+"""ctypes binding of libtlb200.so — the C ABI declared in include/tlb200.h.
+
+There is no fallback: if the shared library is missing or fails to load, importing the
+compute entry points raises (the product path is CUDA-only).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libtlb200.so")
+
+TLB200_OK = 0
+TLB200_EINVAL = -1
+TLB200_EWORKSPACE = -2
+TLB200_ECUDA = -3
+TLB200_EUNSUPPORTED = -4
+
+F32, F64 = 0, 1
+PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
+PATHS = {"auto": PATH_AUTO, "simt": PATH_SIMT, "tcgen05": PATH_TCGEN05}
+MAX_NDIM = 8
+
+
+class MttkrpPlan(ctypes.Structure):
+    """Mirror of tlb200_mttkrp_plan_t."""
+
+    _fields_ = [
+        ("A", c_int64), ("J", c_int64), ("B", c_int64),
+        ("sa", c_int64), ("sj", c_int64), ("sb", c_int64),
+        ("p_first", c_int), ("p_count", c_int),
+        ("q_first", c_int), ("q_count", c_int),
+        ("rank_padded", c_int64), ("splits", c_int64),
+        ("path", c_int),
+    ]
+
+
+_I64P = POINTER(c_int64)
+_VPP = POINTER(c_void_p)
+_INTP = POINTER(c_int)
+
+# name -> (restype, argtypes); must list every symbol of include/tlb200.h
+SIGNATURES = {
+    "tlb200_version": (c_int, []),
+    "tlb200_build_arch": (c_char_p, []),
+    "tlb200_status_string": (c_char_p, [c_int]),
+    "tlb200_last_path": (c_char_p, []),
+    "tlb200_unfold": (c_int, [c_void_p, _I64P, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tlb200_fold": (c_int, [c_void_p, _I64P, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tlb200_khatri_rao": (c_int, [_VPP, _I64P, _I64P, _I64P, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p,
+                                  c_int64, c_void_p]),
+    "tlb200_mttkrp_workspace_bytes": (c_size_t, [_I64P, c_int, c_int, c_int64, c_int, c_int]),
+    "tlb200_mttkrp": (c_int, [c_void_p, _I64P, c_int, c_int, _VPP, _I64P, _I64P, c_int64, c_void_p, c_int, c_void_p,
+                              c_int64, c_void_p, c_size_t, c_int, c_void_p]),
+    "tlb200_mttkrp_plan": (c_int, [_I64P, c_int, c_int, c_int64, c_int, c_int, POINTER(MttkrpPlan)]),
+    "tlb200_mode_dot_workspace_bytes": (c_size_t, [_I64P, c_int, c_int, c_int64, c_int, c_int]),
+    "tlb200_mode_dot": (c_int, [c_void_p, _I64P, c_int, c_int, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p,
+                                c_void_p, c_size_t, c_int, c_void_p]),
+    "tlb200_multi_mode_dot_workspace_bytes": (c_size_t, [_I64P, c_int, _INTP, _I64P, c_int, c_int, c_int]),
+    "tlb200_multi_mode_dot": (c_int, [c_void_p, _I64P, c_int, _INTP, _VPP, _I64P, _I64P, _I64P, c_int, c_int, c_void_p,
+                                      c_void_p, c_size_t, c_int, c_void_p]),
+    "tlb200_gram_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "tlb200_gram": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tlb200_cp_update": (c_int, [_VPP, c_int, c_int, c_int64, c_void_p, c_double, c_void_p, c_int64, c_int64, c_int,
+                                 c_void_p, c_int64, c_void_p]),
+    "tlb200_cp_error": (c_int, [_VPP, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64,
+                                c_void_p, c_int, c_void_p, c_void_p]),
+    "tlb200_sumsq_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "tlb200_sumsq": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tlb200_nncp_update": (c_int, [_VPP, c_int, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
+                                   c_double, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load libtlb200.so (once). Raises RuntimeError if it is missing — never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"tensorly_b200: native library not found at {LIB_PATH}. Build it with "
+            "`python -m tensorly_b200.build` (needs nvcc); there is no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def i64_array(values):
+    values = list(values)
+    return (c_int64 * max(1, len(values)))(*values)
+
+
+def int_array(values):
+    values = list(values)
+    return (c_int * max(1, len(values)))(*values)
+
+
+def ptr_array(ptrs):
+    ptrs = list(ptrs)
+    return (c_void_p * max(1, len(ptrs)))(*[c_void_p(p) if p else c_void_p(None) for p in ptrs])
+
+
+def check(status: int, what: str) -> None:
+    """Map a tlb200 status to the exception the reference raises for the same misuse."""
+    if status == TLB200_OK:
+        return
+    msg = f"{what}: {load().tlb200_status_string(status).decode()} (status {status})"
+    if status == TLB200_EINVAL:
+        raise ValueError(msg)
+    raise RuntimeError(msg)

@@ -1,0 +1,494 @@
+"""Host-side mirror of the reference's tenalg interface for the hot path.
+
+Same names, argument meaning and error behaviour as
+  tensorly.base.unfold / fold                                  (tensorly/base.py:39-79)
+  tensorly.tenalg.core_tenalg.khatri_rao                       (_khatri_rao.py:9-109)
+  tensorly.tenalg.core_tenalg.unfolding_dot_khatri_rao         (mttkrp.py:9-50)
+  tensorly.tenalg.core_tenalg.mode_dot / multi_mode_dot        (n_mode_product.py:5-135)
+but every arithmetic step runs in the hand-written sm_100a kernels behind the C ABI of
+include/tlb200.h.  torch is used only for device memory and the current stream.
+Inputs are borrowed and never mutated; results are new tensors.
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Iterable, Sequence
+
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float32: _lib.F32, torch.float64: _lib.F64}
+
+# Kernel family used by MTTKRP / TTM: "auto" (tcgen05 when eligible, SIMT otherwise),
+# "simt" or "tcgen05".  Both are CUDA; there is no host fallback.
+_path = "auto"
+
+
+def set_kernel_path(path: str) -> None:
+    if path not in _lib.PATHS:
+        raise ValueError(f"unknown kernel path {path!r}; expected one of {sorted(_lib.PATHS)}")
+    global _path
+    _path = path
+
+
+def get_kernel_path() -> str:
+    return _path
+
+
+def last_kernel_path() -> str:
+    """Kernel family the last call on this thread dispatched to ("simt", "tcgen05", ...)."""
+    return _lib.load().tlb200_last_path().decode()
+
+
+# --------------------------------------------------------------------------- helpers
+def _check_tensor(t, name: str, ref: torch.Tensor | None = None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor on a CUDA device (got {type(t).__name__}); "
+                        "use tl.set_backend('pytorch') and CUDA tensors with the b200 tenalg backend")
+    if not t.is_cuda:
+        raise TypeError(f"{name} must live on a CUDA device (got {t.device}); the b200 backend has no CPU path")
+    if t.dtype not in _DTYPES:
+        raise TypeError(f"{name} has dtype {t.dtype}; the b200 backend supports float32 and float64")
+    if t.requires_grad:
+        raise TypeError(f"{name} requires grad; the b200 kernels are not differentiable")
+    if ref is not None:
+        if t.device != ref.device:
+            raise TypeError(f"{name} is on {t.device} but the tensor is on {ref.device}")
+        if t.dtype != ref.dtype:
+            raise TypeError(f"{name} has dtype {t.dtype} but the tensor has dtype {ref.dtype}")
+    return t
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+class _Device:
+    """Make the tensor's device current for the launch (no-op when it already is)."""
+
+    def __init__(self, t: torch.Tensor):
+        self.idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+
+
+def _workspace(nbytes: int, like: torch.Tensor) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=like.device)
+
+
+def _prod(xs: Iterable[int]) -> int:
+    p = 1
+    for x in xs:
+        p *= int(x)
+    return p
+
+
+# --------------------------------------------------------------------------- unfold / fold
+def unfold(tensor: torch.Tensor, mode: int, contiguous: bool = False) -> torch.Tensor:
+    """Mode-`mode` unfolding (tensorly/base.py:39-53), bit-exact.
+
+    Mode 0 is a free view of a contiguous tensor, exactly as in the reference; every other
+    mode is produced by the permuting-copy kernel as a C-contiguous matrix.
+    """
+    _check_tensor(tensor, "tensor")
+    ndim = tensor.dim()
+    if ndim < 1 or ndim > _lib.MAX_NDIM:
+        raise ValueError(f"unfold supports 1..{_lib.MAX_NDIM}-way tensors, got {ndim}")
+    if not -ndim <= mode < ndim:
+        raise ValueError(f"mode {mode} out of range for a {ndim}-way tensor")
+    mode %= ndim
+    x = tensor if tensor.is_contiguous() else tensor.contiguous()
+    rows = x.shape[mode]
+    if mode == 0 and not contiguous:
+        return x.reshape(rows, -1)
+    out = torch.empty((rows, x.numel() // max(rows, 1)), dtype=x.dtype, device=x.device)
+    if x.numel() == 0:
+        return out
+    lib = _lib.load()
+    with _Device(x):
+        st = lib.tlb200_unfold(x.data_ptr(), _lib.i64_array(x.shape), ndim, mode, _DTYPES[x.dtype], out.data_ptr(),
+                               _stream(x))
+    _lib.check(st, "unfold")
+    return out
+
+
+def fold(unfolded_tensor: torch.Tensor, mode: int, shape: Sequence[int]) -> torch.Tensor:
+    """Inverse of unfold (tensorly/base.py:56-79); returns a C-contiguous tensor."""
+    _check_tensor(unfolded_tensor, "unfolded_tensor")
+    shape = tuple(int(s) for s in shape)
+    ndim = len(shape)
+    if ndim < 1 or ndim > _lib.MAX_NDIM:
+        raise ValueError(f"fold supports 1..{_lib.MAX_NDIM}-way shapes, got {ndim}")
+    if not -ndim <= mode < ndim:
+        raise ValueError(f"mode {mode} out of range for shape {shape}")
+    mode %= ndim
+    if unfolded_tensor.dim() != 2 or unfolded_tensor.shape[0] != shape[mode] or unfolded_tensor.numel() != _prod(shape):
+        raise ValueError(f"cannot fold a matrix of shape {tuple(unfolded_tensor.shape)} into {shape} along mode {mode}")
+    u = unfolded_tensor if unfolded_tensor.is_contiguous() else unfolded_tensor.contiguous()
+    out = torch.empty(shape, dtype=u.dtype, device=u.device)
+    if u.numel() == 0:
+        return out
+    lib = _lib.load()
+    with _Device(u):
+        st = lib.tlb200_fold(u.data_ptr(), _lib.i64_array(shape), ndim, mode, _DTYPES[u.dtype], out.data_ptr(), _stream(u))
+    _lib.check(st, "fold")
+    return out
+
+
+# --------------------------------------------------------------------------- khatri_rao
+def khatri_rao(matrices, weights=None, skip_matrix=None, mask=None) -> torch.Tensor:
+    """Khatri-Rao product (tensorly/tenalg/core_tenalg/_khatri_rao.py:9-109), bit-exact:
+    first matrix slowest, left fold of multiplies, weights folded into the first matrix,
+    optional row mask.  One remaining matrix is returned as is (weights ignored), 1-D
+    inputs are treated as single columns with a warning, shape errors raise ValueError.
+    """
+    matrices = list(matrices)
+    if skip_matrix is not None:
+        matrices = [matrices[i] for i in range(len(matrices)) if i != skip_matrix]
+    if len(matrices) == 0:
+        raise ValueError("khatri_rao needs at least one matrix")
+    if len(matrices) == 1:
+        return matrices[0]
+    first = _check_tensor(matrices[0], "matrices[0]")
+    if first.dim() == 2:
+        n_columns = first.shape[1]
+    else:
+        n_columns = 1
+        matrices = [_check_tensor(m, f"matrices[{i}]", first).reshape(-1, 1) for i, m in enumerate(matrices)]
+        warnings.warn("Khatri-rao of a series of vectors instead of matrices. "
+                      "Considering each as a matrix with 1 column.")
+    for i, m in enumerate(matrices):
+        _check_tensor(m, f"matrices[{i}]", first)
+        if m.dim() != 2:
+            raise ValueError("All the matrices must have exactly 2 dimensions!"
+                             f"Matrix {i} has dimension {m.dim()} != 2.")
+        if m.shape[1] != n_columns:
+            raise ValueError("All matrices must have same number of columns!"
+                             f"Matrix {i} has {m.shape[1]} columns != {n_columns}.")
+    if len(matrices) > _lib.MAX_NDIM:
+        raise ValueError(f"khatri_rao supports at most {_lib.MAX_NDIM} matrices")
+    rows = [m.shape[0] for m in matrices]
+    total = _prod(rows)
+    w = None
+    if weights is not None:
+        w = torch.as_tensor(weights, dtype=first.dtype, device=first.device).reshape(-1).contiguous()
+        if w.numel() != n_columns:
+            raise ValueError(f"weights has {w.numel()} entries but the matrices have {n_columns} columns")
+    mk = None
+    if mask is not None:
+        mk = torch.as_tensor(mask, device=first.device).to(first.dtype).reshape(-1).contiguous()
+        if mk.numel() != total:
+            raise ValueError(f"mask has {mk.numel()} entries but the product has {total} rows")
+    out = torch.empty((total, n_columns), dtype=first.dtype, device=first.device)
+    if out.numel() == 0:
+        return out
+    lib = _lib.load()
+    with _Device(first):
+        st = lib.tlb200_khatri_rao(
+            _lib.ptr_array(m.data_ptr() for m in matrices), _lib.i64_array(rows),
+            _lib.i64_array(m.stride(0) for m in matrices), _lib.i64_array(m.stride(1) for m in matrices),
+            len(matrices), n_columns, w.data_ptr() if w is not None else None,
+            mk.data_ptr() if mk is not None else None, _DTYPES[first.dtype], out.data_ptr(), n_columns, _stream(first))
+    _lib.check(st, "khatri_rao")
+    return out
+
+
+# --------------------------------------------------------------------------- MTTKRP
+def mttkrp_plan(shape: Sequence[int], mode: int, rank: int, dtype=torch.float32, path: str | None = None):
+    """The (A, J, B) streaming plan the MTTKRP kernel would use (host-only, no GPU work)."""
+    lib = _lib.load()
+    plan = _lib.MttkrpPlan()
+    st = lib.tlb200_mttkrp_plan(_lib.i64_array(shape), len(shape), mode, rank, _DTYPES[dtype],
+                                _lib.PATHS[path or _path], plan)
+    _lib.check(st, "mttkrp_plan")
+    return plan
+
+
+def unfolding_dot_khatri_rao(tensor: torch.Tensor, cp_tensor, mode: int) -> torch.Tensor:
+    """MTTKRP: dot(unfold(tensor, mode), khatri_rao(factors, weights, skip_matrix=mode))
+    (tensorly/tenalg/core_tenalg/mttkrp.py:9-50) without materialising either operand.
+
+    `cp_tensor` is any 2-iterable `(weights | None, factors)`; factors may have arbitrary
+    strides.  Returns a new (tensor.shape[mode], rank) tensor.
+    """
+    _check_tensor(tensor, "tensor")
+    weights, factors = cp_tensor
+    factors = list(factors)
+    ndim = tensor.dim()
+    if ndim < 2 or ndim > _lib.MAX_NDIM:
+        raise ValueError(f"unfolding_dot_khatri_rao supports 2..{_lib.MAX_NDIM}-way tensors, got {ndim}")
+    if len(factors) != ndim:
+        raise ValueError(f"got {len(factors)} factors for a {ndim}-way tensor")
+    if not -ndim <= mode < ndim:
+        raise ValueError(f"mode {mode} out of range for a {ndim}-way tensor")
+    mode %= ndim
+    rank = None
+    for i, f in enumerate(factors):
+        if i == mode:
+            continue
+        _check_tensor(f, f"factors[{i}]", tensor)
+        if f.dim() != 2:
+            raise ValueError(f"factors[{i}] must be a matrix, got {f.dim()} dimensions")
+        if f.shape[0] != tensor.shape[i]:
+            raise ValueError(f"factors[{i}] has {f.shape[0]} rows but the tensor has extent {tensor.shape[i]} in mode {i}")
+        if rank is None:
+            rank = f.shape[1]
+        elif f.shape[1] != rank:
+            raise ValueError("All matrices must have same number of columns!"
+                             f"Matrix {i} has {f.shape[1]} columns != {rank}.")
+    if rank is None or rank < 1:
+        raise ValueError("rank must be >= 1")
+    w = None
+    if weights is not None:
+        w = torch.as_tensor(weights, dtype=tensor.dtype, device=tensor.device).reshape(-1).contiguous()
+        if w.numel() != rank:
+            raise ValueError(f"weights has {w.numel()} entries but the factors have {rank} columns")
+    x = tensor if tensor.is_contiguous() else tensor.contiguous()
+    out = torch.empty((x.shape[mode], rank), dtype=x.dtype, device=x.device)
+    if x.numel() == 0:
+        return out.zero_()
+    lib = _lib.load()
+    dt = _DTYPES[x.dtype]
+    path = _lib.PATHS[_path]
+    shape = _lib.i64_array(x.shape)
+    nbytes = lib.tlb200_mttkrp_workspace_bytes(shape, ndim, mode, rank, dt, path)
+    if nbytes == 0:
+        raise ValueError(f"unfolding_dot_khatri_rao: unsupported problem shape={tuple(x.shape)} mode={mode} rank={rank}")
+    ws = _workspace(nbytes, x)
+    ptrs = [0 if i == mode else f.data_ptr() for i, f in enumerate(factors)]
+    rs = [0 if i == mode else f.stride(0) for i, f in enumerate(factors)]
+    cs = [0 if i == mode else f.stride(1) for i, f in enumerate(factors)]
+    with _Device(x):
+        st = lib.tlb200_mttkrp(x.data_ptr(), shape, ndim, mode, _lib.ptr_array(ptrs), _lib.i64_array(rs),
+                               _lib.i64_array(cs), rank, w.data_ptr() if w is not None else None, dt, out.data_ptr(),
+                               rank, ws.data_ptr(), ws.numel(), path, _stream(x))
+    _lib.check(st, "unfolding_dot_khatri_rao")
+    return out
+
+
+# --------------------------------------------------------------------------- TTM
+def mode_dot(tensor: torch.Tensor, matrix_or_vector: torch.Tensor, mode: int, transpose: bool = False) -> torch.Tensor:
+    """n-mode product with a matrix or a vector (n_mode_product.py:5-76).
+
+    matrix: (J, I_mode) [or (I_mode, J) with transpose=True] -> mode extent becomes J;
+    vector: (I_mode,) -> the mode is dropped.  ValueError on extent mismatch.
+    """
+    _check_tensor(tensor, "tensor")
+    _check_tensor(matrix_or_vector, "matrix_or_vector", tensor)
+    ndim = tensor.dim()
+    if ndim < 1 or ndim > _lib.MAX_NDIM:
+        raise ValueError(f"mode_dot supports 1..{_lib.MAX_NDIM}-way tensors, got {ndim}")
+    if not -ndim <= mode < ndim:
+        raise ValueError(f"mode {mode} out of range for a {ndim}-way tensor")
+    mode %= ndim
+    m = matrix_or_vector
+    new_shape = list(tensor.shape)
+    if m.dim() == 2:
+        dim = 0 if transpose else 1
+        if m.shape[dim] != tensor.shape[mode]:
+            raise ValueError(
+                f"shapes {tuple(tensor.shape)} and {tuple(m.shape)} not aligned in mode-{mode} multiplication: "
+                f"{tensor.shape[mode]} (mode {mode}) != {m.shape[dim]} (dim 1 of matrix)")
+        rows_out = m.shape[0 if not transpose else 1]
+        rs, cs = (m.stride(0), m.stride(1)) if not transpose else (m.stride(1), m.stride(0))
+        new_shape[mode] = rows_out
+        final_shape = tuple(new_shape)
+    elif m.dim() == 1:
+        if m.shape[0] != tensor.shape[mode]:
+            raise ValueError(
+                f"shapes {tuple(tensor.shape)} and {tuple(m.shape)} not aligned for mode-{mode} multiplication: "
+                f"{tensor.shape[mode]} (mode {mode}) != {m.shape[0]} (vector size)")
+        rows_out, rs, cs = 1, 0, m.stride(0)
+        new_shape[mode] = 1
+        final_shape = tuple(s for i, s in enumerate(tensor.shape) if i != mode) if ndim > 1 else ()
+    else:
+        raise ValueError("Can only take n_mode_product with a vector or a matrix."
+                         f"Provided array of dimension {m.dim()} not in [1, 2].")
+    x = tensor if tensor.is_contiguous() else tensor.contiguous()
+    out = torch.empty(tuple(new_shape), dtype=x.dtype, device=x.device)
+    if out.numel() == 0:
+        return out.reshape(final_shape)
+    if x.numel() == 0:
+        return out.zero_().reshape(final_shape)
+    lib = _lib.load()
+    with _Device(x):
+        st = lib.tlb200_mode_dot(x.data_ptr(), _lib.i64_array(x.shape), ndim, mode, m.data_ptr(), rows_out, rs, cs,
+                                 _DTYPES[x.dtype], out.data_ptr(), None, 0, _lib.PATHS[_path], _stream(x))
+    _lib.check(st, "mode_dot")
+    return out.reshape(final_shape)
+
+
+def multi_mode_dot(tensor: torch.Tensor, matrix_or_vec_list, modes=None, skip=None, transpose: bool = False) -> torch.Tensor:
+    """Chain of n-mode products (n_mode_product.py:79-135): pairs sorted by mode, `skip`
+    indexes the sorted list, vectors drop their mode.  Distinct modes run as one fused
+    C-ABI call (intermediates stay in a workspace); repeated modes fall back to
+    successive mode_dot calls.
+    """
+    _check_tensor(tensor, "tensor")
+    matrix_or_vec_list = list(matrix_or_vec_list)
+    if modes is None:
+        modes = range(len(matrix_or_vec_list))
+    modes = [int(m) for m in modes]
+    pairs = sorted(zip(matrix_or_vec_list, modes), key=lambda p: p[1])
+    pairs = [p for i, p in enumerate(pairs) if not (skip is not None and i == skip)]
+    ndim = tensor.dim()
+    used = [m for _, m in pairs]
+    if len(set(used)) != len(used) or any(not 0 <= m < ndim for m in used):
+        res, decrement = tensor, 0
+        for mat, mode in pairs:
+            res = mode_dot(res, mat, mode - decrement, transpose=transpose)
+            if mat.dim() == 1:
+                decrement += 1
+        return res
+    if not pairs:
+        return tensor.clone()
+    if len(pairs) == 1:
+        return mode_dot(tensor, pairs[0][0], pairs[0][1], transpose=transpose)
+    rows_out, rss, css, ptrs = [], [], [], []
+    new_shape = list(tensor.shape)
+    drop = []
+    for mat, mode in pairs:
+        _check_tensor(mat, "matrix_or_vec_list entry", tensor)
+        if mat.dim() == 2:
+            dim = 0 if transpose else 1
+            if mat.shape[dim] != tensor.shape[mode]:
+                raise ValueError(
+                    f"shapes {tuple(tensor.shape)} and {tuple(mat.shape)} not aligned in mode-{mode} multiplication: "
+                    f"{tensor.shape[mode]} (mode {mode}) != {mat.shape[dim]} (dim 1 of matrix)")
+            r = mat.shape[1 if transpose else 0]
+            rs, cs = (mat.stride(1), mat.stride(0)) if transpose else (mat.stride(0), mat.stride(1))
+        elif mat.dim() == 1:
+            if mat.shape[0] != tensor.shape[mode]:
+                raise ValueError(
+                    f"shapes {tuple(tensor.shape)} and {tuple(mat.shape)} not aligned for mode-{mode} multiplication: "
+                    f"{tensor.shape[mode]} (mode {mode}) != {mat.shape[0]} (vector size)")
+            r, rs, cs = 1, 0, mat.stride(0)
+            drop.append(mode)
+        else:
+            raise ValueError("Can only take n_mode_product with a vector or a matrix."
+                             f"Provided array of dimension {mat.dim()} not in [1, 2].")
+        rows_out.append(r); rss.append(rs); css.append(cs); ptrs.append(mat.data_ptr())
+        new_shape[mode] = r
+    final_shape = tuple(s for i, s in enumerate(new_shape) if i not in drop)
+    x = tensor if tensor.is_contiguous() else tensor.contiguous()
+    out = torch.empty(tuple(new_shape), dtype=x.dtype, device=x.device)
+    if out.numel() == 0 or x.numel() == 0:
+        return out.zero_().reshape(final_shape)
+    lib = _lib.load()
+    dt = _DTYPES[x.dtype]
+    path = _lib.PATHS[_path]
+    shape = _lib.i64_array(x.shape)
+    cmodes = _lib.int_array(used)
+    crows = _lib.i64_array(rows_out)
+    nbytes = lib.tlb200_multi_mode_dot_workspace_bytes(shape, ndim, cmodes, crows, len(pairs), dt, path)
+    ws = _workspace(nbytes, x)
+    with _Device(x):
+        st = lib.tlb200_multi_mode_dot(x.data_ptr(), shape, ndim, cmodes, _lib.ptr_array(ptrs), crows,
+                                       _lib.i64_array(rss), _lib.i64_array(css), len(pairs), dt, out.data_ptr(),
+                                       ws.data_ptr(), ws.numel(), path, _stream(x))
+    _lib.check(st, "multi_mode_dot")
+    return out.reshape(final_shape)
+
+
+# --------------------------------------------------------------------------- CP-ALS pieces
+def sumsq(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """||x||^2 as a device scalar of x.dtype (double accumulation, deterministic)."""
+    _check_tensor(x, "x")
+    xc = x if x.is_contiguous() else x.contiguous()
+    if out is None:
+        out = torch.empty(1, dtype=x.dtype, device=x.device)
+    lib = _lib.load()
+    dt = _DTYPES[x.dtype]
+    ws = _workspace(lib.tlb200_sumsq_workspace_bytes(xc.numel(), dt), x)
+    with _Device(x):
+        st = lib.tlb200_sumsq(xc.data_ptr(), xc.numel(), dt, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(x))
+    _lib.check(st, "sumsq")
+    return out
+
+
+def gram(f: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """F^T F (rank x rank), deterministic."""
+    _check_tensor(f, "f")
+    if f.dim() != 2:
+        raise ValueError("gram expects a matrix")
+    rows, rank = f.shape
+    if out is None:
+        out = torch.empty((rank, rank), dtype=f.dtype, device=f.device)
+    lib = _lib.load()
+    dt = _DTYPES[f.dtype]
+    ws = _workspace(lib.tlb200_gram_workspace_bytes(rows, rank, dt), f)
+    with _Device(f):
+        st = lib.tlb200_gram(f.data_ptr(), rows, rank, f.stride(0), f.stride(1), dt, out.data_ptr(), ws.data_ptr(),
+                             ws.numel(), _stream(f))
+    _lib.check(st, "gram")
+    return out
+
+
+def _gram_ptrs(grams, skip):
+    return _lib.ptr_array(0 if (g is None or i == skip) else g.data_ptr() for i, g in enumerate(grams))
+
+
+def cp_update(grams, mode: int, weights, mttkrp: torch.Tensor, l2_reg: float = 0.0,
+              out: torch.Tensor | None = None) -> torch.Tensor:
+    """ALS factor update: solve(V^T, M^T)^T with V = (w w^T) o prod_{i != mode} G_i + l2 I
+    (tensorly/decomposition/_cp.py:411-428)."""
+    _check_tensor(mttkrp, "mttkrp")
+    rows, rank = mttkrp.shape
+    if mttkrp.stride(1) != 1:
+        mttkrp = mttkrp.contiguous()
+    if out is None:
+        out = torch.empty((rows, rank), dtype=mttkrp.dtype, device=mttkrp.device)
+    lib = _lib.load()
+    with _Device(mttkrp):
+        st = lib.tlb200_cp_update(_gram_ptrs(grams, mode), len(grams), mode, rank,
+                                  weights.data_ptr() if weights is not None else None, float(l2_reg or 0.0),
+                                  mttkrp.data_ptr(), mttkrp.stride(0), rows, _DTYPES[mttkrp.dtype], out.data_ptr(),
+                                  out.stride(0), _stream(mttkrp))
+    _lib.check(st, "cp_update")
+    return out
+
+
+def nncp_update(grams, mode: int, weights, mttkrp: torch.Tensor, factor: torch.Tensor, eps: float) -> torch.Tensor:
+    """In-place multiplicative update of `factor` (tensorly/decomposition/_nn_cp.py:131-136)."""
+    _check_tensor(mttkrp, "mttkrp")
+    _check_tensor(factor, "factor", mttkrp)
+    rows, rank = factor.shape
+    if factor.stride(1) != 1 or mttkrp.stride(1) != 1:
+        raise ValueError("nncp_update needs row-major factor and mttkrp")
+    lib = _lib.load()
+    with _Device(factor):
+        st = lib.tlb200_nncp_update(_gram_ptrs(grams, mode), len(grams), mode, rank,
+                                    weights.data_ptr() if weights is not None else None, mttkrp.data_ptr(),
+                                    mttkrp.stride(0), factor.data_ptr(), factor.stride(0), rows, float(eps),
+                                    _DTYPES[factor.dtype], _stream(factor))
+    _lib.check(st, "nncp_update")
+    return factor
+
+
+def cp_error(grams, weights, mttkrp_last: torch.Tensor, factor_last: torch.Tensor, norm_x2: torch.Tensor,
+             out: torch.Tensor | None = None) -> torch.Tensor:
+    """Relative reconstruction error from the last mode's MTTKRP (_cp.py:217-225):
+    out = [rel_error, iprod, ||cp||^2] as device scalars (no host sync)."""
+    _check_tensor(mttkrp_last, "mttkrp_last")
+    rows, rank = mttkrp_last.shape
+    if out is None:
+        out = torch.empty(3, dtype=mttkrp_last.dtype, device=mttkrp_last.device)
+    lib = _lib.load()
+    with _Device(mttkrp_last):
+        st = lib.tlb200_cp_error(_gram_ptrs(grams, -1), len(grams), rank,
+                                 weights.data_ptr() if weights is not None else None, mttkrp_last.data_ptr(),
+                                 mttkrp_last.stride(0), factor_last.data_ptr(), factor_last.stride(0),
+                                 factor_last.stride(1), rows, norm_x2.data_ptr(), _DTYPES[mttkrp_last.dtype],
+                                 out.data_ptr(), _stream(mttkrp_last))
+    _lib.check(st, "cp_error")
+    return out

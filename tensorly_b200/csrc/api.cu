@@ -1,0 +1,21 @@
+// Library introspection entry points.
+#include "common.cuh"
+
+namespace tlb200 {
+static thread_local const char* g_last_path = "none";
+void set_last_path(const char* name) { g_last_path = name; }
+}  // namespace tlb200
+
+extern "C" int tlb200_version(void) { return 100; }  // 0.1.0
+extern "C" const char* tlb200_build_arch(void) { return "sm_100a"; }
+extern "C" const char* tlb200_last_path(void) { return tlb200::g_last_path; }
+extern "C" const char* tlb200_status_string(int status) {
+    switch (status) {
+        case TLB200_OK: return "ok";
+        case TLB200_EINVAL: return "invalid argument (shape / mode / rank / dtype / pointer)";
+        case TLB200_EWORKSPACE: return "workspace too small";
+        case TLB200_ECUDA: return "CUDA runtime error";
+        case TLB200_EUNSUPPORTED: return "unsupported configuration";
+        default: return "unknown status";
+    }
+}

@@ -1,0 +1,57 @@
+// Shared helpers for the tlb200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/tlb200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ != 1000)
+#error "tlb200 kernels are written for sm_100a (B200) only"
+#endif
+
+namespace tlb200 {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// Name of the kernel family the last API call on this thread dispatched to.
+void set_last_path(const char* name);
+
+inline int cuda_ok(cudaError_t e) { return e == cudaSuccess ? TLB200_OK : TLB200_ECUDA; }
+
+#define TLB_CHECK_LAUNCH()                                  \
+    do {                                                    \
+        cudaError_t e__ = cudaGetLastError();               \
+        if (e__ != cudaSuccess) return TLB200_ECUDA;        \
+    } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline size_t dtype_size(int dtype) { return dtype == TLB200_F64 ? 8 : 4; }
+inline bool dtype_valid(int dtype) { return dtype == TLB200_F32 || dtype == TLB200_F64; }
+
+// Carve sub-buffers out of a caller-provided workspace.
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+    template <typename T>
+    T* take(size_t count) {
+        off = align_up(off, 256);
+        T* r = reinterpret_cast<T*>(base + off);
+        off += count * sizeof(T);
+        return r;
+    }
+    size_t used() const { return align_up(off, 256); }
+};
+
+// ---- internal launchers shared between translation units ------------------
+// Khatri-Rao of `nmats` matrices into out[(rows), ld]; columns [rank, pad_cols) are
+// written as zero.  Unlike the public entry point, weights are applied even for a
+// single matrix.
+template <typename T>
+int launch_khatri_rao(const T* const* mats, const int64_t* rows, const int64_t* row_stride,
+                      const int64_t* col_stride, int nmats, int64_t rank, const T* weights,
+                      const T* mask, T* out, int64_t out_ld, int64_t pad_cols,
+                      cudaStream_t stream);
+
+}  // namespace tlb200

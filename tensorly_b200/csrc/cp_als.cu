@@ -1,0 +1,520 @@
+// CP-ALS normal-equation kernels: Gram, Gram-Hadamard + LU solve, multiplicative update,
+// fast reconstruction error, sum of squares.
+//
+// Reference (caller side of the hot path): tensorly/decomposition/_cp.py:411-428 (V and
+// solve), :217-225 + tensorly/cp_tensor.py:614-644 (error), _nn_cp.py:114-136 (MU),
+// _cp.py:350 (tl.norm).  In the reference these are ~25 tiny array-library calls per mode
+// (and a host sync inside `solve`); here each is one launch, never synchronising, so a
+// whole sweep can sit in a CUDA graph.  All of it is latency-bound R x R work.
+#include "common.cuh"
+
+namespace tlb200 {
+namespace {
+
+constexpr int kMaxRank = 128;
+
+template <typename T>
+struct GramList {
+    const T* g[TLB200_MAX_NDIM];
+    int n;
+};
+
+// V[r][s] = w_r * (prod_{i != mode} G_i[r][s] + l2 * delta_rs) * w_s, evaluated in the
+// reference's order: ones * G_a * G_b ..., += Id, then (w[:,None] * V) * w[None,:].
+template <typename T>
+__device__ __forceinline__ T form_v(const GramList<T>& gl, int mode, int64_t R, const T* __restrict__ w, T l2,
+                                    int r, int s) {
+    T v = T(1);
+    for (int i = 0; i < gl.n; ++i)
+        if (i != mode) v = v * gl.g[i][(int64_t)r * R + s];
+    if (r == s) v += l2;
+    if (w) v = (w[r] * v) * w[s];
+    return v;
+}
+
+// ---- Gram: partial sums over row blocks, then an ordered reduction -----------------
+constexpr int kGramRows = 128;  // rows per CTA
+
+template <typename T, int RB>  // RB = ceil(R / 16)
+__global__ void __launch_bounds__(256)
+gram_partial_kernel(const T* __restrict__ f, int64_t rows, int R, int64_t rs, int64_t cs, T* __restrict__ partial) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* Fs = reinterpret_cast<T*>(smem_raw);   // [32][R + 1]
+    const int ld = R + 1;
+    const int tid = threadIdx.x, tr = tid >> 4, ts = tid & 15;
+    const int64_t row0 = (int64_t)blockIdx.x * kGramRows;
+    T acc[RB][RB];
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+#pragma unroll
+        for (int j = 0; j < RB; ++j) acc[i][j] = T(0);
+    for (int base = 0; base < kGramRows; base += 32) {
+        __syncthreads();
+        for (int e = tid; e < 32 * R; e += 256) {
+            // pick the lane-fastest index along the contiguous dim of F
+            int rr, c;
+            if (cs <= rs) { rr = e / R; c = e - rr * R; } else { c = e / 32; rr = e - c * 32; }
+            const int64_t gr = row0 + base + rr;
+            Fs[rr * ld + c] = gr < rows ? f[gr * rs + c * cs] : T(0);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) {
+            T a[RB], b[RB];
+#pragma unroll
+            for (int i = 0; i < RB; ++i) {
+                a[i] = (tr + 16 * i) < R ? Fs[k * ld + tr + 16 * i] : T(0);
+                b[i] = (ts + 16 * i) < R ? Fs[k * ld + ts + 16 * i] : T(0);
+            }
+#pragma unroll
+            for (int i = 0; i < RB; ++i)
+#pragma unroll
+                for (int j = 0; j < RB; ++j) acc[i][j] += a[i] * b[j];
+        }
+    }
+    T* out = partial + (int64_t)blockIdx.x * R * R;
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+            const int r = tr + 16 * i, s = ts + 16 * j;
+            if (r < R && s < R) out[r * R + s] = acc[i][j];
+        }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gram_reduce_kernel(const T* __restrict__ partial, int nblk, int RR, T* __restrict__ gram) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < RR; e += gridDim.x * blockDim.x) {
+        T s = T(0);
+        for (int b = 0; b < nblk; ++b) s += partial[(int64_t)b * RR + e];
+        gram[e] = s;
+    }
+}
+
+// ---- CP update: V, LU with partial pivoting, solve for a block of rows ---------------
+constexpr int kSolveRows = 64;   // rows of M per CTA
+constexpr int kSolveThreads = 256;
+
+// A = V^T in shared memory (ld = R + 1); perm[] row permutation.  All threads of the CTA.
+template <typename T>
+__device__ void lu_factor_smem(T* A, int* perm, int R, int ld, int* s_piv) {
+    const int tid = threadIdx.x;
+    for (int k = 0; k < R; ++k) {
+        // pivot search by warp 0
+        if (tid < 32) {
+            T best = T(-1);
+            int bi = k;
+            for (int i = k + tid; i < R; i += 32) {
+                T v = A[i * ld + k];
+                v = v < T(0) ? -v : v;
+                if (v > best) { best = v; bi = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                T ob = __shfl_xor_sync(0xffffffffu, best, o);
+                int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if (tid == 0) *s_piv = bi;
+        }
+        __syncthreads();
+        const int piv = *s_piv;
+        if (piv != k) {
+            for (int c = tid; c < R; c += blockDim.x) {
+                T t = A[k * ld + c]; A[k * ld + c] = A[piv * ld + c]; A[piv * ld + c] = t;
+            }
+            if (tid == 0) { int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t; }
+        }
+        __syncthreads();
+        const T pivot = A[k * ld + k];
+        const T inv = T(1) / pivot;
+        // multipliers
+        for (int i = k + 1 + tid; i < R; i += blockDim.x) A[i * ld + k] *= inv;
+        __syncthreads();
+        // trailing update
+        const int n = R - k - 1;
+        for (int e = tid; e < n * n; e += blockDim.x) {
+            const int i = k + 1 + e / n, j = k + 1 + e % n;
+            A[i * ld + j] -= A[i * ld + k] * A[k * ld + j];
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kSolveThreads)
+cp_update_kernel(GramList<T> gl, int mode, int R, const T* __restrict__ w, T l2, const T* __restrict__ m, int64_t m_ld,
+                 int64_t rows, T* __restrict__ out, int64_t out_ld) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ld = R + 1;
+    T* A = reinterpret_cast<T*>(smem_raw);            // [R][ld]   = V^T, then its LU factors
+    T* Y = A + R * ld;                                // [kSolveRows][ld] right-hand sides / solutions
+    int* perm = reinterpret_cast<int*>(Y + kSolveRows * ld);
+    int* s_piv = perm + R;
+    const int tid = threadIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * kSolveRows;
+
+    for (int e = tid; e < R * R; e += blockDim.x) {
+        const int r = e / R, s = e - r * R;
+        A[s * ld + r] = form_v<T>(gl, mode, R, w, l2, r, s);   // store V^T
+    }
+    for (int i = tid; i < R; i += blockDim.x) perm[i] = i;
+    __syncthreads();
+    lu_factor_smem<T>(A, perm, R, ld, s_piv);
+
+    // load permuted right-hand sides: Y[row][i] = M[row][perm[i]]
+    for (int e = tid; e < kSolveRows * R; e += blockDim.x) {
+        const int rr = e / R, c = e - rr * R;
+        const int64_t gr = row0 + rr;
+        Y[rr * ld + c] = gr < rows ? m[gr * m_ld + perm[c]] : T(0);
+    }
+    __syncthreads();
+    // 4 threads per row: thread q of a row owns the partial dot products of columns
+    // j = q, q+4, ... ; the running solution lives in shared memory.
+    const int rr = tid >> 2, q = tid & 3;
+    T* y = Y + rr * ld;
+    // forward substitution, unit lower triangular
+    for (int i = 1; i < R; ++i) {
+        T s = T(0);
+        for (int j = q; j < i; j += 4) s += A[i * ld + j] * y[j];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (q == 0) y[i] -= s;
+        __syncwarp();
+    }
+    // back substitution
+    for (int i = R - 1; i >= 0; --i) {
+        T s = T(0);
+        for (int j = i + 1 + q; j < R; j += 4) s += A[i * ld + j] * y[j];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (q == 0) y[i] = (y[i] - s) / A[i * ld + i];
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int e = tid; e < kSolveRows * R; e += blockDim.x) {
+        const int r2 = e / R, c = e - r2 * R;
+        const int64_t gr = row0 + r2;
+        if (gr < rows) out[gr * out_ld + c] = Y[r2 * ld + c];
+    }
+}
+
+// ---- NN-CP multiplicative update -------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+nncp_update_kernel(GramList<T> gl, int mode, int R, const T* __restrict__ w, const T* __restrict__ m, int64_t m_ld,
+                   T* __restrict__ f, int64_t f_ld, int64_t rows, T eps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ld = R + 1;
+    T* V = reinterpret_cast<T*>(smem_raw);  // [R][ld]
+    T* Fs = V + R * ld;                     // [32][ld]
+    const int tid = threadIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * 32;
+    for (int e = tid; e < R * R; e += 256) {
+        const int r = e / R, s = e - r * R;
+        V[r * ld + s] = form_v<T>(gl, mode, R, w, T(0), r, s);
+    }
+    for (int e = tid; e < 32 * R; e += 256) {
+        const int rr = e / R, c = e - rr * R;
+        const int64_t gr = row0 + rr;
+        Fs[rr * ld + c] = gr < rows ? f[gr * f_ld + c] : T(0);
+    }
+    __syncthreads();
+    const int rr = tid >> 3, cg = tid & 7;
+    const int64_t gr = row0 + rr;
+    if (gr >= rows) return;
+    for (int c = cg; c < R; c += 8) {
+        T den = T(0);
+        for (int s = 0; s < R; ++s) den += Fs[rr * ld + s] * V[s * ld + c];
+        T num = m[gr * m_ld + c];
+        num = num < eps ? eps : num;
+        den = den < eps ? eps : den;
+        f[gr * f_ld + c] = Fs[rr * ld + c] * num / den;
+    }
+}
+
+// ---- error ----------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024)
+cp_error_kernel(GramList<T> gl, int R, const T* __restrict__ w, const T* __restrict__ m, int64_t m_ld,
+                const T* __restrict__ f, int64_t frs, int64_t fcs, int64_t rows, const T* __restrict__ norm_x2,
+                T* __restrict__ err_out) {
+    __shared__ double red[2][32];
+    const int tid = threadIdx.x;
+    double iprod = 0.0, ncp = 0.0;
+    const int64_t total = rows * R;
+    for (int64_t e = tid; e < total; e += blockDim.x) {
+        const int64_t i = e / R, r = e - i * R;
+        iprod += (double)m[i * m_ld + r] * (double)f[i * frs + r * fcs];
+    }
+    for (int e = tid; e < R * R; e += blockDim.x) {
+        const int r = e / R, s = e - r * R;
+        T v = T(1);
+        for (int i = 0; i < gl.n; ++i) v = v * gl.g[i][(int64_t)r * R + s];
+        if (w) v = v * (w[r] * w[s]);
+        ncp += (double)v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        iprod += __shfl_xor_sync(0xffffffffu, iprod, o);
+        ncp += __shfl_xor_sync(0xffffffffu, ncp, o);
+    }
+    if ((tid & 31) == 0) { red[0][tid >> 5] = iprod; red[1][tid >> 5] = ncp; }
+    __syncthreads();
+    if (tid < 32) {
+        iprod = tid < (int)(blockDim.x >> 5) ? red[0][tid] : 0.0;
+        ncp = tid < (int)(blockDim.x >> 5) ? red[1][tid] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            iprod += __shfl_xor_sync(0xffffffffu, iprod, o);
+            ncp += __shfl_xor_sync(0xffffffffu, ncp, o);
+        }
+        if (tid == 0) {
+            const double nx2 = (double)norm_x2[0];
+            double d = nx2 + ncp - 2.0 * iprod;
+            d = d < 0 ? -d : d;
+            err_out[0] = (T)(sqrt(d) / sqrt(nx2));
+            err_out[1] = (T)iprod;
+            err_out[2] = (T)ncp;
+        }
+    }
+}
+
+// ---- sum of squares ---------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+sumsq_partial_kernel(const T* __restrict__ x, int64_t n, double* __restrict__ partial) {
+    __shared__ double red[8];
+    double s = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double v = (double)__ldg(x + i);
+        s += v * v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        partial[blockIdx.x] = t;
+    }
+}
+
+// float4 variant for aligned fp32 arrays (the 4 GB tensor of config 2)
+__global__ void __launch_bounds__(256)
+sumsq_partial_f4_kernel(const float4* __restrict__ x, int64_t n4, double* __restrict__ partial) {
+    __shared__ double red[8];
+    double s = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = __ldg(x + i);
+        s += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        partial[blockIdx.x] = t;
+    }
+}
+
+template <typename T>
+__global__ void sumsq_final_kernel(const double* __restrict__ partial, int n, const T* __restrict__ tail, int ntail,
+                                   T* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < n; ++i) t += partial[i];
+        for (int i = 0; i < ntail; ++i) t += (double)tail[i] * (double)tail[i];
+        out[0] = (T)t;
+    }
+}
+
+constexpr int kSumsqBlocks = kNumSMs * 8;
+
+template <typename T>
+int gram_launch(const T* f, int64_t rows, int64_t R, int64_t rs, int64_t cs, T* gram, void* workspace,
+                cudaStream_t stream) {
+    const int nblk = (int)ceil_div(rows, kGramRows);
+    T* partial = reinterpret_cast<T*>(workspace);
+    const size_t smem = sizeof(T) * 32 * (R + 1);
+    const int RB = (int)ceil_div(R, 16);
+    if (RB <= 1) gram_partial_kernel<T, 1><<<nblk, 256, smem, stream>>>(f, rows, (int)R, rs, cs, partial);
+    else if (RB <= 2) gram_partial_kernel<T, 2><<<nblk, 256, smem, stream>>>(f, rows, (int)R, rs, cs, partial);
+    else if (RB <= 4) gram_partial_kernel<T, 4><<<nblk, 256, smem, stream>>>(f, rows, (int)R, rs, cs, partial);
+    else gram_partial_kernel<T, 8><<<nblk, 256, smem, stream>>>(f, rows, (int)R, rs, cs, partial);
+    TLB_CHECK_LAUNCH();
+    const int RR = (int)(R * R);
+    gram_reduce_kernel<T><<<(RR + 255) / 256, 256, 0, stream>>>(partial, nblk, RR, gram);
+    TLB_CHECK_LAUNCH();
+    return TLB200_OK;
+}
+
+template <typename T>
+int fill_grams(GramList<T>* gl, const void* const* grams, int nmodes, int skip) {
+    if (!grams || nmodes < 1 || nmodes > TLB200_MAX_NDIM) return TLB200_EINVAL;
+    gl->n = nmodes;
+    for (int i = 0; i < TLB200_MAX_NDIM; ++i) gl->g[i] = nullptr;
+    for (int i = 0; i < nmodes; ++i) {
+        if (i != skip && !grams[i]) return TLB200_EINVAL;
+        gl->g[i] = static_cast<const T*>(grams[i]);
+    }
+    return TLB200_OK;
+}
+
+template <typename T>
+int cp_update_launch(const void* const* grams, int nmodes, int mode, int64_t R, const T* w, double l2, const T* m,
+                     int64_t m_ld, int64_t rows, T* out, int64_t out_ld, cudaStream_t stream) {
+    GramList<T> gl;
+    int st = fill_grams<T>(&gl, grams, nmodes, mode);
+    if (st) return st;
+    const int ld = (int)R + 1;
+    const size_t smem = sizeof(T) * ((size_t)R * ld + (size_t)kSolveRows * ld) + sizeof(int) * (R + 1);
+    static bool attr_set[2] = {false, false};
+    const int ti = sizeof(T) == 8;
+    if (!attr_set[ti]) {
+        if (cudaFuncSetAttribute(cp_update_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+            return TLB200_ECUDA;
+        attr_set[ti] = true;
+    }
+    if (smem > 200 * 1024) return TLB200_EUNSUPPORTED;
+    const int nblk = (int)ceil_div(rows, kSolveRows);
+    if (nblk == 0) return TLB200_OK;
+    cp_update_kernel<T><<<nblk, kSolveThreads, smem, stream>>>(gl, mode, (int)R, w, (T)l2, m, m_ld, rows, out, out_ld);
+    TLB_CHECK_LAUNCH();
+    return TLB200_OK;
+}
+
+template <typename T>
+int nncp_update_launch(const void* const* grams, int nmodes, int mode, int64_t R, const T* w, const T* m, int64_t m_ld,
+                       T* f, int64_t f_ld, int64_t rows, double eps, cudaStream_t stream) {
+    GramList<T> gl;
+    int st = fill_grams<T>(&gl, grams, nmodes, mode);
+    if (st) return st;
+    const int ld = (int)R + 1;
+    const size_t smem = sizeof(T) * ((size_t)R * ld + 32 * (size_t)ld);
+    static bool attr_set[2] = {false, false};
+    const int ti = sizeof(T) == 8;
+    if (!attr_set[ti]) {
+        if (cudaFuncSetAttribute(nncp_update_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+            return TLB200_ECUDA;
+        attr_set[ti] = true;
+    }
+    const int nblk = (int)ceil_div(rows, 32);
+    if (nblk == 0) return TLB200_OK;
+    nncp_update_kernel<T><<<nblk, 256, smem, stream>>>(gl, mode, (int)R, w, m, m_ld, f, f_ld, rows, (T)eps);
+    TLB_CHECK_LAUNCH();
+    return TLB200_OK;
+}
+
+}  // namespace
+}  // namespace tlb200
+
+using namespace tlb200;
+
+extern "C" size_t tlb200_gram_workspace_bytes(int64_t rows, int64_t rank, int dtype) {
+    if (rows < 0 || rank < 1 || !dtype_valid(dtype)) return 0;
+    return align_up((size_t)ceil_div(rows > 0 ? rows : 1, kGramRows) * rank * rank * dtype_size(dtype), 256);
+}
+
+extern "C" int tlb200_gram(const void* f, int64_t rows, int64_t rank, int64_t row_stride, int64_t col_stride, int dtype,
+                           void* gram, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!f || !gram || !workspace || rows < 1 || rank < 1 || rank > kMaxRank || !dtype_valid(dtype)) return TLB200_EINVAL;
+    if (workspace_bytes < tlb200_gram_workspace_bytes(rows, rank, dtype)) return TLB200_EWORKSPACE;
+    set_last_path("simt");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == TLB200_F32) return gram_launch<float>((const float*)f, rows, rank, row_stride, col_stride, (float*)gram, workspace, s);
+    return gram_launch<double>((const double*)f, rows, rank, row_stride, col_stride, (double*)gram, workspace, s);
+}
+
+extern "C" int tlb200_cp_update(const void* const* grams, int nmodes, int mode, int64_t rank, const void* weights,
+                                double l2_reg, const void* m, int64_t m_ld, int64_t rows, int dtype, void* out,
+                                int64_t out_ld, void* stream) {
+    if (!m || !out || rank < 1 || rank > kMaxRank || rows < 0 || mode < 0 || mode >= nmodes || m_ld < rank ||
+        out_ld < rank || !dtype_valid(dtype))
+        return TLB200_EINVAL;
+    set_last_path("simt");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == TLB200_F32)
+        return cp_update_launch<float>(grams, nmodes, mode, rank, (const float*)weights, l2_reg, (const float*)m, m_ld, rows,
+                                       (float*)out, out_ld, s);
+    return cp_update_launch<double>(grams, nmodes, mode, rank, (const double*)weights, l2_reg, (const double*)m, m_ld, rows,
+                                    (double*)out, out_ld, s);
+}
+
+extern "C" int tlb200_nncp_update(const void* const* grams, int nmodes, int mode, int64_t rank, const void* weights,
+                                  const void* m, int64_t m_ld, void* f, int64_t f_ld, int64_t rows, double eps, int dtype,
+                                  void* stream) {
+    if (!m || !f || rank < 1 || rank > kMaxRank || rows < 0 || mode < 0 || mode >= nmodes || m_ld < rank || f_ld < rank ||
+        !dtype_valid(dtype))
+        return TLB200_EINVAL;
+    set_last_path("simt");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == TLB200_F32)
+        return nncp_update_launch<float>(grams, nmodes, mode, rank, (const float*)weights, (const float*)m, m_ld, (float*)f,
+                                         f_ld, rows, eps, s);
+    return nncp_update_launch<double>(grams, nmodes, mode, rank, (const double*)weights, (const double*)m, m_ld, (double*)f,
+                                      f_ld, rows, eps, s);
+}
+
+extern "C" int tlb200_cp_error(const void* const* grams, int nmodes, int64_t rank, const void* weights, const void* m_last,
+                               int64_t m_ld, const void* f_last, int64_t f_row_stride, int64_t f_col_stride, int64_t rows,
+                               const void* norm_x2, int dtype, void* err_out, void* stream) {
+    if (!m_last || !f_last || !norm_x2 || !err_out || rank < 1 || rank > kMaxRank || rows < 1 || !dtype_valid(dtype))
+        return TLB200_EINVAL;
+    set_last_path("simt");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == TLB200_F32) {
+        GramList<float> gl;
+        int st = fill_grams<float>(&gl, grams, nmodes, -1);
+        if (st) return st;
+        cp_error_kernel<float><<<1, 1024, 0, s>>>(gl, (int)rank, (const float*)weights, (const float*)m_last, m_ld,
+                                                  (const float*)f_last, f_row_stride, f_col_stride, rows,
+                                                  (const float*)norm_x2, (float*)err_out);
+    } else {
+        GramList<double> gl;
+        int st = fill_grams<double>(&gl, grams, nmodes, -1);
+        if (st) return st;
+        cp_error_kernel<double><<<1, 1024, 0, s>>>(gl, (int)rank, (const double*)weights, (const double*)m_last, m_ld,
+                                                   (const double*)f_last, f_row_stride, f_col_stride, rows,
+                                                   (const double*)norm_x2, (double*)err_out);
+    }
+    TLB_CHECK_LAUNCH();
+    return TLB200_OK;
+}
+
+extern "C" size_t tlb200_sumsq_workspace_bytes(int64_t, int) { return align_up(sizeof(double) * kSumsqBlocks, 256); }
+
+extern "C" int tlb200_sumsq(const void* x, int64_t n, int dtype, void* out, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+    if (!x || !out || !workspace || n < 0 || !dtype_valid(dtype)) return TLB200_EINVAL;
+    if (workspace_bytes < tlb200_sumsq_workspace_bytes(n, dtype)) return TLB200_EWORKSPACE;
+    set_last_path("simt");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    double* partial = static_cast<double*>(workspace);
+    if (dtype == TLB200_F32) {
+        const float* xf = static_cast<const float*>(x);
+        if (reinterpret_cast<uintptr_t>(x) % 16 == 0) {
+            const int64_t n4 = n / 4;
+            sumsq_partial_f4_kernel<<<kSumsqBlocks, 256, 0, s>>>(reinterpret_cast<const float4*>(x), n4, partial);
+            TLB_CHECK_LAUNCH();
+            sumsq_final_kernel<float><<<1, 32, 0, s>>>(partial, kSumsqBlocks, xf + n4 * 4, (int)(n - n4 * 4), (float*)out);
+        } else {
+            sumsq_partial_kernel<float><<<kSumsqBlocks, 256, 0, s>>>(xf, n, partial);
+            TLB_CHECK_LAUNCH();
+            sumsq_final_kernel<float><<<1, 32, 0, s>>>(partial, kSumsqBlocks, xf, 0, (float*)out);
+        }
+    } else {
+        const double* xd = static_cast<const double*>(x);
+        sumsq_partial_kernel<double><<<kSumsqBlocks, 256, 0, s>>>(xd, n, partial);
+        TLB_CHECK_LAUNCH();
+        sumsq_final_kernel<double><<<1, 32, 0, s>>>(partial, kSumsqBlocks, xd, 0, (double*)out);
+    }
+    TLB_CHECK_LAUNCH();
+    return TLB200_OK;
+}

@@ -1,0 +1,110 @@
+// Khatri-Rao product, bit-exact against the reference's left fold of broadcast
+// multiplies (tensorly/tenalg/core_tenalg/_khatri_rao.py:94-109):
+//   out[(i_0..i_{m-1}), r] = ((((M_0[i_0,r] * w[r]) * M_1[i_1,r]) * M_2[i_2,r]) ...) * mask[row]
+// One IEEE-rounded multiply per step (__fmul_rn/__dmul_rn: never contracted, never
+// reassociated).  Output-bandwidth bound: each output element is written once, inputs
+// are tiny and L2-resident.
+#include "common.cuh"
+
+namespace tlb200 {
+namespace {
+
+template <typename T>
+struct KrArgs {
+    const T* mat[TLB200_MAX_NDIM];
+    int64_t rows[TLB200_MAX_NDIM];
+    int64_t rs[TLB200_MAX_NDIM];
+    int64_t cs[TLB200_MAX_NDIM];
+    int nmats;
+};
+
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+
+// blockDim = (32, 8): x runs over columns, y over rows.
+template <typename T>
+__global__ void __launch_bounds__(256)
+khatri_rao_kernel(KrArgs<T> a, int64_t total_rows, int64_t rank, int64_t pad_cols,
+                  const T* __restrict__ weights, const T* __restrict__ mask, T* __restrict__ out,
+                  int64_t out_ld) {
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; row < total_rows;
+         row += (int64_t)gridDim.x * blockDim.y) {
+        int64_t idx[TLB200_MAX_NDIM];
+        int64_t rem = row;
+#pragma unroll
+        for (int i = TLB200_MAX_NDIM - 1; i >= 0; --i) {
+            if (i < a.nmats) {
+                int64_t q = rem / a.rows[i];
+                idx[i] = rem - q * a.rows[i];
+                rem = q;
+            }
+        }
+        T mk = mask ? mask[row] : T(1);
+        for (int64_t c = threadIdx.x; c < pad_cols; c += 32) {
+            T v = T(0);
+            if (c < rank) {
+                v = a.mat[0][idx[0] * a.rs[0] + c * a.cs[0]];
+                if (weights) v = mul_rn(v, weights[c]);
+#pragma unroll
+                for (int i = 1; i < TLB200_MAX_NDIM; ++i)
+                    if (i < a.nmats) v = mul_rn(v, a.mat[i][idx[i] * a.rs[i] + c * a.cs[i]]);
+                if (mask) v = mul_rn(v, mk);
+            }
+            out[row * out_ld + c] = v;
+        }
+    }
+}
+
+}  // namespace
+
+template <typename T>
+int launch_khatri_rao(const T* const* mats, const int64_t* rows, const int64_t* row_stride,
+                      const int64_t* col_stride, int nmats, int64_t rank, const T* weights,
+                      const T* mask, T* out, int64_t out_ld, int64_t pad_cols, cudaStream_t stream) {
+    if (nmats < 1 || nmats > TLB200_MAX_NDIM || rank < 0 || pad_cols < rank || out_ld < pad_cols)
+        return TLB200_EINVAL;
+    KrArgs<T> a;
+    a.nmats = nmats;
+    int64_t total = 1;
+    for (int i = 0; i < nmats; ++i) {
+        if (rows[i] < 0) return TLB200_EINVAL;
+        a.mat[i] = mats[i];
+        a.rows[i] = rows[i];
+        a.rs[i] = row_stride[i];
+        a.cs[i] = col_stride[i];
+        total *= rows[i];
+    }
+    for (int i = nmats; i < TLB200_MAX_NDIM; ++i) { a.mat[i] = nullptr; a.rows[i] = 1; a.rs[i] = 0; a.cs[i] = 0; }
+    if (total == 0 || pad_cols == 0) return TLB200_OK;
+    int64_t blocks = ceil_div(total, 8);
+    if (blocks > (int64_t)kNumSMs * 64) blocks = (int64_t)kNumSMs * 64;
+    khatri_rao_kernel<T><<<(unsigned)blocks, dim3(32, 8), 0, stream>>>(a, total, rank, pad_cols, weights, mask, out, out_ld);
+    TLB_CHECK_LAUNCH();
+    return TLB200_OK;
+}
+
+template int launch_khatri_rao<float>(const float* const*, const int64_t*, const int64_t*, const int64_t*, int, int64_t,
+                                      const float*, const float*, float*, int64_t, int64_t, cudaStream_t);
+template int launch_khatri_rao<double>(const double* const*, const int64_t*, const int64_t*, const int64_t*, int, int64_t,
+                                       const double*, const double*, double*, int64_t, int64_t, cudaStream_t);
+
+}  // namespace tlb200
+
+using namespace tlb200;
+
+extern "C" int tlb200_khatri_rao(const void* const* mats, const int64_t* rows, const int64_t* row_stride,
+                                 const int64_t* col_stride, int nmats, int64_t rank, const void* weights,
+                                 const void* mask, int dtype, void* out, int64_t out_ld, void* stream) {
+    if (!mats || !rows || !row_stride || !col_stride || !dtype_valid(dtype) || nmats < 1 || nmats > TLB200_MAX_NDIM ||
+        rank < 0 || out_ld < rank)
+        return TLB200_EINVAL;
+    for (int i = 0; i < nmats; ++i)
+        if (!mats[i] && rows[i] * rank) return TLB200_EINVAL;
+    set_last_path("khatri_rao");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == TLB200_F32)
+        return launch_khatri_rao<float>(reinterpret_cast<const float* const*>(mats), rows, row_stride, col_stride, nmats,
+                                        rank, (const float*)weights, (const float*)mask, (float*)out, out_ld, rank, s);
+    return launch_khatri_rao<double>(reinterpret_cast<const double* const*>(mats), rows, row_stride, col_stride, nmats,
+                                     rank, (const double*)weights, (const double*)mask, (double*)out, out_ld, rank, s);
+}

@@ -1,0 +1,17 @@
+// tcgen05 (5th-gen tensor core) MTTKRP path — interface used by mttkrp.cu.
+#pragma once
+#include "common.cuh"
+
+namespace tlb200 {
+
+// True when the fp32 3xTF32 tcgen05 kernel can run this plan (shape/alignment rules in
+// mttkrp_tc.cu).
+bool mttkrp_tc_supported(const tlb200_mttkrp_plan_t& pl, int64_t rank, int dtype);
+// Fills rank_padded and splits for the tcgen05 kernel's tiling.
+void mttkrp_tc_fill_plan(tlb200_mttkrp_plan_t* pl, int64_t rank);
+size_t mttkrp_tc_extra_workspace(const tlb200_mttkrp_plan_t& pl);
+// Writes partial[split][J][rank_padded]; the caller runs the deterministic reduction.
+int mttkrp_tc_launch(const float* x, const tlb200_mttkrp_plan_t& pl, int64_t rank, const float* P,
+                     const float* Q, float* partial, void* extra_ws, cudaStream_t stream);
+
+}  // namespace tlb200
