@@ -49,6 +49,9 @@ const char* tlb200_status_string(int status);
 /* Name of the kernel family the last call on this host thread dispatched to
  * ("simt", "tcgen05", "copy", ...).  Used by tests to prove which path ran. */
 const char* tlb200_last_path(void);
+/* Number of kernel launches this library has issued so far in this process (host-side
+ * count; graph replays re-launch the captured kernels without passing through here). */
+int64_t     tlb200_launch_count(void);
 
 /* ---------------------------------------------------------------------------
  * unfold — replaces tensorly.base.unfold (tensorly/base.py:39-53):

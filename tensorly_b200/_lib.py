@@ -47,6 +47,7 @@ SIGNATURES = {
     "tlb200_build_arch": (c_char_p, []),
     "tlb200_status_string": (c_char_p, [c_int]),
     "tlb200_last_path": (c_char_p, []),
+    "tlb200_launch_count": (c_int64, []),
     "tlb200_unfold": (c_int, [c_void_p, _I64P, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tlb200_fold": (c_int, [c_void_p, _I64P, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tlb200_khatri_rao": (c_int, [_VPP, _I64P, _I64P, _I64P, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p,

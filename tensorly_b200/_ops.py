@@ -41,6 +41,11 @@ def last_kernel_path() -> str:
     return _lib.load().tlb200_last_path().decode()
 
 
+def launch_count() -> int:
+    """Kernel launches issued by libtlb200 so far (host-side count)."""
+    return int(_lib.load().tlb200_launch_count())
+
+
 # --------------------------------------------------------------------------- helpers
 def _check_tensor(t, name: str, ref: torch.Tensor | None = None) -> torch.Tensor:
     if not isinstance(t, torch.Tensor):

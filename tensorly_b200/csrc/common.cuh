@@ -18,8 +18,12 @@ void set_last_path(const char* name);
 
 inline int cuda_ok(cudaError_t e) { return e == cudaSuccess ? TLB200_OK : TLB200_ECUDA; }
 
+void count_launch();
+
+// After every kernel launch: count it and surface launch errors.
 #define TLB_CHECK_LAUNCH()                                  \
     do {                                                    \
+        ::tlb200::count_launch();                           \
         cudaError_t e__ = cudaGetLastError();               \
         if (e__ != cudaSuccess) return TLB200_ECUDA;        \
     } while (0)

@@ -1,0 +1,489 @@
+"""GPU parity tests: the CUDA path (called through the C ABI) against the committed
+reference fixtures (tests/golden, generated from the real TensorLy) and against the CPU
+oracle on the same seeded inputs.
+
+Gates (BASELINE.json north_star): unfold / khatri_rao bit-exact; MTTKRP / TTM relative
+Frobenius error <= 1e-5 (fp32) / 1e-12 (fp64) against the numpy `core` result in the same
+dtype; ALS reconstruction error within 1e-4 (relative) after a fixed number of sweeps.
+"""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+import tensorly_b200 as tb
+from oracle import oracle as O
+from conftest import rel_fro
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12}
+PATHS = ["simt", "auto"]
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(autouse=True)
+def _reset_path():
+    tb.set_kernel_path("auto")
+    yield
+    tb.set_kernel_path("auto")
+
+
+# --------------------------------------------------------------------------- unfold / fold
+def test_unfold_fold_golden(golden):
+    g = golden("unfold")
+    for case in g.cases():
+        x = g[f"{case}/x"]
+        xd = dev(x)
+        for mode in range(x.ndim):
+            u = tb.unfold(xd, mode, contiguous=True)
+            assert u.is_contiguous()
+            assert np.array_equal(host(u), g[f"{case}/unfold{mode}"])
+            assert np.array_equal(host(tb.fold(u, mode, x.shape)), x)
+            assert np.array_equal(host(tb.unfold(xd, mode)), g[f"{case}/unfold{mode}"])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(37, 65, 129), (64, 3, 5, 40), (5, 300, 1), (1, 17, 33), (2, 2, 2, 2, 2, 2, 3, 4),
+                                   (130, 257), (96, 32, 64), (33, 40, 7)])
+def test_unfold_fold_bit_exact(shape, dtype):
+    rng = np.random.RandomState(0)
+    x = rng.standard_normal(shape).astype(dtype)
+    xd = dev(x)
+    for mode in range(len(shape)):
+        u = tb.unfold(xd, mode, contiguous=True)
+        assert np.array_equal(host(u), np.ascontiguousarray(O.unfold(x, mode)))
+        assert np.array_equal(host(tb.fold(u, mode, shape)), x)
+    assert tb.last_kernel_path() == "copy"
+
+
+def test_unfold_noncontiguous_input_and_negative_mode():
+    x = np.random.RandomState(1).random_sample((6, 7, 8)).astype(np.float32)
+    xd = dev(x).permute(2, 0, 1)          # non-contiguous view
+    xn = np.transpose(x, (2, 0, 1))
+    for mode in (-1, 0, 1):
+        assert np.array_equal(host(tb.unfold(xd, mode)), O.unfold(xn, mode % 3))
+
+
+# --------------------------------------------------------------------------- khatri_rao
+def test_khatri_rao_golden_bit_exact(golden):
+    g = golden("khatri_rao")
+    for case in g.cases():
+        mats = [dev(m) for m in g.arrays(case, "m")]
+        w = dev(g[f"{case}/w"]) if g.has(f"{case}/w") else None
+        mask = dev(g[f"{case}/mask"]) if g.has(f"{case}/mask") else None
+        skip = int(g[f"{case}/skip"])
+        out = tb.khatri_rao(mats, weights=w, skip_matrix=None if skip < 0 else skip, mask=mask)
+        ref = g[f"{case}/out"]
+        assert host(out).dtype == ref.dtype
+        assert np.array_equal(host(out), ref), case
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_khatri_rao_bit_exact_vs_oracle(dtype):
+    rng = np.random.RandomState(3)
+    for rows, rank in (((1024, 64), 32), ((17, 9, 33), 37), ((5, 4, 3, 2, 6), 5), ((300, 1, 7), 64), ((2, 2), 1)):
+        mats = [(rng.standard_normal((r, rank))).astype(dtype) for r in rows]
+        w = rng.standard_normal(rank).astype(dtype)
+        for weights in (None, w):
+            out = tb.khatri_rao([dev(m) for m in mats], weights=None if weights is None else dev(weights))
+            assert np.array_equal(host(out), O.khatri_rao(mats, weights=weights))
+        # column-major (strided) inputs, e.g. U straight out of an SVD
+        strided = [dev(np.ascontiguousarray(m.T)).T for m in mats]
+        assert not strided[0].is_contiguous() or strided[0].shape[1] == 1 or strided[0].shape[0] == 1
+        assert np.array_equal(host(tb.khatri_rao(strided, weights=dev(w))), O.khatri_rao(mats, weights=w))
+
+
+def test_khatri_rao_reference_semantics():
+    rng = np.random.RandomState(4)
+    mats = [dev(rng.random_sample((n, 3)).astype(np.float32)) for n in (4, 5, 2)]
+    # single remaining matrix is returned as is, weights ignored (_khatri_rao.py:68-69)
+    assert tb.khatri_rao([mats[0]], weights=dev(np.array([2.0, 2.0, 2.0], dtype=np.float32))) is mats[0]
+    assert tb.khatri_rao(mats[:2], skip_matrix=1) is mats[0]
+    with pytest.raises(ValueError):
+        tb.khatri_rao([mats[0], dev(rng.random_sample((3, 4)).astype(np.float32))])
+    with pytest.raises(ValueError):
+        tb.khatri_rao([mats[0], dev(rng.random_sample((3, 3, 2)).astype(np.float32))])
+    with pytest.warns(UserWarning):
+        out = tb.khatri_rao([dev(np.arange(3, dtype=np.float32)), dev(np.arange(4, dtype=np.float32))])
+    assert np.array_equal(host(out), np.outer(np.arange(3), np.arange(4)).reshape(-1, 1).astype(np.float32))
+
+
+# --------------------------------------------------------------------------- MTTKRP
+@pytest.mark.parametrize("path", PATHS)
+def test_mttkrp_golden(golden, path):
+    tb.set_kernel_path(path)
+    g = golden("mttkrp")
+    for case in g.cases():
+        x = g[f"{case}/x"]
+        fs = g.arrays(case, "f")
+        w = g[f"{case}/w"] if g.has(f"{case}/w") else None
+        xd, fd = dev(x), [dev(f) for f in fs]
+        wd = None if w is None else dev(w)
+        for mode in range(x.ndim):
+            out = tb.unfolding_dot_khatri_rao(xd, (wd, fd), mode)
+            assert out.shape == (x.shape[mode], fs[0].shape[1])
+            err = rel_fro(host(out), g[f"{case}/out{mode}"])
+            assert err <= TOL[x.dtype], (case, mode, err)
+
+
+MTTKRP_CASES = [
+    # shape, rank
+    ((64, 48, 80), 32),
+    ((128, 128, 128), 32),
+    ((130, 70, 45), 10),
+    ((256, 64, 96), 64),
+    ((33, 257, 19), 7),
+    ((40, 24, 20, 12), 16),
+    ((12, 10, 9, 8, 6), 5),
+    ((300, 200), 12),
+    ((96, 160, 64), 100),
+    ((16, 16, 4096), 32),
+    ((4096, 16, 16), 32),
+]
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape,rank", MTTKRP_CASES)
+def test_mttkrp_vs_oracle(shape, rank, dtype, path):
+    tb.set_kernel_path(path)
+    rng = np.random.RandomState(hash((shape, rank)) % (2 ** 31))
+    x = rng.random_sample(shape).astype(dtype)
+    fs = [rng.random_sample((s, rank)).astype(dtype) for s in shape]
+    w = (rng.random_sample(rank) + 0.5).astype(dtype)
+    xd, fd, wd = dev(x), [dev(f) for f in fs], dev(w)
+    for mode in range(len(shape)):
+        ref = O.unfolding_dot_khatri_rao(x, (w, fs), mode)
+        out = host(tb.unfolding_dot_khatri_rao(xd, (wd, fd), mode))
+        err = rel_fro(out, ref)
+        assert err <= TOL[np.dtype(dtype)], (shape, rank, mode, tb.last_kernel_path(), err)
+        assert tb.last_kernel_path() in ("simt", "tcgen05")
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_mttkrp_zero_mean_data(path):
+    """Zero-mean data does not average rounding bias away: a plain-TF32
+    tensor-core product fails this test; the 3xTF32 split must pass it."""
+    tb.set_kernel_path(path)
+    rng = np.random.RandomState(11)
+    shape, rank = (128, 96, 160), 32
+    x = rng.standard_normal(shape).astype(np.float32)
+    fs = [rng.standard_normal((s, rank)).astype(np.float32) for s in shape]
+    xd, fd = dev(x), [dev(f) for f in fs]
+    for mode in range(3):
+        ref32 = O.unfolding_dot_khatri_rao(x, (None, fs), mode)
+        truth = O.mttkrp_float64_truth(x, (None, fs), mode)
+        out = host(tb.unfolding_dot_khatri_rao(xd, (None, fd), mode))
+        assert rel_fro(out, ref32) <= 1e-5
+        assert rel_fro(out, truth) <= 1e-5
+
+
+def test_mttkrp_argument_conventions():
+    rng = np.random.RandomState(5)
+    shape, rank = (20, 30, 40), 6
+    x = rng.random_sample(shape).astype(np.float32)
+    fs = [rng.random_sample((s, rank)).astype(np.float32) for s in shape]
+    xd = dev(x)
+    # column-major factors (as LAPACK's U arrives), weights None, tuple or list container
+    fcm = [dev(np.ascontiguousarray(f.T)).T for f in fs]
+    ref = O.unfolding_dot_khatri_rao(x, (None, fs), 1)
+    assert rel_fro(host(tb.unfolding_dot_khatri_rao(xd, [None, fcm], 1)), ref) <= 1e-5
+    # the skipped factor is never read: garbage / wrong shape there is fine, as in the reference
+    fbad = list(fcm)
+    fbad[1] = None
+    assert rel_fro(host(tb.unfolding_dot_khatri_rao(xd, (None, fbad), 1)), ref) <= 1e-5
+    # inputs are not mutated
+    before = [host(f).copy() for f in fcm]
+    tb.unfolding_dot_khatri_rao(xd, (None, fcm), 0)
+    for a, b in zip(before, fcm):
+        assert np.array_equal(a, host(b))
+    # non-contiguous tensor
+    xp = dev(np.ascontiguousarray(np.transpose(x, (2, 0, 1)))).permute(1, 2, 0)
+    assert rel_fro(host(tb.unfolding_dot_khatri_rao(xp, (None, fcm), 2)),
+                   O.unfolding_dot_khatri_rao(x, (None, fs), 2)) <= 1e-5
+    # 2-way tensors ignore the weights, exactly like the reference (_khatri_rao.py:68-69)
+    x2 = rng.random_sample((30, 20)).astype(np.float64)
+    f2 = [rng.random_sample((30, 4)), rng.random_sample((20, 4))]
+    w2 = rng.random_sample(4) + 1
+    ref2 = O.unfolding_dot_khatri_rao(x2, (w2, f2), 0)
+    assert rel_fro(host(tb.unfolding_dot_khatri_rao(dev(x2), (dev(w2), [dev(f) for f in f2]), 0)), ref2) <= 1e-12
+    with pytest.raises(ValueError):
+        tb.unfolding_dot_khatri_rao(xd, (None, fcm[:2]), 0)
+    with pytest.raises(ValueError):
+        bad = list(fcm)
+        bad[2] = dev(rng.random_sample((41, rank)).astype(np.float32))
+        tb.unfolding_dot_khatri_rao(xd, (None, bad), 0)
+    with pytest.raises(TypeError):
+        tb.unfolding_dot_khatri_rao(xd, (None, [f.double() for f in fcm]), 0)
+
+
+# --------------------------------------------------------------------------- mode_dot / multi_mode_dot
+@pytest.mark.parametrize("path", PATHS)
+def test_mode_dot_golden(golden, path):
+    tb.set_kernel_path(path)
+    g = golden("mode_dot")
+    assert np.array_equal(host(tb.mode_dot(dev(g["a/x"]), dev(g["a/m"]), 0)), g["a/out"])
+    assert np.array_equal(host(tb.mode_dot(dev(g["a/x"]), dev(g["a/v"]), 2)), g["a/outv"])
+    for case in ("b", "c", "d"):
+        x = g[f"{case}/x"]
+        xd = dev(x)
+        for mode in range(x.ndim):
+            m, v = g[f"{case}/m{mode}"], g[f"{case}/v{mode}"]
+            out = tb.mode_dot(xd, dev(m), mode)
+            assert tuple(out.shape) == g[f"{case}/out{mode}"].shape
+            assert rel_fro(host(out), g[f"{case}/out{mode}"]) <= TOL[x.dtype]
+            outT = tb.mode_dot(xd, dev(np.ascontiguousarray(m.T)), mode, transpose=True)
+            assert rel_fro(host(outT), g[f"{case}/outT{mode}"]) <= TOL[x.dtype]
+            outv = tb.mode_dot(xd, dev(v), mode)
+            assert tuple(outv.shape) == g[f"{case}/outv{mode}"].shape
+            assert rel_fro(host(outv), g[f"{case}/outv{mode}"]) <= TOL[x.dtype]
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape,J", [((64, 96, 128), 32), ((128, 128, 128), 64), ((50, 33, 70), 17), ((20, 12, 10, 16), 8),
+                                     ((256, 40), 24), ((8, 512, 64), 64), ((64, 64, 3), 5)])
+def test_mode_dot_vs_oracle(shape, J, dtype, path):
+    tb.set_kernel_path(path)
+    rng = np.random.RandomState(7)
+    x = rng.standard_normal(shape).astype(dtype)
+    xd = dev(x)
+    for mode, s in enumerate(shape):
+        m = rng.standard_normal((J, s)).astype(dtype)
+        ref = O.mode_dot(x, m, mode)
+        out = tb.mode_dot(xd, dev(m), mode)
+        assert out.is_contiguous() and tuple(out.shape) == ref.shape
+        assert rel_fro(host(out), ref) <= TOL[np.dtype(dtype)], (shape, mode, tb.last_kernel_path())
+        # column-major U with transpose=True: how HOOI calls it (_tucker.py:194-196)
+        u = dev(np.ascontiguousarray(m)).T      # (s, J) view with stride (1, s)
+        assert rel_fro(host(tb.mode_dot(xd, u, mode, transpose=True)), ref) <= TOL[np.dtype(dtype)]
+
+
+def test_mode_dot_errors():
+    x = dev(np.zeros((3, 4, 2), dtype=np.float32))
+    with pytest.raises(ValueError):
+        tb.mode_dot(x, dev(np.zeros((2, 5), dtype=np.float32)), 0)      # test_n_mode_product.py:65-72
+    with pytest.raises(ValueError):
+        tb.mode_dot(x, dev(np.zeros((5, 2), dtype=np.float32)), 0, transpose=True)
+    with pytest.raises(ValueError):
+        tb.mode_dot(x, dev(np.zeros(5, dtype=np.float32)), 1)
+    with pytest.raises(ValueError):
+        tb.mode_dot(x, dev(np.zeros((2, 2, 2), dtype=np.float32)), 1)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_multi_mode_dot_golden(golden, path):
+    tb.set_kernel_path(path)
+    g = golden("multi_mode_dot")
+    for case in g.cases():
+        x = g[f"{case}/x"]
+        fs = g.arrays(case, "f")
+        tol = TOL[x.dtype]
+        xd = dev(x)
+        # column-major (I_n, R_n) factors with transpose=True, as HOOI passes them
+        fd = [dev(np.ascontiguousarray(f.T)).T for f in fs]
+        assert rel_fro(host(tb.multi_mode_dot(xd, fd, transpose=True)), g[f"{case}/full"]) <= tol
+        for k in range(x.ndim):
+            out = tb.multi_mode_dot(xd, fd, skip=k, transpose=True)
+            assert tuple(out.shape) == g[f"{case}/skip{k}"].shape
+            assert rel_fro(host(out), g[f"{case}/skip{k}"]) <= tol
+        ms = [dev(np.ascontiguousarray(fs[2].T)), dev(np.ascontiguousarray(fs[0].T))]
+        assert rel_fro(host(tb.multi_mode_dot(xd, ms, modes=[2, 0])), g[f"{case}/sub20"]) <= tol
+        out = tb.multi_mode_dot(xd, [dev(g[f"{case}/vec0"]), dev(g[f"{case}/vec2"])], modes=[0, 2])
+        assert tuple(out.shape) == g[f"{case}/vecs02"].shape
+        assert rel_fro(host(out), g[f"{case}/vecs02"]) <= tol
+
+
+def test_multi_mode_dot_vector_order_independence():
+    # test_n_mode_product.py:139-153: contracting every mode with a vector gives the same
+    # scalar whatever the order the pairs are listed in
+    rng = np.random.RandomState(9)
+    shape = (5, 6, 7, 4)
+    x = rng.random_sample(shape)
+    vs = [rng.random_sample(s) for s in shape]
+    truth = np.einsum("ijkl,i,j,k,l->", x, *vs)
+    xd, vd = dev(x), [dev(v) for v in vs]
+    for perm in itertools.permutations(range(4)):
+        out = tb.multi_mode_dot(xd, [vd[i] for i in perm], modes=list(perm))
+        assert out.dim() == 0
+        assert abs(float(out) - truth) <= 1e-10 * abs(truth)
+
+
+# --------------------------------------------------------------------------- normal-equation kernels
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("rows,rank", [(1024, 32), (2048, 64), (100, 10), (37, 5), (513, 100)])
+def test_gram_update_error_kernels(rows, rank, dtype):
+    rng = np.random.RandomState(13)
+    tol = 2e-5 if dtype == np.float32 else 1e-11
+    fs = [rng.random_sample((rows, rank)).astype(dtype), rng.random_sample((50, rank)).astype(dtype),
+          rng.random_sample((60, rank)).astype(dtype)]
+    w = (rng.random_sample(rank) + 0.5).astype(dtype)
+    grams = [f.T @ f for f in fs]
+    gd = [tb.gram(dev(f)) for f in fs]
+    for a, b in zip(gd, grams):
+        assert rel_fro(host(a), b) <= tol
+    # column-major factor
+    assert rel_fro(host(tb.gram(dev(np.ascontiguousarray(fs[0].T)).T)), grams[0]) <= tol
+    m = rng.random_sample((rows, rank)).astype(dtype)
+    l2 = 0.1
+    V = np.ones((rank, rank), dtype=dtype) * grams[1] * grams[2] + np.eye(rank, dtype=dtype) * dtype(l2)
+    V = w[:, None] * V * w[None, :]
+    ref = np.linalg.solve(V.T.astype(np.float64), m.T.astype(np.float64)).T
+    out = tb.cp_update(gd, 0, dev(w), dev(m), l2_reg=l2)
+    cond = np.linalg.cond(V.astype(np.float64))
+    eps = np.finfo(dtype).eps
+    assert rel_fro(host(out), ref) <= 20 * cond * eps
+    # MU update
+    f0 = dev(fs[0].copy())
+    acc = w[:, None] * (grams[1] * grams[2]) * w[None, :]
+    e = np.finfo(dtype).eps
+    ref_mu = fs[0] * np.clip(m, e, None) / np.clip(fs[0] @ acc, e, None)
+    tb.nncp_update(gd, 0, dev(w), dev(m), f0, float(e))
+    assert rel_fro(host(f0), ref_mu) <= (1e-5 if dtype == np.float32 else 1e-12)
+    # error
+    nx2 = dev(np.array([12345.678], dtype=dtype))
+    errs = host(tb.cp_error(gd, dev(w), dev(m), dev(fs[0]), nx2))
+    iprod = np.sum(m.astype(np.float64) * fs[0])
+    ncp = np.sum((grams[0] * grams[1] * grams[2]).astype(np.float64) * np.outer(w, w))
+    assert abs(errs[1] - iprod) <= tol * abs(iprod) * 10
+    assert abs(errs[2] - ncp) <= tol * abs(ncp) * 10
+    ref_err = np.sqrt(abs(12345.678 + ncp - 2 * iprod)) / np.sqrt(12345.678)
+    assert abs(errs[0] - ref_err) <= 1e-4 * ref_err
+    x = rng.standard_normal(100003).astype(dtype)
+    assert abs(float(tb.sumsq(dev(x))) - float(np.sum(x.astype(np.float64) ** 2))) <= 1e-6 * float(np.sum(x.astype(np.float64) ** 2))
+
+
+# --------------------------------------------------------------------------- ALS level
+@pytest.mark.parametrize("use_graph", [False, True])
+@pytest.mark.parametrize("tag", ["p32", "p64", "p4way"])
+def test_parafac_driver_vs_reference(golden, tag, use_graph):
+    g = golden("als")
+    x = g[f"{tag}/x"]
+    rank, iters = int(g[f"{tag}/rank"]), int(g[f"{tag}/iters"])
+    init = (None, [dev(f) for f in g.arrays(tag, "init")])
+    cp, errs = tb.parafac(dev(x), rank, n_iter_max=iters, init=init, tol=0, return_errors=True, use_graph=use_graph)
+    ref = g[f"{tag}/errors"]
+    assert len(errs) == iters
+    rel = np.max(np.abs(np.array(errs) - ref) / ref)
+    assert rel <= 1e-4, rel                    # north-star ALS gate
+    if x.dtype == np.float64:
+        assert rel <= 1e-9
+        for a, b in zip(cp[1], g.arrays(tag, "f")):
+            assert rel_fro(host(a), b) <= 1e-6
+
+
+def test_parafac_config1_fp64(golden):
+    """BASELINE config 1: rank 10, 100^3, float64, identical input and initial factors."""
+    g = golden("als")
+    x = O.random_tensor((100, 100, 100), 0)
+    w, fs = O.random_cp_factors((100, 100, 100), 10, 1)
+    iters = int(g["c1/iters"])
+    cp, errs = tb.parafac(dev(x), 10, n_iter_max=iters, init=(None, [dev(f) for f in fs]), tol=0, return_errors=True)
+    ref = g["c1/errors"]
+    assert np.max(np.abs(np.array(errs) - ref) / ref) <= 1e-9
+    assert rel_fro(host(cp[1][0])[:4], g["c1/f0_head"]) <= 1e-6
+    # init="random" reproduces random_cp(random_state=1): same trajectory
+    cp2, errs2 = tb.parafac(dev(x), 10, n_iter_max=3, init="random", random_state=1, tol=0, return_errors=True)
+    assert np.max(np.abs(np.array(errs2) - ref[:3]) / ref[:3]) <= 1e-9
+
+
+def test_parafac_lowrank_and_tol(golden):
+    g = golden("als")
+    x = g["lowrank/x"]
+    init = (None, [dev(f) for f in g.arrays("lowrank", "init")])
+    cp, errs = tb.parafac(dev(x), 5, n_iter_max=8, init=init, tol=0, return_errors=True)
+    assert np.max(np.abs(np.array(errs) - g["lowrank/errors"])) <= 1e-8
+    # early stop on tolerance: stops where the reference's rule stops
+    ref = g["lowrank/errors"]
+    tol = 1e-3
+    stop = next(i for i in range(1, len(ref)) if abs(ref[i - 1] - ref[i]) < tol)
+    _, errs2 = tb.parafac(dev(x), 5, n_iter_max=8, init=init, tol=tol, return_errors=True)
+    assert len(errs2) == stop + 1
+    # init tuple is not mutated
+    for a, b in zip(init[1], g.arrays("lowrank", "init")):
+        assert np.array_equal(host(a), b)
+
+
+def test_non_negative_parafac_driver_vs_reference(golden):
+    g = golden("als")
+    x = g["nn/x"]
+    init = (None, [dev(f) for f in g.arrays("nn", "init")])
+    cp, errs = tb.non_negative_parafac(dev(x), 6, n_iter_max=10, init=init, tol=1e-30, return_errors=True)
+    ref = g["nn/errors"]
+    assert np.max(np.abs(np.array(errs) - ref) / ref) <= 1e-4
+    for a, b in zip(cp[1], g.arrays("nn", "f")):
+        assert rel_fro(host(a), b) <= 1e-3
+        assert float(a.min()) >= 0.0
+
+
+# --------------------------------------------------------------------------- unmodified TensorLy on the b200 backend
+@pytest.fixture
+def tl_b200():
+    try:
+        tl = tb.import_tensorly()
+    except ImportError:
+        pytest.skip("tensorly not importable on this box")
+    prev_backend, prev_tenalg = tl.get_backend(), tl.tenalg.get_backend()
+    tl.set_backend("pytorch")
+    tb.use()
+    yield tl
+    tl.tenalg.set_backend(prev_tenalg)
+    tl.set_backend(prev_backend)
+
+
+def test_reference_parafac_runs_unmodified_on_backend(tl_b200, golden):
+    tl = tl_b200
+    from tensorly.cp_tensor import CPTensor
+    from tensorly.decomposition import parafac
+    g = golden("als")
+    for tag in ("p32", "p64", "p4way"):
+        x = g[f"{tag}/x"]
+        rank, iters = int(g[f"{tag}/rank"]), int(g[f"{tag}/iters"])
+        init = CPTensor((torch.ones(rank, dtype=dev(x).dtype, device="cuda"), [dev(f) for f in g.arrays(tag, "init")]))
+        cp, errs = parafac(dev(x), rank, n_iter_max=iters, init=init, tol=0, return_errors=True)
+        ref = g[f"{tag}/errors"]
+        got = np.array([float(e) for e in errs])
+        assert np.max(np.abs(got - ref) / ref) <= 1e-4
+        assert tb.last_kernel_path() in ("simt", "tcgen05")
+
+
+def test_reference_nn_parafac_and_tucker_run_unmodified_on_backend(tl_b200, golden):
+    from tensorly.cp_tensor import CPTensor
+    from tensorly.decomposition import non_negative_parafac, partial_tucker, tucker
+    g = golden("als")
+    x = g["nn/x"]
+    init = CPTensor((torch.ones(6, dtype=torch.float32, device="cuda"), [dev(f) for f in g.arrays("nn", "init")]))
+    cp, errs = non_negative_parafac(dev(x), 6, n_iter_max=10, init=init, tol=1e-30, return_errors=True)
+    ref = g["nn/errors"]
+    assert np.max(np.abs(np.array([float(e) for e in errs]) - ref) / ref) <= 1e-4
+    x = g["tucker/x"]
+    ranks = [int(r) for r in g["tucker/ranks"]]
+    (core, factors), errs = tucker(dev(x), ranks, n_iter_max=5, init="random", random_state=1, tol=0, return_errors=True)
+    ref = g["tucker/errors"]
+    assert np.max(np.abs(np.array([float(e) for e in errs]) - ref) / ref) <= 1e-4
+    assert abs(float(torch.linalg.norm(core)) - float(g["tucker/core_norm"])) <= 1e-6 * float(g["tucker/core_norm"])
+    (core2, factors2), errs2 = partial_tucker(dev(x), ranks[:2], modes=[0, 1], n_iter_max=3, init="svd", tol=0)
+    assert tuple(core2.shape) == (ranks[0], ranks[1], x.shape[2])
+    assert tb.last_kernel_path() in ("simt", "tcgen05")
+
+
+def test_reference_reconstruction_uses_backend(tl_b200):
+    tl = tl_b200
+    rng = np.random.RandomState(2)
+    fs = [dev(rng.random_sample((s, 4))) for s in (6, 7, 8)]
+    w = dev(rng.random_sample(4))
+    full = tl.cp_to_tensor((w, fs))              # calls the dispatched khatri_rao
+    ref = O.cp_to_tensor((host(w), [host(f) for f in fs]))
+    assert rel_fro(host(full), ref) <= 1e-12
+    assert tl.tenalg.get_backend() == "b200"
+    with pytest.raises(ValueError):
+        tl.tenalg.set_backend("no-such-backend")
