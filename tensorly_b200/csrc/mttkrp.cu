@@ -171,7 +171,17 @@ extern "C" size_t tlb200_mttkrp_workspace_bytes(const int64_t* shape, int ndim, 
                                                 int path) {
     tlb200_mttkrp_plan_t pl;
     if (make_plan(shape, ndim, mode, rank, dtype, path, &pl)) return 0;
-    return workspace_for(pl, dtype);
+    size_t need = workspace_for(pl, dtype);
+    if (path == TLB200_PATH_AUTO && pl.path == TLB200_PATH_TCGEN05) {
+        // AUTO may still have to take the SIMT path at launch time (e.g. a tensor pointer that
+        // is not 16-byte aligned cannot be described to TMA): size for both.
+        tlb200_mttkrp_plan_t simt;
+        if (!make_plan(shape, ndim, mode, rank, dtype, TLB200_PATH_SIMT, &simt)) {
+            const size_t s = workspace_for(simt, dtype);
+            if (s > need) need = s;
+        }
+    }
+    return need;
 }
 
 extern "C" int tlb200_mttkrp(const void* x, const int64_t* shape, int ndim, int mode, const void* const* factors,
@@ -184,6 +194,11 @@ extern "C" int tlb200_mttkrp(const void* x, const int64_t* shape, int ndim, int 
     if (!x || !factors || !f_row_stride || !f_col_stride || !out || out_ld < rank || !workspace) return TLB200_EINVAL;
     for (int i = 0; i < ndim; ++i)
         if (i != mode && !factors[i]) return TLB200_EINVAL;
+    if (pl.path == TLB200_PATH_TCGEN05 && reinterpret_cast<uintptr_t>(x) % 16) {
+        if (path == TLB200_PATH_TCGEN05) return TLB200_EUNSUPPORTED;
+        st = make_plan(shape, ndim, mode, rank, dtype, TLB200_PATH_SIMT, &pl);
+        if (st) return st;
+    }
     if (workspace_bytes < workspace_for(pl, dtype)) return TLB200_EWORKSPACE;
     if (reinterpret_cast<uintptr_t>(workspace) % 256) return TLB200_EINVAL;
     cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -404,7 +404,8 @@ def test_parafac_lowrank_and_tol(golden):
     assert np.max(np.abs(np.array(errs) - g["lowrank/errors"])) <= 1e-8
     # early stop on tolerance: stops where the reference's rule stops
     ref = g["lowrank/errors"]
-    tol = 1e-3
+    dec = np.abs(np.diff(ref))
+    tol = float(np.sqrt(dec[3] * dec[4]))          # between the 4th and 5th decrease
     stop = next(i for i in range(1, len(ref)) if abs(ref[i - 1] - ref[i]) < tol)
     _, errs2 = tb.parafac(dev(x), 5, n_iter_max=8, init=init, tol=tol, return_errors=True)
     assert len(errs2) == stop + 1
