@@ -385,7 +385,7 @@ int flush_period() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("TLB200_TC_FLUSH");
-        v = e ? atoi(e) : 8;
+        v = e ? atoi(e) : 4;
         if (v < AS) v = AS;     // the deferred drain assumes a group is at least as long as the A ring
     }
     return v;

@@ -1,0 +1,67 @@
+"""CPU stand-in for tensorly_b200.cp_als.CudaOps built on the oracle — TEST ONLY.
+Lets the sharded CP-ALS driver's host logic (slab partition, which partials are
+all-reduced, error assembly) run under gloo on a box without a GPU."""
+import numpy as np
+import torch
+
+from oracle import oracle as O
+
+
+def _np(t):
+    return None if t is None else t.detach().cpu().numpy()
+
+
+def _form_v(grams, mode, weights, l2):
+    rank = grams[0].shape[0]
+    v = np.ones((rank, rank), dtype=_np(grams[0]).dtype)
+    for i, g in enumerate(grams):
+        if i != mode:
+            v = v * _np(g)
+    if l2:
+        v = v + np.eye(rank, dtype=v.dtype) * l2
+    w = _np(weights)
+    return w[:, None] * v * w[None, :]
+
+
+class OracleOps:
+    supports_graphs = False
+
+    @staticmethod
+    def mttkrp(x, cp, mode):
+        w, fs = cp
+        return torch.from_numpy(np.ascontiguousarray(O.unfolding_dot_khatri_rao(_np(x), (_np(w), [_np(f) for f in fs]), mode)))
+
+    @staticmethod
+    def gram(f, out=None):
+        g = torch.from_numpy(_np(f).T @ _np(f))
+        return g if out is None else out.copy_(g)
+
+    @staticmethod
+    def cp_update(grams, mode, weights, m, l2_reg=0.0, out=None):
+        v = _form_v(grams, mode, weights, l2_reg)
+        f = torch.from_numpy(np.ascontiguousarray(np.linalg.solve(v.T, _np(m).T).T))
+        return f if out is None else out.copy_(f)
+
+    @staticmethod
+    def nncp_update(grams, mode, weights, m, factor, eps):
+        v = _form_v(grams, mode, weights, 0.0)
+        f = _np(factor)
+        factor.copy_(torch.from_numpy(f * np.clip(_np(m), eps, None) / np.clip(f @ v, eps, None)))
+        return factor
+
+    @staticmethod
+    def cp_error(grams, weights, m_last, f_last, norm_x2, out=None):
+        w = _np(weights)
+        ncp = np.ones_like(_np(grams[0]))
+        for g in grams:
+            ncp = ncp * _np(g)
+        ncp = float(np.sum(ncp * np.outer(w, w)))
+        iprod = float(np.sum(_np(m_last) * _np(f_last)))
+        nx2 = float(norm_x2[0])
+        vals = torch.tensor([np.sqrt(abs(nx2 + ncp - 2 * iprod)) / np.sqrt(nx2), iprod, ncp], dtype=m_last.dtype)
+        return vals if out is None else out.copy_(vals)
+
+    @staticmethod
+    def sumsq(x, out=None):
+        v = torch.tensor([float(np.sum(_np(x).astype(np.float64) ** 2))], dtype=x.dtype)
+        return v if out is None else out.copy_(v)
