@@ -326,9 +326,12 @@ def mode_dot(tensor: torch.Tensor, matrix_or_vector: torch.Tensor, mode: int, tr
     if x.numel() == 0:
         return out.zero_().reshape(final_shape)
     lib = _lib.load()
+    shape = _lib.i64_array(x.shape)
+    dt, path = _DTYPES[x.dtype], _lib.PATHS[_path]
+    ws = _workspace(lib.tlb200_mode_dot_workspace_bytes(shape, ndim, mode, rows_out, dt, path), x)
     with _Device(x):
-        st = lib.tlb200_mode_dot(x.data_ptr(), _lib.i64_array(x.shape), ndim, mode, m.data_ptr(), rows_out, rs, cs,
-                                 _DTYPES[x.dtype], out.data_ptr(), None, 0, _lib.PATHS[_path], _stream(x))
+        st = lib.tlb200_mode_dot(x.data_ptr(), shape, ndim, mode, m.data_ptr(), rows_out, rs, cs, dt, out.data_ptr(),
+                                 ws.data_ptr(), ws.numel(), path, _stream(x))
     _lib.check(st, "mode_dot")
     return out.reshape(final_shape)
 

@@ -4,10 +4,9 @@
 
 namespace tlb200 {
 
-// True when the fp32 3xTF32 tcgen05 kernel can run this plan (shape/alignment rules in
-// mttkrp_tc.cu).
+// True when the fp32 3xTF32 tcgen05 engine (tc_stream.cu) can run this plan.
 bool mttkrp_tc_supported(const tlb200_mttkrp_plan_t& pl, int64_t rank, int dtype);
-// Fills rank_padded and splits for the tcgen05 kernel's tiling.
+// Fills rank_padded and splits for the tcgen05 engine's tiling.
 void mttkrp_tc_fill_plan(tlb200_mttkrp_plan_t* pl, int64_t rank);
 size_t mttkrp_tc_extra_workspace(const tlb200_mttkrp_plan_t& pl);
 // Writes partial[split][J][rank_padded]; the caller runs the deterministic reduction.

@@ -1,0 +1,64 @@
+// tcgen05 "stream GEMM": the tensor-core engine shared by MTTKRP and TTM.
+//
+//   C[kr][m, n] = sum over the K chunks of item (mt, kr) of  X_tile[128 x KS] * B_tile[KS x RP]
+//
+// X is the big tensor, streamed from HBM exactly once by TMA; B is small (Khatri-Rao rows
+// synthesised on the fly, or a pre-split factor matrix).  fp32 in, fp32 out, error-
+// compensated 3xTF32 on the tensor cores (see tc_stream.cu for the full design notes).
+#pragma once
+#include "common.cuh"
+#include <cuda.h>
+
+namespace tlb200 {
+
+enum TcXLayout {
+    TC_X_KMAJOR_1 = 0,   // tile = 128 rows x 32 k (one 128-byte line per row)         [any B]
+    TC_X_KMAJOR_2 = 1,   // tile = 128 rows x 64 k (two adjacent lines per row: DRAM-friendly) [B % 32 == 0]
+    TC_X_MMAJOR = 2      // tile = 64 k-rows x 128 m (m contiguous in memory)
+};
+enum TcBMode {
+    TC_B_KR = 0,         // B(k=(a,b), n) = P[a, n] * Q[b, n], synthesised by 4 warps
+    TC_B_MAT = 1         // B(k=b, n) from pre-split hi/lo matrices via TMA
+};
+
+struct TcStreamParams {
+    // K space: A x B, chunked along B in steps of KS
+    int64_t M;                 // extent of the streamed (row) dim
+    int64_t A, B;
+    int64_t chunks_per_a;      // ceil(B / KS)
+    int64_t total_chunks;      // A * chunks_per_a
+    // items: (mt, kr) with mt < m_tiles, kr < k_ranges; item kr covers chunks
+    // [kr * chunks_per_range, min(total, (kr+1) * chunks_per_range))
+    int m_tiles;
+    int64_t k_ranges;
+    int64_t chunks_per_range;
+    int group_chunks;          // chunks per TMEM accumulation group (RZ accumulate => keep short)
+    // B operand, KR mode
+    const float* P;            // [A][RP] or null
+    const float* Q;            // [B][RP]
+    // output: out[kr * sOk + m * sOm + n * sOn], n < n_valid
+    float* out;
+    int64_t sOk, sOm, sOn;
+    int n_valid;
+};
+
+struct TcStreamLaunch {
+    TcStreamParams p;
+    CUtensorMap x_map;         // see tc_stream.cu for the dims per layout
+    CUtensorMap bhi_map, blo_map;   // TC_B_MAT only
+    int rp;                    // 32 or 64
+    int x_layout;              // TcXLayout
+    int b_mode;                // TcBMode
+};
+
+// true when cuTensorMapEncodeTiled could be resolved (a driver is present)
+bool tc_available();
+// encode helper (returns TLB200_ECUDA on failure)
+int tc_encode_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, bool swizzle128);
+int tc_stream_launch(const TcStreamLaunch& l, cudaStream_t stream);
+// K extent of one chunk for a layout
+inline int tc_chunk_k(int x_layout) { return x_layout == TC_X_KMAJOR_1 ? 32 : 64; }
+int tc_group_chunks(int x_layout);
+
+}  // namespace tlb200

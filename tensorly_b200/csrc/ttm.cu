@@ -61,16 +61,25 @@ static int ttm_simt(const T* x, const TtmDims& d, const T* m, int64_t I, int64_t
     return launch_stream_gemm<T>(p, stream_gemm_tr_for(I, dtype), kmajor, stream);
 }
 
+// workspace one mode_dot needs (tcgen05 path: the pre-split hi/lo copies of the matrix)
+static size_t mode_dot_ws(const TtmDims& d, int64_t I, int dtype, int path) {
+    if (path != TLB200_PATH_SIMT && dtype == TLB200_F32 && ttm_tc_supported(d.L, d.J, d.T, I))
+        return ttm_tc_workspace(d.L, d.J, d.T, I);
+    return 0;
+}
+
 template <typename T>
 static int mode_dot_impl(const T* x, const int64_t* shape, int ndim, int mode, const T* m, int64_t I, int64_t mrs,
-                         int64_t mcs, T* out, int path, cudaStream_t stream) {
+                         int64_t mcs, T* out, void* ws, size_t ws_bytes, int path, cudaStream_t stream) {
     TtmDims d;
     int st = ttm_dims(shape, ndim, mode, &d);
     if (st) return st;
-    if (path != TLB200_PATH_SIMT && sizeof(T) == 4 && ttm_tc_supported(d.L, d.J, d.T, I)) {
+    if (path != TLB200_PATH_SIMT && sizeof(T) == 4 && ttm_tc_supported(d.L, d.J, d.T, I) &&
+        reinterpret_cast<uintptr_t>(x) % 16 == 0) {
+        if (!ws || ws_bytes < ttm_tc_workspace(d.L, d.J, d.T, I)) return TLB200_EWORKSPACE;
         set_last_path("tcgen05");
         return ttm_tc_launch(reinterpret_cast<const float*>(x), d.L, d.J, d.T, reinterpret_cast<const float*>(m), I,
-                             mrs, mcs, reinterpret_cast<float*>(out), stream);
+                             mrs, mcs, reinterpret_cast<float*>(out), ws, stream);
     }
     if (path == TLB200_PATH_TCGEN05) return TLB200_EUNSUPPORTED;
     set_last_path("simt");
@@ -81,19 +90,24 @@ static int mode_dot_impl(const T* x, const int64_t* shape, int ndim, int mode, c
 
 using namespace tlb200;
 
-extern "C" size_t tlb200_mode_dot_workspace_bytes(const int64_t*, int, int, int64_t, int, int) { return 0; }
+extern "C" size_t tlb200_mode_dot_workspace_bytes(const int64_t* shape, int ndim, int mode, int64_t rows_out, int dtype,
+                                                  int path) {
+    TtmDims d;
+    if (ttm_dims(shape, ndim, mode, &d) || !dtype_valid(dtype) || rows_out < 1) return 0;
+    return mode_dot_ws(d, rows_out, dtype, path);
+}
 
 extern "C" int tlb200_mode_dot(const void* x, const int64_t* shape, int ndim, int mode, const void* m, int64_t rows_out,
-                               int64_t m_row_stride, int64_t m_col_stride, int dtype, void* out, void* /*workspace*/,
-                               size_t /*workspace_bytes*/, int path, void* stream) {
+                               int64_t m_row_stride, int64_t m_col_stride, int dtype, void* out, void* workspace,
+                               size_t workspace_bytes, int path, void* stream) {
     if (!x || !m || !out || rows_out < 1 || !dtype_valid(dtype) || path < TLB200_PATH_AUTO || path > TLB200_PATH_TCGEN05)
         return TLB200_EINVAL;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == TLB200_F32)
         return mode_dot_impl<float>((const float*)x, shape, ndim, mode, (const float*)m, rows_out, m_row_stride,
-                                    m_col_stride, (float*)out, path, s);
+                                    m_col_stride, (float*)out, workspace, workspace_bytes, path, s);
     return mode_dot_impl<double>((const double*)x, shape, ndim, mode, (const double*)m, rows_out, m_row_stride,
-                                 m_col_stride, (double*)out, path, s);
+                                 m_col_stride, (double*)out, workspace, workspace_bytes, path, s);
 }
 
 // ---- chain -------------------------------------------------------------------------
@@ -122,11 +136,27 @@ static int64_t chain_max_intermediate(const int64_t* shape, int ndim, const int*
     return mx;
 }
 
+// largest per-step scratch (tcgen05 steps need the pre-split matrix)
+static size_t chain_step_ws(const int64_t* shape, int ndim, const int* modes, const int64_t* rows_out, int nmats, int dtype,
+                            int path) {
+    int64_t cur[TLB200_MAX_NDIM];
+    for (int i = 0; i < ndim; ++i) cur[i] = shape[i];
+    size_t mx = 0;
+    for (int k = 0; k < nmats; ++k) {
+        TtmDims d;
+        if (ttm_dims(cur, ndim, modes[k], &d)) return 0;
+        const size_t w = mode_dot_ws(d, rows_out[k], dtype, path);
+        if (w > mx) mx = w;
+        cur[modes[k]] = rows_out[k];
+    }
+    return align_up(mx, 256);
+}
+
 extern "C" size_t tlb200_multi_mode_dot_workspace_bytes(const int64_t* shape, int ndim, const int* modes,
-                                                        const int64_t* rows_out, int nmats, int dtype, int /*path*/) {
+                                                        const int64_t* rows_out, int nmats, int dtype, int path) {
     if (chain_check(shape, ndim, modes, rows_out, nmats) || !dtype_valid(dtype)) return 0;
     const int64_t mx = chain_max_intermediate(shape, ndim, modes, rows_out, nmats);
-    return 2 * align_up((size_t)mx * dtype_size(dtype), 256) + 256;
+    return 2 * align_up((size_t)mx * dtype_size(dtype), 256) + chain_step_ws(shape, ndim, modes, rows_out, nmats, dtype, path) + 512;
 }
 
 template <typename T>
@@ -134,8 +164,11 @@ static int chain_impl(const T* x, const int64_t* shape, int ndim, const int* mod
                       const int64_t* rows_out, const int64_t* mrs, const int64_t* mcs, int nmats, T* out,
                       void* workspace, int path, cudaStream_t stream) {
     const int64_t mx = chain_max_intermediate(shape, ndim, modes, rows_out, nmats);
+    const int dtype = sizeof(T) == 8 ? TLB200_F64 : TLB200_F32;
+    const size_t step_ws = chain_step_ws(shape, ndim, modes, rows_out, nmats, dtype, path);
     Carver ws(workspace);
     T* buf[2] = {ws.take<T>((size_t)mx), ws.take<T>((size_t)mx)};
+    void* scratch = step_ws ? ws.take<char>(step_ws) : nullptr;
     int64_t cur[TLB200_MAX_NDIM];
     int64_t total = 1;
     for (int i = 0; i < ndim; ++i) { cur[i] = shape[i]; total *= shape[i]; }
@@ -147,7 +180,8 @@ static int chain_impl(const T* x, const int64_t* shape, int ndim, const int* mod
     const T* src = x;
     for (int k = 0; k < nmats; ++k) {
         T* dst = (k == nmats - 1) ? out : buf[k & 1];
-        int st = mode_dot_impl<T>(src, cur, ndim, modes[k], mats[k], rows_out[k], mrs[k], mcs[k], dst, path, stream);
+        int st = mode_dot_impl<T>(src, cur, ndim, modes[k], mats[k], rows_out[k], mrs[k], mcs[k], dst, scratch, step_ws, path,
+                                  stream);
         if (st) return st;
         cur[modes[k]] = rows_out[k];
         src = dst;
@@ -168,7 +202,7 @@ extern "C" int tlb200_multi_mode_dot(const void* x, const int64_t* shape, int nd
         if (!mats[k]) return TLB200_EINVAL;
     if (workspace_bytes < tlb200_multi_mode_dot_workspace_bytes(shape, ndim, modes, rows_out, nmats, dtype, path))
         return TLB200_EWORKSPACE;
-    if (nmats > 1 && (!workspace || reinterpret_cast<uintptr_t>(workspace) % 256)) return TLB200_EINVAL;
+    if (nmats > 0 && (!workspace || reinterpret_cast<uintptr_t>(workspace) % 256)) return TLB200_EINVAL;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == TLB200_F32)
         return chain_impl<float>((const float*)x, shape, ndim, modes, reinterpret_cast<const float* const*>(mats), rows_out,

@@ -1,8 +1,133 @@
-// tcgen05 TTM path (placeholder until the kernel lands: every call takes the SIMT path).
+// TTM (mode_dot) on the tcgen05 stream-GEMM engine (tc_stream.cu).
+//
+//   out[l, i, t] = sum_j M[i, j] * X[l, j, t]         X viewed in place as [L, J, T]
+//
+//   T >= 32 : rows of the MMA = t (contiguous), contraction = j: per l, tiles of 64 j-rows x 128 t
+//             (TC_X_MMAJOR); one work item per (l, t-tile), written straight into out[l, :, t-tile].
+//   T == 1  : rows = l, contraction = j contiguous (TC_X_KMAJOR_*): out[l, i].
+// The small matrix is split once per call into tf32 hi / lo parts (zero-padded [RP][Kpad], K-major)
+// by a tiny prep kernel; the B-producer warp then streams its K slices with TMA.
 #include "ttm_tc.cuh"
+#include "tc_stream.cuh"
 
 namespace tlb200 {
-bool ttm_tc_supported(int64_t, int64_t, int64_t, int64_t) { return false; }
-int ttm_tc_launch(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, float*,
-                  cudaStream_t) { return TLB200_EUNSUPPORTED; }
+namespace {
+
+__global__ void __launch_bounds__(256)
+split_matrix_kernel(const float* __restrict__ m, int64_t I, int64_t J, int64_t mrs, int64_t mcs, int RP, int64_t Kpad,
+                    float* __restrict__ hi, float* __restrict__ lo) {
+    const int64_t total = (int64_t)RP * Kpad;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / Kpad, j = e - i * Kpad;
+        const float v = (i < I && j < J) ? m[i * mrs + j * mcs] : 0.f;
+        const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        hi[e] = h;
+        lo[e] = v - h;
+    }
+}
+
+struct TtmGeom {
+    int layout;
+    int64_t M, A, B;       // engine extents: rows, batch, contraction
+    int ks;
+    int64_t kpad;
+    int rp;
+};
+
+bool geom(int64_t L, int64_t J, int64_t T, int64_t I, TtmGeom* g) {
+    if (I > 64 || I < 1) return false;
+    g->rp = I <= 32 ? 32 : 64;
+    if (T >= 32) {
+        if (T % 4) return false;                 // TMA strides: multiples of 16 bytes
+        g->layout = TC_X_MMAJOR; g->M = T; g->A = L; g->B = J;
+    } else if (T == 1) {
+        if (J % 4) return false;
+        g->layout = (J % 32 == 0) ? TC_X_KMAJOR_2 : TC_X_KMAJOR_1; g->M = L; g->A = 1; g->B = J;
+    } else {
+        return false;
+    }
+    if (g->M >= (1LL << 31) || g->A >= (1LL << 31) || g->B >= (1LL << 31)) return false;
+    g->ks = tc_chunk_k(g->layout);
+    g->kpad = ceil_div(J, g->ks) * g->ks;
+    return true;
+}
+
+}  // namespace
+
+bool ttm_tc_supported(int64_t L, int64_t J, int64_t T, int64_t I) {
+    TtmGeom g;
+    if (!geom(L, J, T, I, &g)) return false;
+    if (L * J * T < (1 << 18) || g.M < 32 || J < 16) return false;   // launch-bound sizes: SIMT
+    return tc_available();
+}
+
+size_t ttm_tc_workspace(int64_t L, int64_t J, int64_t T, int64_t I) {
+    TtmGeom g;
+    if (!geom(L, J, T, I, &g)) return 0;
+    return 2 * align_up((size_t)g.rp * g.kpad * 4, 256) + 256;
+}
+
+int ttm_tc_launch(const float* x, int64_t L, int64_t J, int64_t T, const float* m, int64_t I, int64_t mrs, int64_t mcs,
+                  float* out, void* workspace, cudaStream_t stream) {
+    TtmGeom g;
+    if (!geom(L, J, T, I, &g) || !workspace) return TLB200_EUNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(x) % 16) return TLB200_EUNSUPPORTED;
+    Carver ws(workspace);
+    float* bhi = ws.take<float>((size_t)g.rp * g.kpad);
+    float* blo = ws.take<float>((size_t)g.rp * g.kpad);
+    {
+        const int64_t total = (int64_t)g.rp * g.kpad;
+        int64_t blocks = ceil_div(total, 256);
+        if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+        split_matrix_kernel<<<(unsigned)blocks, 256, 0, stream>>>(m, I, J, mrs, mcs, g.rp, g.kpad, bhi, blo);
+        TLB_CHECK_LAUNCH();
+    }
+    TcStreamLaunch l;
+    l.rp = g.rp;
+    l.x_layout = g.layout;
+    l.b_mode = TC_B_MAT;
+    uint64_t dims[4], strides[3];
+    uint32_t box[4];
+    int st;
+    if (g.layout == TC_X_MMAJOR) {           // X[l][j][t]: dims (T, J, L)
+        dims[0] = T; dims[1] = J; dims[2] = L;
+        strides[0] = (uint64_t)T * 4; strides[1] = (uint64_t)J * T * 4;
+        box[0] = 128; box[1] = 64; box[2] = 1;
+        st = tc_encode_map(&l.x_map, x, 3, dims, strides, box, false);
+    } else if (g.layout == TC_X_KMAJOR_2) {  // X[l][j]: dims (32, J/32, L, 1)
+        dims[0] = 32; dims[1] = J / 32; dims[2] = L; dims[3] = 1;
+        strides[0] = 128; strides[1] = (uint64_t)J * 4; strides[2] = (uint64_t)J * 4 * L;
+        box[0] = 32; box[1] = 2; box[2] = 128; box[3] = 1;
+        st = tc_encode_map(&l.x_map, x, 4, dims, strides, box, true);
+    } else {                                 // X[l][j]: dims (J, L, 1)
+        dims[0] = J; dims[1] = L; dims[2] = 1;
+        strides[0] = (uint64_t)J * 4; strides[1] = (uint64_t)J * 4 * L;
+        box[0] = 32; box[1] = 128; box[2] = 1;
+        st = tc_encode_map(&l.x_map, x, 3, dims, strides, box, true);
+    }
+    if (st) return st;
+    {
+        uint64_t bd[2] = {(uint64_t)g.kpad, (uint64_t)g.rp}, bs[1] = {(uint64_t)g.kpad * 4};
+        uint32_t bb[2] = {32, (uint32_t)g.rp};
+        st = tc_encode_map(&l.bhi_map, bhi, 2, bd, bs, bb, true);
+        if (st) return st;
+        st = tc_encode_map(&l.blo_map, blo, 2, bd, bs, bb, true);
+        if (st) return st;
+    }
+    TcStreamParams& p = l.p;
+    p.M = g.M; p.A = g.A; p.B = g.B;
+    p.chunks_per_a = ceil_div(g.B, g.ks);
+    p.total_chunks = g.A * p.chunks_per_a;
+    p.m_tiles = (int)ceil_div(g.M, 128);
+    p.k_ranges = g.A;                         // one item per (row tile, batch): all of K
+    p.chunks_per_range = p.chunks_per_a;
+    p.group_chunks = tc_group_chunks(g.layout);
+    p.P = nullptr; p.Q = nullptr;
+    p.out = out;
+    if (g.layout == TC_X_MMAJOR) { p.sOk = I * T; p.sOm = 1; p.sOn = T; }
+    else                         { p.sOk = 0; p.sOm = I; p.sOn = 1; }
+    p.n_valid = (int)I;
+    return tc_stream_launch(l, stream);
+}
+
 }  // namespace tlb200
