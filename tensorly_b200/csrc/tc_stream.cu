@@ -245,6 +245,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                     const uint32_t a_hi = tmem_base + a_col0 + ar.idx * C::A_COLS;
                     const uint32_t a_lo = a_hi + KS;
                     const uint32_t bbase = smem_u32(b_smem + br.idx * C::B_STAGE);
+                    if (!(p.debug & 2))
 #pragma unroll
                     for (int ks = 0; ks < KS / 8; ++ks) {
                         const uint32_t sub = (ks >> 2) * C::B_SUB + (ks & 3) * 32;
@@ -323,7 +324,8 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 tc_fence_after();
                 const uint32_t abase = lane_addr + a_col0 + ar.idx * C::A_COLS;
                 uint32_t h[32];
-                if constexpr (KS == 32) {
+                if (p.debug & 4) {
+                } else if constexpr (KS == 32) {
 #pragma unroll
                     for (int k = 0; k < 32; ++k) h[k] = ta[k] & 0xFFFFE000u;                     // exact tf32 part
                     TLB_TMEM_ST32(abase, h);
@@ -432,6 +434,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                     mbar_wait(&b_empty[br.idx], br.phase ^ 1u);
                     unsigned char* bt = b_smem + br.idx * C::B_STAGE;
+                    if (!(p.debug & 1))
 #pragma unroll
                     for (int ko = 0; ko < KO; ++ko) {
                         const int k = ko * 32 + lane;                         // lane = k within the 128-byte line
@@ -477,6 +480,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 const uint32_t buf = G & 1u;
                 mbar_wait(&d_full[buf], (G >> 1) & 1u);
                 tc_fence_after();
+                if (!(p.debug & 8))
 #pragma unroll
                 for (int c0 = 0; c0 < RP; c0 += 32) {
                     uint32_t r[32];
@@ -596,7 +600,11 @@ int tc_group_chunks(int x_layout) {
     return g < 1 ? 1 : g;
 }
 
-int tc_stream_launch(const TcStreamLaunch& l, cudaStream_t stream) {
+int tc_stream_launch(const TcStreamLaunch& l_in, cudaStream_t stream) {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("TLB200_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    TcStreamLaunch l = l_in;
+    l.p.debug = dbg;
     if (l.rp == 32) return launch_xl<32>(l, stream);
     if (l.rp == 64) return launch_xl<64>(l, stream);
     return TLB200_EUNSUPPORTED;

@@ -40,6 +40,7 @@ struct TcStreamParams {
     float* out;
     int64_t sOk, sOm, sOn;
     int n_valid;
+    int debug;                 // TLB200_TC_DEBUG bitmask (perf triage only): 1 skip KR math, 2 skip MMAs, 4 skip TMEM stores, 8 skip epilogue loads
 };
 
 struct TcStreamLaunch {
