@@ -84,7 +84,7 @@ int mttkrp_tc_launch(const float* x, const tlb200_mttkrp_plan_t& pl, int64_t /*r
     p.m_tiles = (int)ceil_div(pl.J, 128);
     p.k_ranges = pl.splits;
     p.chunks_per_range = ceil_div(p.total_chunks, pl.splits);
-    p.group_chunks = tc_group_chunks(l.x_layout);
+    p.group_units = tc_group_units();
     p.P = P; p.Q = Q;
     p.out = partial;
     p.sOk = pl.J * pl.rank_padded; p.sOm = pl.rank_padded; p.sOn = 1;

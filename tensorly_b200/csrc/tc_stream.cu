@@ -12,9 +12,15 @@
 // term ~2^-22): three MMAs per K step.
 //
 // Why short accumulation groups: the tensor core accumulates with round-toward-zero
-// (measured), a systematic ~2^-24 relative loss per MMA.  The TMEM accumulator is therefore
-// drained every `group_chunks` tiles into fp32 registers (round-to-nearest adds) by dedicated
-// epilogue warps while the MMAs continue into the second TMEM accumulator.
+// (measured), a systematic ~2^-24 relative loss per MMA.  The TMEM accumulators are therefore
+// drained every `group_units` 32-element K units into fp32 registers (round-to-nearest adds)
+// by dedicated epilogue warps while the MMAs continue into the second accumulator set.
+//
+// Why two MMAs of different width per K step: a chain of small dependent MMAs (N = 32) runs
+// at the tensor pipe's latency (~100 clk each, measured), not its throughput.  The three
+// products are therefore issued as  D1[128 x 2R] += A_hi * [B_hi | B_lo]  and
+// D2[128 x R] += A_lo * B_hi : fewer, wider instructions on two independent accumulator
+// chains.  Only the hi*hi columns carry a significant truncation error.
 //
 // Why the A operand goes through TMEM: with A read from shared memory the tile would cross
 // the 128 B/clk shared-memory port six times (TMA write, split read+write, three MMA reads);
@@ -128,23 +134,24 @@ struct Ring {
 // ---- compile-time configuration per (RP, X layout) -------------------------------------
 template <int RP, int XL>
 struct Cfg {
-    static constexpr int KS = XL == TC_X_KMAJOR_1 ? 32 : 64;        // K extent of one chunk
-    static constexpr int KO = KS / 32;                              // 128-byte lines per row / B sub-tiles
+    static constexpr int KS = XL == TC_X_KMAJOR_1 ? 32 : 64;        // K extent of one X stage
+    static constexpr int KO = KS / 32;                              // 32-element units per X stage
     static constexpr int X_STAGE = TM * KS * 4;
     static constexpr int XS = KS == 32 ? 6 : (RP == 64 ? 3 : 4);
-    static constexpr int AS = KS == 32 ? 4 : 3;
-    static constexpr int BS = (KS == 64 && RP == 64) ? 2 : 3;
-    static constexpr int B_SUB = RP * 128;                          // one [RP rows x 128 B] sub-tile
-    static constexpr int B_STAGE = 2 * KO * B_SUB;                  // [hi|lo][ko][RP][128 B]
-    static constexpr int STAGE_F = KS * RP;                         // floats in one Q staging buffer
+    static constexpr int D_COLS = 3 * RP;                           // per accumulator set: D1 [hh | hl] (2RP) + D2 [lh] (RP)
+    static constexpr int A_COLS = 64;                               // TMEM columns per A unit: [hi 32 | lo 32]
+    static constexpr int AS = (512 - 2 * D_COLS) / A_COLS >= 5 ? 4 : (512 - 2 * D_COLS) / A_COLS;
+    static constexpr int B_UNIT = 2 * RP * 128;                     // [hi RP rows | lo RP rows] x 128 B, K-major SW128
+    static constexpr int BS = RP == 64 ? 4 : 6;
+    static constexpr int STAGE_F = 32 * RP;                         // floats in one Q staging buffer (one unit)
     static constexpr int OFF_X = 0;
     static constexpr int OFF_B = OFF_X + XS * X_STAGE;
-    static constexpr int OFF_STAGE = OFF_B + BS * B_STAGE;
+    static constexpr int OFF_STAGE = OFF_B + BS * B_UNIT;
     static constexpr int OFF_BAR = OFF_STAGE + 2 * STAGE_F * 4;
     static constexpr int NUM_BARS = 2 * XS + 2 * AS + 2 * BS + 4;
     static constexpr int SMEM = OFF_BAR + NUM_BARS * 8 + 16;
-    static constexpr int A_COLS = 2 * KS;                           // TMEM columns per A stage: [hi KS | lo KS]
-    static constexpr int TMEM_COLS = 2 * RP + AS * A_COLS;
+    static constexpr int TMEM_COLS = 2 * D_COLS + AS * A_COLS;
+    static_assert(AS >= 2, "need at least two A units");
     static_assert(TMEM_COLS <= 512, "TMEM budget");
     static_assert(SMEM + 1024 <= 227 * 1024, "smem budget");
 };
@@ -197,7 +204,9 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t a_col0 = 2 * RP;      // TMEM: D0 [0,RP) D1 [RP,2RP) then AS stages of [hi KS | lo KS]
+    // TMEM columns: accumulator set 0 [0, 3RP), set 1 [3RP, 6RP), then AS A-operand units of [hi 32 | lo 32]
+    const uint32_t a_col0 = 2 * C::D_COLS;
+    const int GU = p.group_units;
 
     if (warp == 0) {
         // ================= TMA producer of X tiles =================
@@ -217,7 +226,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                     unsigned char* dst = x_smem + xr.idx * C::X_STAGE;
                     if constexpr (XL == TC_X_KMAJOR_1)      tma_load_3d(dst, &xmap, &x_full[xr.idx], bc * 32, m0, a);
                     else if constexpr (XL == TC_X_KMAJOR_2) tma_load_4d(dst, &xmap, &x_full[xr.idx], 0, bc * 2, m0, a);
-                    else                          tma_load_3d(dst, &xmap, &x_full[xr.idx], m0, bc * 64, a);
+                    else                                    tma_load_3d(dst, &xmap, &x_full[xr.idx], m0, bc * 64, a);
                     xr.advance(XS);
                     if (++bc == (int)p.chunks_per_a) { bc = 0; ++a; }
                 }
@@ -226,40 +235,40 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            constexpr uint32_t idesc = idesc_tf32(TM, RP);
+            constexpr uint32_t idesc1 = idesc_tf32(TM, 2 * RP);   // A_hi x [B_hi | B_lo]
+            constexpr uint32_t idesc2 = idesc_tf32(TM, RP);       // A_lo x B_hi
             Ring ar, br;
             uint32_t G = 0;          // global accumulation-group counter
             for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
                 const int64_t kr = it / p.m_tiles;
                 const int64_t c_begin = kr * p.chunks_per_range;
                 const int64_t c_end = min(p.total_chunks, c_begin + p.chunks_per_range);
-                const int n = (int)(c_end - c_begin);
-                int cg = 0;
+                const int n = (int)(c_end - c_begin) * KO;       // 32-element units of this item
+                int ug = 0;
                 for (int i = 0; i < n; ++i) {
                     const uint32_t buf = G & 1u;
-                    if (cg == 0 && G >= 2) mbar_wait(&d_empty[buf], ((G >> 1) - 1) & 1u);
+                    if (ug == 0 && G >= 2) mbar_wait(&d_empty[buf], ((G >> 1) - 1) & 1u);
                     mbar_wait(&a_full[ar.idx], ar.phase);
                     mbar_wait(&b_full[br.idx], br.phase);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + buf * RP;
+                    const uint32_t d1 = tmem_base + buf * C::D_COLS;
+                    const uint32_t d2 = d1 + 2 * RP;
                     const uint32_t a_hi = tmem_base + a_col0 + ar.idx * C::A_COLS;
-                    const uint32_t a_lo = a_hi + KS;
-                    const uint32_t bbase = smem_u32(b_smem + br.idx * C::B_STAGE);
+                    const uint32_t a_lo = a_hi + 32;
+                    const uint32_t bbase = smem_u32(b_smem + br.idx * C::B_UNIT);
                     if (!(p.debug & 2))
 #pragma unroll
-                    for (int ks = 0; ks < KS / 8; ++ks) {
-                        const uint32_t sub = (ks >> 2) * C::B_SUB + (ks & 3) * 32;
-                        const uint64_t dbh = desc_kmajor_sw128(bbase + sub);
-                        const uint64_t dbl = desc_kmajor_sw128(bbase + KO * C::B_SUB + sub);
-                        mma_ts_tf32(d_tmem, a_hi + ks * 8, dbh, idesc, (cg == 0 && ks == 0) ? 0u : 1u);
-                        mma_ts_tf32(d_tmem, a_lo + ks * 8, dbh, idesc, 1u);
-                        mma_ts_tf32(d_tmem, a_hi + ks * 8, dbl, idesc, 1u);
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t db = desc_kmajor_sw128(bbase + ks * 32);
+                        const uint32_t accf = (ug == 0 && ks == 0) ? 0u : 1u;
+                        mma_ts_tf32(d1, a_hi + ks * 8, db, idesc1, accf);
+                        mma_ts_tf32(d2, a_lo + ks * 8, db, idesc2, accf);
                     }
                     tc_commit(&a_empty[ar.idx]);
                     tc_commit(&b_empty[br.idx]);
                     ar.advance(AS);
                     br.advance(BS);
-                    if (++cg == p.group_chunks || i == n - 1) { tc_commit(&d_full[buf]); ++G; cg = 0; }
+                    if (++ug == GU || i == n - 1) { tc_commit(&d_full[buf]); ++G; ug = 0; }
                 }
             }
         }
@@ -320,42 +329,41 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 }
                 mbar_arrive(&x_empty[xr.idx]);
                 xr.advance(XS);
-                mbar_wait(&a_empty[ar.idx], ar.phase ^ 1u);
-                tc_fence_after();
-                const uint32_t abase = lane_addr + a_col0 + ar.idx * C::A_COLS;
                 uint32_t h[32];
-                if (p.debug & 4) {
-                } else if constexpr (KS == 32) {
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) h[k] = ta[k] & 0xFFFFE000u;                     // exact tf32 part
-                    TLB_TMEM_ST32(abase, h);
+                for (int u = 0; u < KO; ++u) {
+                    mbar_wait(&a_empty[ar.idx], ar.phase ^ 1u);
+                    tc_fence_after();
+                    const uint32_t abase = lane_addr + a_col0 + ar.idx * C::A_COLS;
+                    if (!(p.debug & 4)) {
+                        if (KS == 32 || u == 0) {
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) h[k] = __float_as_uint(__uint_as_float(ta[k]) - __uint_as_float(h[k]));
-                    TLB_TMEM_ST32(abase + KS, h);                                                // exact remainder
-                } else {
+                            for (int k = 0; k < 32; ++k) h[k] = ((KS == 64 && flip) ? tb[k & (KS == 64 ? 31 : 0)] : ta[k]) & 0xFFFFE000u;
+                            TLB_TMEM_ST32(abase, h);                                         // exact tf32 part
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) h[k] = (flip ? tb[k] : ta[k]) & 0xFFFFE000u;
-                    TLB_TMEM_ST32(abase, h);
+                            for (int k = 0; k < 32; ++k)
+                                h[k] = __float_as_uint(__uint_as_float((KS == 64 && flip) ? tb[k & (KS == 64 ? 31 : 0)] : ta[k]) -
+                                                       __uint_as_float(h[k]));
+                            TLB_TMEM_ST32(abase + 32, h);                                    // exact remainder
+                        } else {
 #pragma unroll
-                    for (int k = 0; k < 32; ++k)
-                        h[k] = __float_as_uint(__uint_as_float(flip ? tb[k] : ta[k]) - __uint_as_float(h[k]));
-                    TLB_TMEM_ST32(abase + KS, h);
+                            for (int k = 0; k < 32; ++k) h[k] = (flip ? ta[k] : tb[k & (KS == 64 ? 31 : 0)]) & 0xFFFFE000u;
+                            TLB_TMEM_ST32(abase, h);
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) h[k] = (flip ? ta[k] : tb[k]) & 0xFFFFE000u;
-                    TLB_TMEM_ST32(abase + 32, h);
-#pragma unroll
-                    for (int k = 0; k < 32; ++k)
-                        h[k] = __float_as_uint(__uint_as_float(flip ? ta[k] : tb[k]) - __uint_as_float(h[k]));
-                    TLB_TMEM_ST32(abase + KS + 32, h);
+                            for (int k = 0; k < 32; ++k)
+                                h[k] = __float_as_uint(__uint_as_float(flip ? ta[k] : tb[k & (KS == 64 ? 31 : 0)]) - __uint_as_float(h[k]));
+                            TLB_TMEM_ST32(abase + 32, h);
+                        }
+                    }
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                    mbar_arrive(&a_full[ar.idx]);
+                    ar.advance(AS);
                 }
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                tc_fence_before();
-                mbar_arrive(&a_full[ar.idx]);
-                ar.advance(AS);
             }
         }
     } else if (warp < 10) {
-        // ================= B producer =================
+        // ================= B producer (one 32-element K unit at a time) =================
         if constexpr (BM == TC_B_MAT) {
             if (warp == 6 && lane == 0) {
                 Ring br;
@@ -365,15 +373,15 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                     const int64_t c_end = min(p.total_chunks, c_begin + p.chunks_per_range);
                     int bc = (int)(c_begin % p.chunks_per_a);
                     for (int64_t c = c_begin; c < c_end; ++c) {
-                        mbar_wait(&b_empty[br.idx], br.phase ^ 1u);
-                        mbar_expect_tx(&b_full[br.idx], C::B_STAGE);
-                        unsigned char* dst = b_smem + br.idx * C::B_STAGE;
 #pragma unroll
-                        for (int ko = 0; ko < KO; ++ko) {
-                            tma_load_2d(dst + ko * C::B_SUB, &bhi_map, &b_full[br.idx], bc * KS + ko * 32, 0);
-                            tma_load_2d(dst + (KO + ko) * C::B_SUB, &blo_map, &b_full[br.idx], bc * KS + ko * 32, 0);
+                        for (int u = 0; u < KO; ++u) {
+                            mbar_wait(&b_empty[br.idx], br.phase ^ 1u);
+                            mbar_expect_tx(&b_full[br.idx], C::B_UNIT);
+                            unsigned char* dst = b_smem + br.idx * C::B_UNIT;
+                            tma_load_2d(dst, &bhi_map, &b_full[br.idx], bc * KS + u * 32, 0);
+                            tma_load_2d(dst + RP * 128, &blo_map, &b_full[br.idx], bc * KS + u * 32, 0);
+                            br.advance(BS);
                         }
-                        br.advance(BS);
                         if (++bc == (int)p.chunks_per_a) bc = 0;
                     }
                 }
@@ -381,15 +389,14 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         } else {
             const int kt = tid - 192;             // 0..127
             const int kw = kt >> 5;               // warp within the group
-            constexpr int F4_PER_THREAD = (KS * RP / 4) / 128;
+            constexpr int F4_PER_THREAD = (32 * RP / 4) / 128;
             constexpr int F4_PER_ROW = RP / 4;
             constexpr int R_PER_WARP = RP / 4;
             float4 qreg[F4_PER_THREAD];
             float preg[R_PER_WARP];
             Ring br;
             int sbuf = 0;
-            auto load_q = [&](int bc) {
-                const int64_t b0 = (int64_t)bc * KS;
+            auto load_q = [&](int64_t b0) {
 #pragma unroll
                 for (int f = 0; f < F4_PER_THREAD; ++f) {
                     const int idx = kt + f * 128;
@@ -402,11 +409,12 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 const int64_t kr = it / p.m_tiles;
                 const int64_t c_begin = kr * p.chunks_per_range;
                 const int64_t c_end = min(p.total_chunks, c_begin + p.chunks_per_range);
-                const int n = (int)(c_end - c_begin);
+                const int n = (int)(c_end - c_begin) * KO;      // units
                 int a = (int)(c_begin / p.chunks_per_a);
-                int bc = (int)(c_begin - (int64_t)a * p.chunks_per_a);
+                int bu = (int)(c_begin - (int64_t)a * p.chunks_per_a) * KO;     // unit index within this `a`
+                const int units_per_a = (int)p.chunks_per_a * KO;
                 int a_loaded = -1;
-                if (n > 0) load_q(bc);
+                if (n > 0) load_q((int64_t)bu * 32);
                 for (int i = 0; i < n; ++i) {
                     float* st = stage + sbuf * C::STAGE_F;
                     sbuf ^= 1;
@@ -427,36 +435,34 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                         for (int j = 0; j < R_PER_WARP; ++j) preg[j] = p.P ? __ldg(p.P + (int64_t)a * RP + kw + 4 * j) : 1.0f;
                         a_loaded = a;
                     }
-                    // advance to the next chunk's coordinates and prefetch its Q rows from L2
-                    int bc_n = bc + 1, a_n = a;
-                    if (bc_n == (int)p.chunks_per_a) { bc_n = 0; ++a_n; }
-                    if (i + 1 < n) load_q(bc_n);
+                    // advance to the next unit's coordinates and prefetch its Q rows from L2
+                    int bu_n = bu + 1, a_n = a;
+                    if (bu_n == units_per_a) { bu_n = 0; ++a_n; }
+                    if (i + 1 < n) load_q((int64_t)bu_n * 32);
                     asm volatile("bar.sync 1, 128;" ::: "memory");
+                    // all column reads first (they cannot be reordered across the stores below by the compiler)
+                    float qv[R_PER_WARP];
+                    const float* srow = st + lane * RP;                   // lane = k within the unit
+#pragma unroll
+                    for (int j = 0; j < R_PER_WARP; ++j) qv[j] = srow[(kw + 4 * j + lane) & (RP - 1)];
                     mbar_wait(&b_empty[br.idx], br.phase ^ 1u);
-                    unsigned char* bt = b_smem + br.idx * C::B_STAGE;
+                    unsigned char* bhi = b_smem + br.idx * C::B_UNIT;
+                    unsigned char* blo = bhi + RP * 128;
                     if (!(p.debug & 1))
 #pragma unroll
-                    for (int ko = 0; ko < KO; ++ko) {
-                        const int k = ko * 32 + lane;                         // lane = k within the 128-byte line
-                        const float* srow = st + k * RP;
-                        unsigned char* bhi = bt + ko * C::B_SUB;
-                        unsigned char* blo = bt + (KO + ko) * C::B_SUB;
-#pragma unroll
-                        for (int j = 0; j < R_PER_WARP; ++j) {
-                            const int r = kw + 4 * j;
-                            const float qv = srow[(r + k) & (RP - 1)];
-                            const float krv = __fmul_rn(preg[j], qv);
-                            const uint32_t h = __float_as_uint(krv) & 0xFFFFE000u;
-                            const float lo = krv - __uint_as_float(h);
-                            const uint32_t off = r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4;
-                            *reinterpret_cast<uint32_t*>(bhi + off) = h;
-                            *reinterpret_cast<float*>(blo + off) = lo;
-                        }
+                    for (int j = 0; j < R_PER_WARP; ++j) {
+                        const int r = kw + 4 * j;
+                        const float krv = __fmul_rn(preg[j], qv[j]);
+                        const uint32_t hbits = __float_as_uint(krv) & 0xFFFFE000u;
+                        const float lo = krv - __uint_as_float(hbits);
+                        const uint32_t off = r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4;
+                        *reinterpret_cast<uint32_t*>(bhi + off) = hbits;
+                        *reinterpret_cast<float*>(blo + off) = lo;
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core reads
                     mbar_arrive(&b_full[br.idx]);
                     br.advance(BS);
-                    bc = bc_n; a = a_n;
+                    bu = bu_n; a = a_n;
                 }
             }
         }
@@ -471,8 +477,8 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             const int64_t kr = it / p.m_tiles;
             const int64_t c_begin = kr * p.chunks_per_range;
             const int64_t c_end = min(p.total_chunks, c_begin + p.chunks_per_range);
-            const int n = (int)(c_end - c_begin);
-            const int ngroups = (n + p.group_chunks - 1) / p.group_chunks;
+            const int n = (int)(c_end - c_begin) * KO;
+            const int ngroups = (n + GU - 1) / GU;
             float acc[RP];
 #pragma unroll
             for (int c = 0; c < RP; ++c) acc[c] = 0.f;
@@ -482,12 +488,15 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 tc_fence_after();
                 if (!(p.debug & 8))
 #pragma unroll
-                for (int c0 = 0; c0 < RP; c0 += 32) {
-                    uint32_t r[32];
-                    TLB_TMEM_LD32(lane_addr + buf * RP + c0, r);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                for (int part = 0; part < 3; ++part) {        // hh, hl, lh column blocks of this set
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) acc[c0 + c] += __uint_as_float(r[c]);
+                    for (int c0 = 0; c0 < RP; c0 += 32) {
+                        uint32_t r[32];
+                        TLB_TMEM_LD32(lane_addr + buf * C::D_COLS + part * RP + c0, r);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) acc[c0 + c] += __uint_as_float(r[c]);
+                    }
                 }
                 tc_fence_before();
                 mbar_arrive(&d_empty[buf]);
@@ -586,18 +595,16 @@ int tc_encode_map(CUtensorMap* map, const float* base, int rank, const uint64_t*
     return r == CUDA_SUCCESS ? TLB200_OK : TLB200_ECUDA;
 }
 
-int tc_group_chunks(int x_layout) {
-    // accumulation-group length in units of 32 contraction elements (12 MMAs each); measured error
-    // ~7e-7 per unit (probes + scripts/tc_check.py), so 4 units keep MTTKRP/TTM at ~3e-6
+int tc_group_units() {
+    // accumulation-group length in 32-element K units.  Only the hi*hi products carry a significant
+    // round-toward-zero loss (4 MMAs per unit, ~6e-8 each, measured): 8 units keep MTTKRP/TTM near 2e-6.
     static int units = -1;
     if (units < 0) {
         const char* e = getenv("TLB200_TC_FLUSH");
-        units = e ? atoi(e) : 4;
+        units = e ? atoi(e) : 8;
         if (units < 1) units = 1;
     }
-    const int per_chunk = tc_chunk_k(x_layout) / 32;
-    const int g = units / per_chunk;
-    return g < 1 ? 1 : g;
+    return units;
 }
 
 int tc_stream_launch(const TcStreamLaunch& l_in, cudaStream_t stream) {

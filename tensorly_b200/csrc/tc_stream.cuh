@@ -32,7 +32,7 @@ struct TcStreamParams {
     int m_tiles;
     int64_t k_ranges;
     int64_t chunks_per_range;
-    int group_chunks;          // chunks per TMEM accumulation group (RZ accumulate => keep short)
+    int group_units;           // 32-element K units per TMEM accumulation group (RZ accumulate => keep short)
     // B operand, KR mode
     const float* P;            // [A][RP] or null
     const float* Q;            // [B][RP]
@@ -60,6 +60,6 @@ int tc_encode_map(CUtensorMap* map, const float* base, int rank, const uint64_t*
 int tc_stream_launch(const TcStreamLaunch& l, cudaStream_t stream);
 // K extent of one chunk for a layout
 inline int tc_chunk_k(int x_layout) { return x_layout == TC_X_KMAJOR_1 ? 32 : 64; }
-int tc_group_chunks(int x_layout);
+int tc_group_units();
 
 }  // namespace tlb200

@@ -121,7 +121,7 @@ int ttm_tc_launch(const float* x, int64_t L, int64_t J, int64_t T, const float* 
     p.m_tiles = (int)ceil_div(g.M, 128);
     p.k_ranges = g.A;                         // one item per (row tile, batch): all of K
     p.chunks_per_range = p.chunks_per_a;
-    p.group_chunks = tc_group_chunks(g.layout);
+    p.group_units = tc_group_units();
     p.P = nullptr; p.Q = nullptr;
     p.out = out;
     if (g.layout == TC_X_MMAJOR) { p.sOk = I * T; p.sOm = 1; p.sOn = T; }
