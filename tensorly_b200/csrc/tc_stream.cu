@@ -18,9 +18,11 @@
 //
 // Why two MMAs of different width per K step: a chain of small dependent MMAs (N = 32) runs
 // at the tensor pipe's latency (~100 clk each, measured), not its throughput.  The three
-// products are therefore issued as  D1[128 x 2R] += A_hi * [B_hi | B_lo]  and
-// D2[128 x R] += A_lo * B_hi : fewer, wider instructions on two independent accumulator
-// chains.  Only the hi*hi columns carry a significant truncation error.
+// products are therefore issued as  D[128 x 2R] += A_hi * [B_hi | B_lo]  followed by
+// D[:, R:2R] += A_lo * B_hi : two instructions per K step, the wide one covering two
+// products (measured cost per MMA: max(48, N/2) clk for M=128, K=8 — probes/mma_rate.cu).
+// The hi*hi columns carry the only significant truncation error; the two small cross terms
+// share the other R columns.
 //
 // Why the A operand goes through TMEM: with A read from shared memory the tile would cross
 // the 128 B/clk shared-memory port six times (TMA write, split read+write, three MMA reads);
@@ -137,17 +139,17 @@ struct Cfg {
     static constexpr int KS = XL == TC_X_KMAJOR_1 ? 32 : 64;        // K extent of one X stage
     static constexpr int KO = KS / 32;                              // 32-element units per X stage
     static constexpr int X_STAGE = TM * KS * 4;
-    static constexpr int XS = KS == 32 ? 6 : (RP == 64 ? 3 : 4);
-    static constexpr int D_COLS = 3 * RP;                           // per accumulator set: D1 [hh | hl] (2RP) + D2 [lh] (RP)
+    static constexpr int XS = KS == 32 ? 6 : 4;
+    static constexpr int D_COLS = 2 * RP;                           // per accumulator set: [hi*hi (RP) | hi*lo + lo*hi (RP)]
     static constexpr int A_COLS = 64;                               // TMEM columns per A unit: [hi 32 | lo 32]
-    static constexpr int AS = (512 - 2 * D_COLS) / A_COLS >= 5 ? 4 : (512 - 2 * D_COLS) / A_COLS;
+    static constexpr int AS = 4;
     static constexpr int B_UNIT = 2 * RP * 128;                     // [hi RP rows | lo RP rows] x 128 B, K-major SW128
-    static constexpr int BS = RP == 64 ? 4 : 6;
-    static constexpr int STAGE_F = 32 * RP;                         // floats in one Q staging buffer (one unit)
+    static constexpr int BS = RP == 64 ? 4 : 8;                     // power of two (slot = unit % BS)
+    static constexpr int STAGE_F = 32 * RP + RP;                    // per KR warp: rotated Q staging [32][RP] + P row [RP]
     static constexpr int OFF_X = 0;
     static constexpr int OFF_B = OFF_X + XS * X_STAGE;
     static constexpr int OFF_STAGE = OFF_B + BS * B_UNIT;
-    static constexpr int OFF_BAR = OFF_STAGE + 2 * STAGE_F * 4;
+    static constexpr int OFF_BAR = OFF_STAGE + 4 * STAGE_F * 4;
     static constexpr int NUM_BARS = 2 * XS + 2 * AS + 2 * BS + 4;
     static constexpr int SMEM = OFF_BAR + NUM_BARS * 8 + 16;
     static constexpr int TMEM_COLS = 2 * D_COLS + AS * A_COLS;
@@ -184,7 +186,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < XS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 128); }
         for (int i = 0; i < AS; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], BM == TC_B_KR ? 128 : 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], BM == TC_B_KR ? 32 : 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -204,7 +206,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // TMEM columns: accumulator set 0 [0, 3RP), set 1 [3RP, 6RP), then AS A-operand units of [hi 32 | lo 32]
+    // TMEM columns: accumulator set 0 [0, 2RP), set 1 [2RP, 4RP), then AS A-operand units of [hi 32 | lo 32]
     const uint32_t a_col0 = 2 * C::D_COLS;
     const int GU = p.group_units;
 
@@ -235,8 +237,8 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            constexpr uint32_t idesc1 = idesc_tf32(TM, 2 * RP);   // A_hi x [B_hi | B_lo]
-            constexpr uint32_t idesc2 = idesc_tf32(TM, RP);       // A_lo x B_hi
+            constexpr uint32_t idesc1 = idesc_tf32(TM, 2 * RP);   // A_hi x [B_hi | B_lo] -> columns [0, 2RP)
+            constexpr uint32_t idesc2 = idesc_tf32(TM, RP);       // A_lo x B_hi          -> columns [RP, 2RP)
             Ring ar, br;
             uint32_t G = 0;          // global accumulation-group counter
             for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
@@ -252,7 +254,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                     mbar_wait(&b_full[br.idx], br.phase);
                     tc_fence_after();
                     const uint32_t d1 = tmem_base + buf * C::D_COLS;
-                    const uint32_t d2 = d1 + 2 * RP;
+                    const uint32_t d2 = d1 + RP;
                     const uint32_t a_hi = tmem_base + a_col0 + ar.idx * C::A_COLS;
                     const uint32_t a_lo = a_hi + 32;
                     const uint32_t bbase = smem_u32(b_smem + br.idx * C::B_UNIT);
@@ -262,7 +264,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                         const uint64_t db = desc_kmajor_sw128(bbase + ks * 32);
                         const uint32_t accf = (ug == 0 && ks == 0) ? 0u : 1u;
                         mma_ts_tf32(d1, a_hi + ks * 8, db, idesc1, accf);
-                        mma_ts_tf32(d2, a_lo + ks * 8, db, idesc2, accf);
+                        mma_ts_tf32(d2, a_lo + ks * 8, db, idesc2, 1u);
                     }
                     tc_commit(&a_empty[ar.idx]);
                     tc_commit(&b_empty[br.idx]);
@@ -277,7 +279,8 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        Ring xr, ar;
+        Ring xr, ar, ar_pub;       // ar: next A unit to fill; ar_pub: next A unit to publish (a_full)
+        int unpublished = 0;       // A units whose tcgen05.st have been issued but not yet waited for
         for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
             const int64_t kr = it / p.m_tiles;
             const int64_t c_begin = kr * p.chunks_per_range;
@@ -327,8 +330,13 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < 32; ++k) tb[k] = __float_as_uint(xc[(32 + k) * TM]);
                 }
-                mbar_arrive(&x_empty[xr.idx]);
-                xr.advance(XS);
+                // While those shared-memory loads are in flight, publish the A units stored in the
+                // previous iteration (their tcgen05.st have had a whole iteration to complete).
+                if (unpublished) {
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                    for (; unpublished > 0; --unpublished) { mbar_arrive(&a_full[ar_pub.idx]); ar_pub.advance(AS); }
+                }
                 uint32_t h[32];
 #pragma unroll
                 for (int u = 0; u < KO; ++u) {
@@ -355,12 +363,20 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                             TLB_TMEM_ST32(abase + 32, h);
                         }
                     }
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                    tc_fence_before();
-                    mbar_arrive(&a_full[ar.idx]);
                     ar.advance(AS);
+                    ++unpublished;
                 }
+                // every loaded value has been consumed: only now hand the X stage back to the TMA producer
+                // (generic-proxy reads must be ordered before the async-proxy overwrite)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&x_empty[xr.idx]);
+                xr.advance(XS);
             }
+        }
+        if (unpublished) {
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            for (; unpublished > 0; --unpublished) { mbar_arrive(&a_full[ar_pub.idx]); ar_pub.advance(AS); }
         }
     } else if (warp < 10) {
         // ================= B producer (one 32-element K unit at a time) =================
@@ -387,83 +403,86 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 }
             }
         } else {
-            const int kt = tid - 192;             // 0..127
-            const int kw = kt >> 5;               // warp within the group
-            constexpr int F4_PER_THREAD = (32 * RP / 4) / 128;
-            constexpr int F4_PER_ROW = RP / 4;
-            constexpr int R_PER_WARP = RP / 4;
-            float4 qreg[F4_PER_THREAD];
-            float preg[R_PER_WARP];
-            Ring br;
-            int sbuf = 0;
+            // Each of the 4 KR warps synthesises whole 32-element units on its own (units g = kw, kw+4, ...
+            // of this CTA's unit sequence), so four units are in flight and no cross-warp barrier is needed.
+            const int kw = warp - 6;
+            constexpr int F4 = RP / 4;                    // float4 per lane per unit (a unit is 32 x RP floats)
+            float* st = stage + kw * C::STAGE_F;         // rotated staging: (k, r) at st[k*RP + (r + k) % RP]
+            float* prow = st + 32 * RP;                  // P[a, :] of the current `a`
+            float4 qreg[F4];
             auto load_q = [&](int64_t b0) {
 #pragma unroll
-                for (int f = 0; f < F4_PER_THREAD; ++f) {
-                    const int idx = kt + f * 128;
-                    const int k = idx / F4_PER_ROW;
-                    qreg[f] = (b0 + k < p.B) ? __ldg(reinterpret_cast<const float4*>(p.Q + (b0 + k) * RP) + (idx % F4_PER_ROW))
+                for (int f = 0; f < F4; ++f) {
+                    const int idx = lane + f * 32;        // float4 index within the unit, row-major [32][RP/4]
+                    const int k = idx / F4;
+                    qreg[f] = (b0 + k < p.B) ? __ldg(reinterpret_cast<const float4*>(p.Q + (b0 + k) * RP) + (idx % F4))
                                              : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             };
+            uint32_t g_base = 0;                          // global index of the current item's first unit
+            int a_loaded = -1;
             for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
                 const int64_t kr = it / p.m_tiles;
                 const int64_t c_begin = kr * p.chunks_per_range;
                 const int64_t c_end = min(p.total_chunks, c_begin + p.chunks_per_range);
-                const int n = (int)(c_end - c_begin) * KO;      // units
-                int a = (int)(c_begin / p.chunks_per_a);
-                int bu = (int)(c_begin - (int64_t)a * p.chunks_per_a) * KO;     // unit index within this `a`
+                const int n = (int)(c_end - c_begin) * KO;      // units of this item
                 const int units_per_a = (int)p.chunks_per_a * KO;
-                int a_loaded = -1;
-                if (n > 0) load_q((int64_t)bu * 32);
-                for (int i = 0; i < n; ++i) {
-                    float* st = stage + sbuf * C::STAGE_F;
-                    sbuf ^= 1;
-                    // rotated staging: element (k, r) lives at st[k*RP + (r + k) % RP] so that both the
-                    // row-wise writes here and the column-wise reads below are (nearly) conflict-free
+                const int a0 = (int)(c_begin / p.chunks_per_a);
+                const int bu0 = (int)(c_begin - (int64_t)a0 * p.chunks_per_a) * KO;
+                int i = (int)((kw - (int)(g_base & 3u)) & 3);     // first local unit handled by this warp
+                int a = a0, bu = bu0 + i;
+                while (bu >= units_per_a) { bu -= units_per_a; ++a; }
+                if (i < n) load_q((int64_t)bu * 32);
+                for (; i < n; i += 4) {
+                    const uint32_t g = g_base + (uint32_t)i;
+                    const int slot = (int)(g & (BS - 1));
+                    const uint32_t use_parity = (g / BS) & 1u;
+                    __syncwarp();                          // previous unit's staging reads are done
 #pragma unroll
-                    for (int f = 0; f < F4_PER_THREAD; ++f) {
-                        const int idx = kt + f * 128;
-                        const int k = idx / F4_PER_ROW, r = (idx % F4_PER_ROW) * 4;
+                    for (int f = 0; f < F4; ++f) {
+                        const int idx = lane + f * 32;
+                        const int k = idx / F4, r = (idx % F4) * 4;
                         float* rowp = st + k * RP;
                         rowp[(r + 0 + k) & (RP - 1)] = qreg[f].x;
                         rowp[(r + 1 + k) & (RP - 1)] = qreg[f].y;
                         rowp[(r + 2 + k) & (RP - 1)] = qreg[f].z;
                         rowp[(r + 3 + k) & (RP - 1)] = qreg[f].w;
                     }
-                    if (a != a_loaded) {            // P row of this `a`: one value per r handled by this warp
-#pragma unroll
-                        for (int j = 0; j < R_PER_WARP; ++j) preg[j] = p.P ? __ldg(p.P + (int64_t)a * RP + kw + 4 * j) : 1.0f;
+                    if (a != a_loaded) {
+                        for (int r = lane; r < RP; r += 32) prow[r] = p.P ? __ldg(p.P + (int64_t)a * RP + r) : 1.0f;
                         a_loaded = a;
                     }
-                    // advance to the next unit's coordinates and prefetch its Q rows from L2
-                    int bu_n = bu + 1, a_n = a;
-                    if (bu_n == units_per_a) { bu_n = 0; ++a_n; }
-                    if (i + 1 < n) load_q((int64_t)bu_n * 32);
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    // all column reads first (they cannot be reordered across the stores below by the compiler)
-                    float qv[R_PER_WARP];
-                    const float* srow = st + lane * RP;                   // lane = k within the unit
-#pragma unroll
-                    for (int j = 0; j < R_PER_WARP; ++j) qv[j] = srow[(kw + 4 * j + lane) & (RP - 1)];
-                    mbar_wait(&b_empty[br.idx], br.phase ^ 1u);
-                    unsigned char* bhi = b_smem + br.idx * C::B_UNIT;
+                    // coordinates of this warp's next unit; prefetch its Q rows from L2
+                    int a_n = a, bu_n = bu + 4;
+                    while (bu_n >= units_per_a) { bu_n -= units_per_a; ++a_n; }
+                    if (i + 4 < n) load_q((int64_t)bu_n * 32);
+                    __syncwarp();
+                    mbar_wait(&b_empty[slot], use_parity ^ 1u);
+                    unsigned char* bhi = b_smem + slot * C::B_UNIT;
                     unsigned char* blo = bhi + RP * 128;
+                    const float* srow = st + lane * RP;                   // lane = k within the unit
                     if (!(p.debug & 1))
 #pragma unroll
-                    for (int j = 0; j < R_PER_WARP; ++j) {
-                        const int r = kw + 4 * j;
-                        const float krv = __fmul_rn(preg[j], qv[j]);
-                        const uint32_t hbits = __float_as_uint(krv) & 0xFFFFE000u;
-                        const float lo = krv - __uint_as_float(hbits);
-                        const uint32_t off = r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4;
-                        *reinterpret_cast<uint32_t*>(bhi + off) = hbits;
-                        *reinterpret_cast<float*>(blo + off) = lo;
+                    for (int r0 = 0; r0 < RP; r0 += 8) {
+                        float qv[8], pv[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { qv[j] = srow[(r0 + j + lane) & (RP - 1)]; pv[j] = prow[r0 + j]; }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int r = r0 + j;
+                            const float krv = __fmul_rn(pv[j], qv[j]);
+                            const uint32_t hbits = __float_as_uint(krv) & 0xFFFFE000u;
+                            const float lo = krv - __uint_as_float(hbits);
+                            const uint32_t off = r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4;
+                            *reinterpret_cast<uint32_t*>(bhi + off) = hbits;
+                            *reinterpret_cast<float*>(blo + off) = lo;
+                        }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core reads
-                    mbar_arrive(&b_full[br.idx]);
-                    br.advance(BS);
-                    bu = bu_n; a = a_n;
+                    mbar_arrive(&b_full[slot]);
+                    a = a_n; bu = bu_n;
                 }
+                g_base += (uint32_t)n;
             }
         }
     } else {
@@ -488,7 +507,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 tc_fence_after();
                 if (!(p.debug & 8))
 #pragma unroll
-                for (int part = 0; part < 3; ++part) {        // hh, hl, lh column blocks of this set
+                for (int part = 0; part < 2; ++part) {        // hi*hi block, cross-term block of this set
 #pragma unroll
                     for (int c0 = 0; c0 < RP; c0 += 32) {
                         uint32_t r[32];
@@ -557,7 +576,9 @@ int launch_cfg(const TcStreamLaunch& l, cudaStream_t stream) {
     }
     int64_t n_items = (int64_t)l.p.m_tiles * l.p.k_ranges;
     if (n_items <= 0) return TLB200_OK;
-    const unsigned grid = (unsigned)(n_items < kNumSMs ? n_items : kNumSMs);
+    static int grid_cap = -1;
+    if (grid_cap < 0) { const char* e = getenv("TLB200_TC_GRID"); grid_cap = e ? atoi(e) : kNumSMs; if (grid_cap < 1) grid_cap = kNumSMs; }
+    const unsigned grid = (unsigned)(n_items < grid_cap ? n_items : grid_cap);
     tc_stream_kernel<RP, XL, BM><<<grid, NUM_THREADS, smem, stream>>>(l.x_map, l.bhi_map, l.blo_map, l.p);
     TLB_CHECK_LAUNCH();
     return TLB200_OK;

@@ -268,6 +268,27 @@ def test_mode_dot_vs_oracle(shape, J, dtype, path):
         assert rel_fro(host(tb.mode_dot(xd, u, mode, transpose=True)), ref) <= TOL[np.dtype(dtype)]
 
 
+def test_mode_dot_many_short_items_rowwise():
+    """Regression: a persistent CTA that runs several short work items back to back (last-mode
+    TTM, 256 row tiles x 8 K chunks) once handed a shared-memory stage back to TMA before every
+    warp had consumed it; a few rows per tile came out ~10% off, invisible in a Frobenius norm.
+    Check every output row on its own."""
+    rng = np.random.RandomState(17)
+    x = rng.standard_normal((256, 128, 512)).astype(np.float32)
+    m = rng.standard_normal((64, 512)).astype(np.float32)
+    ref = O.mode_dot(x.astype(np.float64), m.astype(np.float64), 2).reshape(-1, 64)
+    out = host(tb.mode_dot(dev(x), dev(m), 2)).reshape(-1, 64).astype(np.float64)
+    row_err = np.linalg.norm(out - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert row_err.max() <= 1e-4, (int(np.argmax(row_err)), float(row_err.max()), tb.last_kernel_path())
+    # same for MTTKRP with many short items: (32768, 8, 64), mode 0
+    x = rng.standard_normal((32768, 8, 64)).astype(np.float32)
+    fs = [rng.standard_normal((s, 64)).astype(np.float32) for s in x.shape]
+    ref = O.mttkrp_float64_truth(x, (None, fs), 0)
+    out = host(tb.unfolding_dot_khatri_rao(dev(x), (None, [dev(f) for f in fs]), 0)).astype(np.float64)
+    row_err = np.linalg.norm(out - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert row_err.max() <= 1e-4, (int(np.argmax(row_err)), float(row_err.max()), tb.last_kernel_path())
+
+
 def test_mode_dot_errors():
     x = dev(np.zeros((3, 4, 2), dtype=np.float32))
     with pytest.raises(ValueError):
