@@ -58,4 +58,10 @@ int launch_khatri_rao(const T* const* mats, const int64_t* rows, const int64_t* 
                       const T* mask, T* out, int64_t out_ld, int64_t pad_cols,
                       cudaStream_t stream);
 
+// Transposed + zero-padded: out[c * rows_padded + row], c < pad_cols, row < rows_padded (tcgen05 engine's Q table).
+template <typename T>
+int launch_khatri_rao_t(const T* const* mats, const int64_t* rows, const int64_t* row_stride,
+                        const int64_t* col_stride, int nmats, int64_t rank, const T* weights, T* out,
+                        int64_t rows_padded, int64_t pad_cols, T* out_lo, cudaStream_t stream);
+
 }  // namespace tlb200

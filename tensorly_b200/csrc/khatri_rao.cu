@@ -55,7 +55,71 @@ khatri_rao_kernel(KrArgs<T> a, int64_t total_rows, int64_t rank, int64_t pad_col
     }
 }
 
+// Transposed, zero-padded variant for the tcgen05 engine: out[c * out_ld + row] for row < rows_padded
+// (rows >= total_rows and columns >= rank are written as zero); with out_lo the value is split into its
+// tf32 truncation (out) and the exact remainder (out_lo).  blockDim = (32, 8): x runs over rows
+// so that the stores are coalesced.
+template <typename T>
+__global__ void __launch_bounds__(256)
+khatri_rao_t_kernel(KrArgs<T> a, int64_t total_rows, int64_t rows_padded, int64_t rank, int64_t pad_cols,
+                    const T* __restrict__ weights, T* __restrict__ out, int64_t out_ld, T* __restrict__ out_lo) {
+    for (int64_t row = (int64_t)blockIdx.x * 32 + threadIdx.x; row < rows_padded; row += (int64_t)gridDim.x * 32) {
+        int64_t idx[TLB200_MAX_NDIM];
+        int64_t rem = row < total_rows ? row : 0;
+#pragma unroll
+        for (int i = TLB200_MAX_NDIM - 1; i >= 0; --i) {
+            if (i < a.nmats) {
+                int64_t q = rem / a.rows[i];
+                idx[i] = rem - q * a.rows[i];
+                rem = q;
+            }
+        }
+        for (int64_t c = threadIdx.y; c < pad_cols; c += 8) {
+            T v = T(0);
+            if (c < rank && row < total_rows) {
+                v = a.mat[0][idx[0] * a.rs[0] + c * a.cs[0]];
+                if (weights) v = mul_rn(v, weights[c]);
+#pragma unroll
+                for (int i = 1; i < TLB200_MAX_NDIM; ++i)
+                    if (i < a.nmats) v = mul_rn(v, a.mat[i][idx[i] * a.rs[i] + c * a.cs[i]]);
+            }
+            if (out_lo) {     // tf32 split for the tensor-core engine: hi = truncation, lo = exact remainder
+                const float f = (float)v;
+                const float h = __uint_as_float(__float_as_uint(f) & 0xFFFFE000u);
+                out[c * out_ld + row] = (T)h;
+                out_lo[c * out_ld + row] = (T)(f - h);
+            } else {
+                out[c * out_ld + row] = v;
+            }
+        }
+    }
+}
+
 }  // namespace
+
+template <typename T>
+int launch_khatri_rao_t(const T* const* mats, const int64_t* rows, const int64_t* row_stride, const int64_t* col_stride,
+                        int nmats, int64_t rank, const T* weights, T* out, int64_t rows_padded, int64_t pad_cols,
+                        T* out_lo, cudaStream_t stream) {
+    if (nmats < 1 || nmats > TLB200_MAX_NDIM || rank < 0 || pad_cols < rank) return TLB200_EINVAL;
+    KrArgs<T> a;
+    a.nmats = nmats;
+    int64_t total = 1;
+    for (int i = 0; i < nmats; ++i) {
+        a.mat[i] = mats[i]; a.rows[i] = rows[i]; a.rs[i] = row_stride[i]; a.cs[i] = col_stride[i];
+        total *= rows[i];
+    }
+    for (int i = nmats; i < TLB200_MAX_NDIM; ++i) { a.mat[i] = nullptr; a.rows[i] = 1; a.rs[i] = 0; a.cs[i] = 0; }
+    if (rows_padded < total) return TLB200_EINVAL;
+    if (rows_padded == 0 || pad_cols == 0) return TLB200_OK;
+    int64_t blocks = ceil_div(rows_padded, 32);
+    if (blocks > (int64_t)kNumSMs * 64) blocks = (int64_t)kNumSMs * 64;
+    khatri_rao_t_kernel<T><<<(unsigned)blocks, dim3(32, 8), 0, stream>>>(a, total, rows_padded, rank, pad_cols, weights, out, rows_padded, out_lo);
+    TLB_CHECK_LAUNCH();
+    return TLB200_OK;
+}
+template int launch_khatri_rao_t<float>(const float* const*, const int64_t*, const int64_t*, const int64_t*, int, int64_t,
+                                        const float*, float*, int64_t, int64_t, float*, cudaStream_t);
 
 template <typename T>
 int launch_khatri_rao(const T* const* mats, const int64_t* rows, const int64_t* row_stride,

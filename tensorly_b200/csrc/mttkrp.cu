@@ -95,7 +95,7 @@ static size_t workspace_for(const tlb200_mttkrp_plan_t& pl, int dtype) {
     const size_t es = dtype_size(dtype);
     size_t total = 0;
     if (pl.p_count > 0) total += align_up((size_t)pl.A * pl.rank_padded * es, 256);
-    total += align_up((size_t)pl.B * pl.rank_padded * es, 256);
+    total += align_up((size_t)2 * (pl.B + 64) * pl.rank_padded * es, 256);   // Q (tcgen05: transposed hi + lo, B padded to 64)
     total += align_up((size_t)pl.splits * pl.J * pl.rank_padded * es, 256);
     if (pl.path == TLB200_PATH_TCGEN05) total += mttkrp_tc_extra_workspace(pl);
     return total + 256;
@@ -107,7 +107,7 @@ static int run(const T* x, const int64_t* shape, int ndim, int mode, const T* co
                int64_t out_ld, void* workspace, const tlb200_mttkrp_plan_t& pl, cudaStream_t stream) {
     Carver ws(workspace);
     T* P = pl.p_count > 0 ? ws.take<T>((size_t)pl.A * pl.rank_padded) : nullptr;
-    T* Q = ws.take<T>((size_t)pl.B * pl.rank_padded);
+    T* Q = ws.take<T>((size_t)2 * (pl.B + 64) * pl.rank_padded);
     T* partial = ws.take<T>((size_t)pl.splits * pl.J * pl.rank_padded);
 
     // The reference's khatri_rao returns a single remaining matrix untouched, i.e. it
@@ -120,8 +120,19 @@ static int run(const T* x, const int64_t* shape, int ndim, int mode, const T* co
         if (st) return st;
         w = nullptr;  // weights go to the first non-skipped factor only
     }
-    st = launch_khatri_rao<T>(factors + pl.q_first, shape + pl.q_first, frs + pl.q_first, fcs + pl.q_first,
-                              pl.q_count, rank, w, nullptr, Q, pl.rank_padded, pl.rank_padded, stream);
+    if (pl.path == TLB200_PATH_TCGEN05) {
+        // the tensor-core engine takes Q transposed ([rank_padded][Bpad], K-major rows, zero padded) and already
+        // split into tf32 hi / lo tables, which TMA streams straight into the B-operand ring
+        const int64_t bpad = ceil_div(pl.B, 64) * 64;
+        float* qhi = reinterpret_cast<float*>(Q);
+        st = launch_khatri_rao_t<float>(reinterpret_cast<const float* const*>(factors) + pl.q_first, shape + pl.q_first,
+                                        frs + pl.q_first, fcs + pl.q_first, pl.q_count, rank,
+                                        reinterpret_cast<const float*>(w), qhi, bpad, pl.rank_padded,
+                                        qhi + pl.rank_padded * bpad, stream);
+    } else {
+        st = launch_khatri_rao<T>(factors + pl.q_first, shape + pl.q_first, frs + pl.q_first, fcs + pl.q_first,
+                                  pl.q_count, rank, w, nullptr, Q, pl.rank_padded, pl.rank_padded, stream);
+    }
     if (st) return st;
 
     if (pl.path == TLB200_PATH_TCGEN05) {

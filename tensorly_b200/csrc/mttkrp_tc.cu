@@ -52,7 +52,7 @@ int mttkrp_tc_launch(const float* x, const tlb200_mttkrp_plan_t& pl, int64_t /*r
     TcStreamLaunch l;
     l.rp = (int)pl.rank_padded;
     l.x_layout = layout_for(pl);
-    l.b_mode = TC_B_KR;
+    l.b_mode = TC_B_MAT;
     const int ks = tc_chunk_k(l.x_layout);
     uint64_t dims[4], strides[3];
     uint32_t box[4];
@@ -74,8 +74,15 @@ int mttkrp_tc_launch(const float* x, const tlb200_mttkrp_plan_t& pl, int64_t /*r
         st = tc_encode_map(&l.x_map, x, 3, dims, strides, box, false);
     }
     if (st) return st;
-    l.bhi_map = l.x_map;   // unused in KR mode
-    l.blo_map = l.x_map;
+    {   // Q^T hi / lo tables [rank_padded][ldq]: one unit = box of 32 contraction elements x all rows, swizzled
+        const uint64_t ldq = (uint64_t)ceil_div(pl.B, 64) * 64;
+        uint64_t qd[2] = {ldq, (uint64_t)pl.rank_padded}, qs[1] = {ldq * 4};
+        uint32_t qb[2] = {32, (uint32_t)pl.rank_padded};
+        st = tc_encode_map(&l.bhi_map, Q, 2, qd, qs, qb, true);
+        if (st) return st;
+        st = tc_encode_map(&l.blo_map, Q + pl.rank_padded * ldq, 2, qd, qs, qb, true);
+        if (st) return st;
+    }
 
     TcStreamParams& p = l.p;
     p.M = pl.J; p.A = pl.A; p.B = pl.B;
@@ -85,7 +92,7 @@ int mttkrp_tc_launch(const float* x, const tlb200_mttkrp_plan_t& pl, int64_t /*r
     p.k_ranges = pl.splits;
     p.chunks_per_range = ceil_div(p.total_chunks, pl.splits);
     p.group_units = tc_group_units();
-    p.P = P; p.Q = Q;
+    p.P = P;     // outer Khatri-Rao table: applied per `a` by the epilogue
     p.out = partial;
     p.sOk = pl.J * pl.rank_padded; p.sOm = pl.rank_padded; p.sOn = 1;
     p.n_valid = (int)pl.rank_padded;

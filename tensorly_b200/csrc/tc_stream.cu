@@ -31,13 +31,19 @@
 // the DRAM-friendliest shape: two adjacent 128-byte lines per row per TMA box (measured
 // 6.8 TB/s vs 4.5 TB/s for one line per row on rows that are megabytes apart).
 //
-// Warp roles (14 warps, 1 CTA per SM, persistent over work items):
+// Warp roles (16 warps, 1 CTA per SM, persistent over work items):
 //   warp 0       TMA producer of X tiles (ring of XS stages)
-//   warp 1       MMA issuer (single thread)
-//   warps 2-5    convert: smem X tile -> registers -> hi/lo -> TMEM A ring (AS stages)
-//   warps 6-9    B producer: Khatri-Rao rows P[a,:]*Q[b,:] split hi/lo into a K-major
-//                SWIZZLE_128B smem ring (or, for TTM, TMA loads of the pre-split matrix)
-//   warps 10-13  epilogue: drain TMEM accumulation groups, write C
+//   warp 1       MMA issuer (one elected lane)
+//   warps 2-9    convert: smem X tile -> registers -> hi/lo -> TMEM A ring; two sets of four
+//                warps (one warp per TMEM lane quarter) take alternate tiles, which hides the
+//                barrier/LDS/tcgen05.st latencies of one tile behind the other
+//   warp 10      B producer: TMA loads of the pre-split (tf32 hi / lo) small operand — the
+//                factor matrix of a TTM, or the inner Khatri-Rao table Q of an MTTKRP — K-major
+//                SWIZZLE_128B, one 32-element unit at a time (warp 11 is idle)
+//   warps 12-15  epilogue: drain TMEM accumulation groups, write C.  For MTTKRP the Khatri-Rao
+//                row is P[a,:] * Q[b,:]: the tensor core contracts with Q only and the epilogue
+//                scales each drained group by P[a,:] (groups never straddle an `a` boundary), so
+//                no Khatri-Rao tile is ever formed — not even in shared memory.
 #include "tc_stream.cuh"
 
 #include <cstdlib>
@@ -46,7 +52,7 @@ namespace tlb200 {
 namespace {
 
 constexpr int TM = 128;
-constexpr int NUM_THREADS = 448;
+constexpr int NUM_THREADS = 512;
 constexpr uint32_t SPIN_LIMIT = 1u << 22;   // x ~1 us per try_wait: seconds, then trap (never hang the GPU)
 
 // ---- PTX wrappers ---------------------------------------------------------------------
@@ -70,6 +76,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (++spins > SPIN_LIMIT) asm volatile("trap;");
     }
 }
+// One elected lane of a fully converged warp (the operands of tcgen05/TMA instructions must live in uniform
+// registers: computing them warp-uniformly and predicating only the issue avoids a per-instruction
+// R2UR "waterfall" loop on the issuing thread — measured ~95 clk per MMA with `if (lane == 0)`).
+__device__ __forceinline__ uint32_t elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xFFFFFFFF;\n\t@px mov.s32 %0, 1;\n\t}\n" : "+r"(pred));
+    return pred;
+}
+// wait for two barriers at once: the two try_wait round trips overlap instead of adding up
+__device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t parity_a, uint64_t* bar_b, uint32_t parity_b) {
+    uint32_t da = 0, db = 0, spins = 0;
+    const uint32_t aa = smem_u32(bar_a), ab = smem_u32(bar_b);
+    while (true) {
+        if (!da) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                              : "=r"(da) : "r"(aa), "r"(parity_a) : "memory");
+        if (!db) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                              : "=r"(db) : "r"(ab), "r"(parity_b) : "memory");
+        if (da && db) break;
+        if (++spins > SPIN_LIMIT) asm volatile("trap;");
+    }
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -79,6 +106,12 @@ __device__ __forceinline__ void mma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, ui
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
                  ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// same, accumulate flag hard-wired to true (no predicate register set-up on the issuing thread)
+__device__ __forceinline__ void mma_ts_tf32_acc(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -126,6 +159,10 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
                  "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])                                                       \
                  : "memory")
 
+// perf triage: timestamp event `ev` of iteration `i` of role `role` (CTA 0 only, first 256 iterations)
+#define TLB_TRACE(role, i, ev)                                                                   \
+    do { if (tr && (i) < 256) p.trace[(((role) * 256) + (i)) * 8 + (ev)] = clock64(); } while (0)
+
 // ring position: stage index + phase parity, advanced without divisions
 struct Ring {
     int idx = 0;
@@ -139,21 +176,19 @@ struct Cfg {
     static constexpr int KS = XL == TC_X_KMAJOR_1 ? 32 : 64;        // K extent of one X stage
     static constexpr int KO = KS / 32;                              // 32-element units per X stage
     static constexpr int X_STAGE = TM * KS * 4;
-    static constexpr int XS = KS == 32 ? 6 : 4;
+    static constexpr int XS = KS == 32 ? 8 : (RP == 32 ? 5 : 4);     // bytes in flight per SM hide HBM latency
     static constexpr int D_COLS = 2 * RP;                           // per accumulator set: [hi*hi (RP) | hi*lo + lo*hi (RP)]
     static constexpr int A_COLS = 64;                               // TMEM columns per A unit: [hi 32 | lo 32]
-    static constexpr int AS = 4;
+    static constexpr int AS = RP == 32 ? 6 : 4;
     static constexpr int B_UNIT = 2 * RP * 128;                     // [hi RP rows | lo RP rows] x 128 B, K-major SW128
-    static constexpr int BS = RP == 64 ? 4 : 8;                     // power of two (slot = unit % BS)
-    static constexpr int STAGE_F = 32 * RP + RP;                    // per KR warp: rotated Q staging [32][RP] + P row [RP]
+    static constexpr int BS = 4;                                    // B-operand ring (32-element units)
     static constexpr int OFF_X = 0;
     static constexpr int OFF_B = OFF_X + XS * X_STAGE;
-    static constexpr int OFF_STAGE = OFF_B + BS * B_UNIT;
-    static constexpr int OFF_BAR = OFF_STAGE + 4 * STAGE_F * 4;
+    static constexpr int OFF_BAR = OFF_B + BS * B_UNIT;
     static constexpr int NUM_BARS = 2 * XS + 2 * AS + 2 * BS + 4;
     static constexpr int SMEM = OFF_BAR + NUM_BARS * 8 + 16;
     static constexpr int TMEM_COLS = 2 * D_COLS + AS * A_COLS;
-    static_assert(AS >= 2, "need at least two A units");
+    static_assert(AS >= 2 && AS % KO == 0, "A ring must hold whole tiles");
     static_assert(TMEM_COLS <= 512, "TMEM budget");
     static_assert(SMEM + 1024 <= 227 * 1024, "smem budget");
 };
@@ -168,7 +203,6 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* x_smem = smem + C::OFF_X;
     unsigned char* b_smem = smem + C::OFF_B;
-    float* stage = reinterpret_cast<float*>(smem + C::OFF_STAGE);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
     uint64_t* x_full = bars;
     uint64_t* x_empty = x_full + XS;
@@ -182,21 +216,21 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n_items = (int64_t)p.m_tiles * p.k_ranges;
+    const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0;
+    int tri = 0;   // trace iteration counter of this role
 
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < XS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 128); }
         for (int i = 0; i < AS; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], BM == TC_B_KR ? 32 : 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&xmap)) : "memory");
-            if (BM == TC_B_MAT) {
-                asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&bhi_map)) : "memory");
-                asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&blo_map)) : "memory");
-            }
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&bhi_map)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&blo_map)) : "memory");
         }
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
@@ -211,8 +245,8 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     const int GU = p.group_units;
 
     if (warp == 0) {
-        // ================= TMA producer of X tiles =================
-        if (lane == 0) {
+        // ================= TMA producer of X tiles (whole warp loops, one elected lane issues) =================
+        {
             Ring xr;
             for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
                 const int mt = (int)(it % p.m_tiles);
@@ -224,71 +258,108 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 const int m0 = mt * TM;
                 for (int64_t c = c_begin; c < c_end; ++c) {
                     mbar_wait(&x_empty[xr.idx], xr.phase ^ 1u);
-                    mbar_expect_tx(&x_full[xr.idx], C::X_STAGE);
-                    unsigned char* dst = x_smem + xr.idx * C::X_STAGE;
-                    if constexpr (XL == TC_X_KMAJOR_1)      tma_load_3d(dst, &xmap, &x_full[xr.idx], bc * 32, m0, a);
-                    else if constexpr (XL == TC_X_KMAJOR_2) tma_load_4d(dst, &xmap, &x_full[xr.idx], 0, bc * 2, m0, a);
-                    else                                    tma_load_3d(dst, &xmap, &x_full[xr.idx], m0, bc * 64, a);
+                    TLB_TRACE(0, tri, 0);
+                    if (elect_one_sync()) {
+                        mbar_expect_tx(&x_full[xr.idx], C::X_STAGE);
+                        unsigned char* dst = x_smem + xr.idx * C::X_STAGE;
+                        if constexpr (XL == TC_X_KMAJOR_1)      tma_load_3d(dst, &xmap, &x_full[xr.idx], bc * 32, m0, a);
+                        else if constexpr (XL == TC_X_KMAJOR_2) tma_load_4d(dst, &xmap, &x_full[xr.idx], 0, bc * 2, m0, a);
+                        else                                    tma_load_3d(dst, &xmap, &x_full[xr.idx], m0, bc * 64, a);
+                    }
+                    __syncwarp();
+                    TLB_TRACE(0, tri, 1); ++tri;
                     xr.advance(XS);
                     if (++bc == (int)p.chunks_per_a) { bc = 0; ++a; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer (whole warp runs the loop, one elected lane issues) =================
+        {
             constexpr uint32_t idesc1 = idesc_tf32(TM, 2 * RP);   // A_hi x [B_hi | B_lo] -> columns [0, 2RP)
             constexpr uint32_t idesc2 = idesc_tf32(TM, RP);       // A_lo x B_hi          -> columns [RP, 2RP)
             Ring ar, br;
             uint32_t G = 0;          // global accumulation-group counter
+            // loop-invariant operand pieces: the issuing thread is a single latency-bound instruction
+            // stream, so every add it does not execute shortens the MMA cadence
+            const uint32_t d_base = tmem_base;
+            const uint32_t a_base = tmem_base + a_col0;
+            const uint64_t d0 = desc_kmajor_sw128(smem_u32(b_smem));
+            const uint32_t bdesc_lo0 = (uint32_t)d0, bdesc_hi = (uint32_t)(d0 >> 32);
             for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
                 const int64_t kr = it / p.m_tiles;
                 const int64_t c_begin = kr * p.chunks_per_range;
                 const int64_t c_end = min(p.total_chunks, c_begin + p.chunks_per_range);
-                const int n = (int)(c_end - c_begin) * KO;       // 32-element units of this item
+                const int n = (int)(c_end - c_begin);           // tiles (chunks) of this item, KO units each
                 int ug = 0;
+                int bc = (int)(c_begin % p.chunks_per_a);       // tile index within the current `a`
                 for (int i = 0; i < n; ++i) {
-                    const uint32_t buf = G & 1u;
-                    if (ug == 0 && G >= 2) mbar_wait(&d_empty[buf], ((G >> 1) - 1) & 1u);
-                    mbar_wait(&a_full[ar.idx], ar.phase);
-                    mbar_wait(&b_full[br.idx], br.phase);
-                    tc_fence_after();
-                    const uint32_t d1 = tmem_base + buf * C::D_COLS;
-                    const uint32_t d2 = d1 + RP;
-                    const uint32_t a_hi = tmem_base + a_col0 + ar.idx * C::A_COLS;
-                    const uint32_t a_lo = a_hi + 32;
-                    const uint32_t bbase = smem_u32(b_smem + br.idx * C::B_UNIT);
-                    if (!(p.debug & 2))
+                    const bool a_end = p.P != nullptr && bc + 1 == (int)p.chunks_per_a;   // last tile of this `a`
+                    if (++bc == (int)p.chunks_per_a) bc = 0;
+                    // one A barrier pair per tile: both units of a tile are stored and published together
+                    const int as0 = ar.idx;
+                    const uint32_t aph = ar.phase;
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t db = desc_kmajor_sw128(bbase + ks * 32);
-                        const uint32_t accf = (ug == 0 && ks == 0) ? 0u : 1u;
-                        mma_ts_tf32(d1, a_hi + ks * 8, db, idesc1, accf);
-                        mma_ts_tf32(d2, a_lo + ks * 8, db, idesc2, 1u);
+                    for (int u = 0; u < KO; ++u) {
+                        const uint32_t buf = G & 1u;
+                        if (ug == 0 && G >= 2) mbar_wait(&d_empty[buf], ((G >> 1) - 1) & 1u);
+                        TLB_TRACE(1, tri, 0);
+                        if (u == 0) mbar_wait2(&a_full[as0], aph, &b_full[br.idx], br.phase);
+                        else        mbar_wait(&b_full[br.idx], br.phase);
+                        TLB_TRACE(1, tri, 2);
+                        tc_fence_after();
+                        const uint32_t d1 = d_base + buf * C::D_COLS;
+                        const uint32_t d2 = d1 + RP;
+                        const uint32_t a_hi = a_base + ar.idx * C::A_COLS;       // a_lo = a_hi + 32
+                        const uint32_t blo = bdesc_lo0 + br.idx * (C::B_UNIT >> 4); // low word of the K-major SW128 descriptor
+                        const bool group_end = (ug + 1 == GU) || ((i == n - 1 || a_end) && u == KO - 1);
+                        if (elect_one_sync()) {
+                            if (!(p.debug & 2)) {
+                                // first K step of a group overwrites the accumulators, everything else accumulates
+                                mma_ts_tf32(d1, a_hi, ((uint64_t)bdesc_hi << 32) | blo, idesc1, ug == 0 ? 0u : 1u);
+                                mma_ts_tf32_acc(d2, a_hi + 32, ((uint64_t)bdesc_hi << 32) | blo, idesc2);
+#pragma unroll
+                                for (int ks = 1; ks < 4; ++ks) {
+                                    const uint64_t db = ((uint64_t)bdesc_hi << 32) | (blo + ks * 2);   // +32 bytes per K step
+                                    mma_ts_tf32_acc(d1, a_hi + ks * 8, db, idesc1);
+                                    mma_ts_tf32_acc(d2, a_hi + 32 + ks * 8, db, idesc2);
+                                }
+                            }
+                            tc_commit(&b_empty[br.idx]);
+                            if (u == KO - 1) tc_commit(&a_empty[as0]);
+                            if (group_end) tc_commit(&d_full[buf]);
+                        }
+                        __syncwarp();
+                        TLB_TRACE(1, tri, 3); ++tri;
+                        ar.advance(AS);
+                        br.advance(BS);
+                        if (group_end) { ++G; ug = 0; } else { ++ug; }
                     }
-                    tc_commit(&a_empty[ar.idx]);
-                    tc_commit(&b_empty[br.idx]);
-                    ar.advance(AS);
-                    br.advance(BS);
-                    if (++ug == GU || i == n - 1) { tc_commit(&d_full[buf]); ++G; ug = 0; }
                 }
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < 10) {
         // ================= convert: smem X tile -> hi/lo -> TMEM A ring =================
-        const int q = warp & 3;
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int cset = (warp - 2) >> 2;       // convert set 0 / 1: takes the tiles with (global index & 1) == cset
         const int row = q * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        Ring xr, ar, ar_pub;       // ar: next A unit to fill; ar_pub: next A unit to publish (a_full)
+        uint32_t cbase = 0;        // global index (per CTA) of the current item's first tile
+        int pub_slot[2] = {0, 0};  // A slots stored but not yet published
         int unpublished = 0;       // A units whose tcgen05.st have been issued but not yet waited for
         for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
             const int64_t kr = it / p.m_tiles;
             const int64_t c_begin = kr * p.chunks_per_range;
             const int64_t c_end = min(p.total_chunks, c_begin + p.chunks_per_range);
             const int n = (int)(c_end - c_begin);
-            for (int i = 0; i < n; ++i) {
-                mbar_wait(&x_full[xr.idx], xr.phase);
-                const unsigned char* xt = x_smem + xr.idx * C::X_STAGE;
+            for (int i = (int)((cset - (int)(cbase & 1u)) & 1); i < n; i += 2) {
+                const uint32_t gc = cbase + (uint32_t)i;                 // global tile index
+                const int xs = (int)(gc % XS);
+                const uint32_t xphase = (gc / XS) & 1u;
+                if (warp == 2) TLB_TRACE(2, tri, 0);
+                mbar_wait(&x_full[xs], xphase);
+                if (warp == 2) TLB_TRACE(2, tri, 1);
+                const unsigned char* xt = x_smem + xs * C::X_STAGE;
                 // ta = first 32 contraction elements of this thread's row, tb = the next 32 (KS == 64 only)
                 uint32_t ta[32];
                 uint32_t tb[KS == 64 ? 32 : 1];
@@ -330,19 +401,45 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < 32; ++k) tb[k] = __float_as_uint(xc[(32 + k) * TM]);
                 }
-                // While those shared-memory loads are in flight, publish the A units stored in the
-                // previous iteration (their tcgen05.st have had a whole iteration to complete).
+                // Hand the X stage back to the TMA producer as early as possible (bytes in flight hide the
+                // HBM latency) — but only once every load has really landed in registers: touching one
+                // register of each 128-bit load makes the scoreboard wait for it, and the proxy fence orders
+                // these generic-proxy reads before the async-proxy overwrite.  (Releasing right after *issuing*
+                // the loads let TMA overwrite rows that slower warps had not read yet.)
+                {
+                    uint32_t touch = 0;
+                    if constexpr (XL == TC_X_MMAJOR) {
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) touch ^= ta[k] ^ tb[k & (KS == 64 ? 31 : 0)];
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) touch ^= ta[4 * c] ^ tb[(4 * c) & (KS == 64 ? 31 : 0)];
+                    }
+                    asm volatile("" ::"r"(touch));
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(&x_empty[xs]);
+                }
+                if (warp == 2) TLB_TRACE(2, tri, 2);
+                // Publish the A units stored in the previous iteration (their tcgen05.st have had a whole
+                // iteration to complete).
                 if (unpublished) {
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     tc_fence_before();
-                    for (; unpublished > 0; --unpublished) { mbar_arrive(&a_full[ar_pub.idx]); ar_pub.advance(AS); }
+                    for (int j = 0; j < unpublished; ++j) mbar_arrive(&a_full[pub_slot[j]]);
+                    unpublished = 0;
                 }
+                if (warp == 2) TLB_TRACE(2, tri, 3);
                 uint32_t h[32];
 #pragma unroll
                 for (int u = 0; u < KO; ++u) {
-                    mbar_wait(&a_empty[ar.idx], ar.phase ^ 1u);
-                    tc_fence_after();
-                    const uint32_t abase = lane_addr + a_col0 + ar.idx * C::A_COLS;
+                    const uint32_t gu = gc * KO + u;                      // global unit index
+                    const int as = (int)(gu % AS);
+                    if (u == 0) {                                         // one barrier pair per tile (slot of unit 0)
+                        mbar_wait(&a_empty[as], ((gu / AS) & 1u) ^ 1u);
+                        tc_fence_after();
+                    }
+                    if (warp == 2) TLB_TRACE(2, tri, 4 + u);
+                    const uint32_t abase = lane_addr + a_col0 + as * C::A_COLS;
                     if (!(p.debug & 4)) {
                         if (KS == 32 || u == 0) {
 #pragma unroll
@@ -363,126 +460,46 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                             TLB_TMEM_ST32(abase + 32, h);
                         }
                     }
-                    ar.advance(AS);
-                    ++unpublished;
+                    if (u == 0) { pub_slot[0] = as; unpublished = 1; }
                 }
-                // every loaded value has been consumed: only now hand the X stage back to the TMA producer
-                // (generic-proxy reads must be ordered before the async-proxy overwrite)
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(&x_empty[xr.idx]);
-                xr.advance(XS);
+                // publish right away: the other convert set hides this wait
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                for (int j = 0; j < unpublished; ++j) mbar_arrive(&a_full[pub_slot[j]]);
+                unpublished = 0;
+                if (warp == 2) { TLB_TRACE(2, tri, 6); ++tri; }
             }
+            cbase += (uint32_t)n;
         }
         if (unpublished) {
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
-            for (; unpublished > 0; --unpublished) { mbar_arrive(&a_full[ar_pub.idx]); ar_pub.advance(AS); }
+            for (int j = 0; j < unpublished; ++j) mbar_arrive(&a_full[pub_slot[j]]);
         }
-    } else if (warp < 10) {
-        // ================= B producer (one 32-element K unit at a time) =================
-        if constexpr (BM == TC_B_MAT) {
-            if (warp == 6 && lane == 0) {
-                Ring br;
-                for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-                    const int64_t kr = it / p.m_tiles;
-                    const int64_t c_begin = kr * p.chunks_per_range;
-                    const int64_t c_end = min(p.total_chunks, c_begin + p.chunks_per_range);
-                    int bc = (int)(c_begin % p.chunks_per_a);
-                    for (int64_t c = c_begin; c < c_end; ++c) {
-#pragma unroll
-                        for (int u = 0; u < KO; ++u) {
-                            mbar_wait(&b_empty[br.idx], br.phase ^ 1u);
-                            mbar_expect_tx(&b_full[br.idx], C::B_UNIT);
-                            unsigned char* dst = b_smem + br.idx * C::B_UNIT;
-                            tma_load_2d(dst, &bhi_map, &b_full[br.idx], bc * KS + u * 32, 0);
-                            tma_load_2d(dst + RP * 128, &blo_map, &b_full[br.idx], bc * KS + u * 32, 0);
-                            br.advance(BS);
-                        }
-                        if (++bc == (int)p.chunks_per_a) bc = 0;
-                    }
-                }
-            }
-        } else {
-            // Each of the 4 KR warps synthesises whole 32-element units on its own (units g = kw, kw+4, ...
-            // of this CTA's unit sequence), so four units are in flight and no cross-warp barrier is needed.
-            const int kw = warp - 6;
-            constexpr int F4 = RP / 4;                    // float4 per lane per unit (a unit is 32 x RP floats)
-            float* st = stage + kw * C::STAGE_F;         // rotated staging: (k, r) at st[k*RP + (r + k) % RP]
-            float* prow = st + 32 * RP;                  // P[a, :] of the current `a`
-            float4 qreg[F4];
-            auto load_q = [&](int64_t b0) {
-#pragma unroll
-                for (int f = 0; f < F4; ++f) {
-                    const int idx = lane + f * 32;        // float4 index within the unit, row-major [32][RP/4]
-                    const int k = idx / F4;
-                    qreg[f] = (b0 + k < p.B) ? __ldg(reinterpret_cast<const float4*>(p.Q + (b0 + k) * RP) + (idx % F4))
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            };
-            uint32_t g_base = 0;                          // global index of the current item's first unit
-            int a_loaded = -1;
+    } else if (warp < 12) {
+        // ================= B producer: TMA loads of the pre-split small operand, one 32-element unit at a time =========
+        if (warp == 10) {
+            Ring br;
             for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
                 const int64_t kr = it / p.m_tiles;
                 const int64_t c_begin = kr * p.chunks_per_range;
                 const int64_t c_end = min(p.total_chunks, c_begin + p.chunks_per_range);
-                const int n = (int)(c_end - c_begin) * KO;      // units of this item
-                const int units_per_a = (int)p.chunks_per_a * KO;
-                const int a0 = (int)(c_begin / p.chunks_per_a);
-                const int bu0 = (int)(c_begin - (int64_t)a0 * p.chunks_per_a) * KO;
-                int i = (int)((kw - (int)(g_base & 3u)) & 3);     // first local unit handled by this warp
-                int a = a0, bu = bu0 + i;
-                while (bu >= units_per_a) { bu -= units_per_a; ++a; }
-                if (i < n) load_q((int64_t)bu * 32);
-                for (; i < n; i += 4) {
-                    const uint32_t g = g_base + (uint32_t)i;
-                    const int slot = (int)(g & (BS - 1));
-                    const uint32_t use_parity = (g / BS) & 1u;
-                    __syncwarp();                          // previous unit's staging reads are done
+                int bc = (int)(c_begin % p.chunks_per_a);
+                for (int64_t c = c_begin; c < c_end; ++c) {
 #pragma unroll
-                    for (int f = 0; f < F4; ++f) {
-                        const int idx = lane + f * 32;
-                        const int k = idx / F4, r = (idx % F4) * 4;
-                        float* rowp = st + k * RP;
-                        rowp[(r + 0 + k) & (RP - 1)] = qreg[f].x;
-                        rowp[(r + 1 + k) & (RP - 1)] = qreg[f].y;
-                        rowp[(r + 2 + k) & (RP - 1)] = qreg[f].z;
-                        rowp[(r + 3 + k) & (RP - 1)] = qreg[f].w;
-                    }
-                    if (a != a_loaded) {
-                        for (int r = lane; r < RP; r += 32) prow[r] = p.P ? __ldg(p.P + (int64_t)a * RP + r) : 1.0f;
-                        a_loaded = a;
-                    }
-                    // coordinates of this warp's next unit; prefetch its Q rows from L2
-                    int a_n = a, bu_n = bu + 4;
-                    while (bu_n >= units_per_a) { bu_n -= units_per_a; ++a_n; }
-                    if (i + 4 < n) load_q((int64_t)bu_n * 32);
-                    __syncwarp();
-                    mbar_wait(&b_empty[slot], use_parity ^ 1u);
-                    unsigned char* bhi = b_smem + slot * C::B_UNIT;
-                    unsigned char* blo = bhi + RP * 128;
-                    const float* srow = st + lane * RP;                   // lane = k within the unit
-                    if (!(p.debug & 1))
-#pragma unroll
-                    for (int r0 = 0; r0 < RP; r0 += 8) {
-                        float qv[8], pv[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { qv[j] = srow[(r0 + j + lane) & (RP - 1)]; pv[j] = prow[r0 + j]; }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int r = r0 + j;
-                            const float krv = __fmul_rn(pv[j], qv[j]);
-                            const uint32_t hbits = __float_as_uint(krv) & 0xFFFFE000u;
-                            const float lo = krv - __uint_as_float(hbits);
-                            const uint32_t off = r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4;
-                            *reinterpret_cast<uint32_t*>(bhi + off) = hbits;
-                            *reinterpret_cast<float*>(blo + off) = lo;
+                    for (int u = 0; u < KO; ++u) {
+                        mbar_wait(&b_empty[br.idx], br.phase ^ 1u);
+                        if (elect_one_sync()) {
+                            mbar_expect_tx(&b_full[br.idx], C::B_UNIT);
+                            unsigned char* dst = b_smem + br.idx * C::B_UNIT;
+                            tma_load_2d(dst, &bhi_map, &b_full[br.idx], bc * KS + u * 32, 0);
+                            tma_load_2d(dst + RP * 128, &blo_map, &b_full[br.idx], bc * KS + u * 32, 0);
                         }
+                        __syncwarp();
+                        br.advance(BS);
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core reads
-                    mbar_arrive(&b_full[slot]);
-                    a = a_n; bu = bu_n;
+                    if (++bc == (int)p.chunks_per_a) bc = 0;
                 }
-                g_base += (uint32_t)n;
             }
         }
     } else {
@@ -496,30 +513,48 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             const int64_t kr = it / p.m_tiles;
             const int64_t c_begin = kr * p.chunks_per_range;
             const int64_t c_end = min(p.total_chunks, c_begin + p.chunks_per_range);
-            const int n = (int)(c_end - c_begin) * KO;
-            const int ngroups = (n + GU - 1) / GU;
+            const int n = (int)(c_end - c_begin) * KO;                    // 32-element units of this item
+            const int units_per_a = (int)p.chunks_per_a * KO;
+            int a = (int)(c_begin / p.chunks_per_a);
+            int bu = (int)(c_begin - (int64_t)a * p.chunks_per_a) * KO;   // unit index within the current `a`
             float acc[RP];
 #pragma unroll
             for (int c = 0; c < RP; ++c) acc[c] = 0.f;
-            for (int g = 0; g < ngroups; ++g) {
+            int done = 0;
+            while (done < n) {
+                // this group: up to GU units, never across an `a` boundary when the result is scaled by P[a, :]
+                int len = min(GU, n - done);
+                if (p.P != nullptr) len = min(len, units_per_a - bu);
                 const uint32_t buf = G & 1u;
+                if (warp == 12) TLB_TRACE(4, tri, 0);
                 mbar_wait(&d_full[buf], (G >> 1) & 1u);
+                if (warp == 12) TLB_TRACE(4, tri, 1);
                 tc_fence_after();
-                if (!(p.debug & 8))
+                float part[RP];
 #pragma unroll
-                for (int part = 0; part < 2; ++part) {        // hi*hi block, cross-term block of this set
+                for (int c0 = 0; c0 < RP; c0 += 32) {
+                    uint32_t r0[32], r1[32];
+                    TLB_TMEM_LD32(lane_addr + buf * C::D_COLS + c0, r0);            // hi*hi block
+                    TLB_TMEM_LD32(lane_addr + buf * C::D_COLS + RP + c0, r1);       // cross-term block
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int c0 = 0; c0 < RP; c0 += 32) {
-                        uint32_t r[32];
-                        TLB_TMEM_LD32(lane_addr + buf * C::D_COLS + part * RP + c0, r);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) acc[c0 + c] += __uint_as_float(r[c]);
-                    }
+                    for (int c = 0; c < 32; ++c) part[c0 + c] = __uint_as_float(r0[c]) + __uint_as_float(r1[c]);
                 }
                 tc_fence_before();
                 mbar_arrive(&d_empty[buf]);
+                if (p.P != nullptr) {
+                    const float* prow = p.P + (int64_t)a * RP;              // Khatri-Rao outer factor of this `a`
+#pragma unroll
+                    for (int c = 0; c < RP; ++c) acc[c] = fmaf(__ldg(prow + c), part[c], acc[c]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < RP; ++c) acc[c] += part[c];
+                }
+                if (warp == 12) { TLB_TRACE(4, tri, 2); ++tri; }
                 ++G;
+                done += len;
+                bu += len;
+                if (bu >= units_per_a) { bu = 0; ++a; }
             }
             const int64_t gm = (int64_t)mt * TM + row;
             if (gm < p.M) {
@@ -586,7 +621,7 @@ int launch_cfg(const TcStreamLaunch& l, cudaStream_t stream) {
 
 template <int RP, int XL>
 int launch_bm(const TcStreamLaunch& l, cudaStream_t s) {
-    return l.b_mode == TC_B_KR ? launch_cfg<RP, XL, TC_B_KR>(l, s) : launch_cfg<RP, XL, TC_B_MAT>(l, s);
+    return launch_cfg<RP, XL, TC_B_MAT>(l, s);
 }
 template <int RP>
 int launch_xl(const TcStreamLaunch& l, cudaStream_t s) {
@@ -623,19 +658,26 @@ int tc_group_units() {
     if (units < 0) {
         const char* e = getenv("TLB200_TC_FLUSH");
         units = e ? atoi(e) : 8;
-        if (units < 1) units = 1;
+        if (units < 2) units = 2;
+        units &= ~1;          // whole tiles (2 units) per group
     }
     return units;
 }
+
+static long long* g_trace = nullptr;
 
 int tc_stream_launch(const TcStreamLaunch& l_in, cudaStream_t stream) {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("TLB200_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
     TcStreamLaunch l = l_in;
     l.p.debug = dbg;
+    l.p.trace = g_trace;
     if (l.rp == 32) return launch_xl<32>(l, stream);
     if (l.rp == 64) return launch_xl<64>(l, stream);
     return TLB200_EUNSUPPORTED;
 }
 
 }  // namespace tlb200
+
+// perf triage hook (not part of the public ABI): device buffer of 5*256*8 int64 receiving CTA 0's timestamps
+extern "C" void tlb200_debug_set_trace(void* device_buffer) { tlb200::g_trace = static_cast<long long*>(device_buffer); }

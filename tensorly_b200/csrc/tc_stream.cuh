@@ -17,8 +17,7 @@ enum TcXLayout {
     TC_X_MMAJOR = 2      // tile = 64 k-rows x 128 m (m contiguous in memory)
 };
 enum TcBMode {
-    TC_B_KR = 0,         // B(k=(a,b), n) = P[a, n] * Q[b, n], synthesised by 4 warps
-    TC_B_MAT = 1         // B(k=b, n) from pre-split hi/lo matrices via TMA
+    TC_B_MAT = 1         // B(k=b, n) from pre-split hi/lo matrices via TMA ([RP rows][K], K-major)
 };
 
 struct TcStreamParams {
@@ -33,20 +32,20 @@ struct TcStreamParams {
     int64_t k_ranges;
     int64_t chunks_per_range;
     int group_units;           // 32-element K units per TMEM accumulation group (RZ accumulate => keep short)
-    // B operand, KR mode
+    // optional per-`a` scaling of the result (MTTKRP: the outer Khatri-Rao table), applied by the epilogue
     const float* P;            // [A][RP] or null
-    const float* Q;            // [B][RP]
     // output: out[kr * sOk + m * sOm + n * sOn], n < n_valid
     float* out;
     int64_t sOk, sOm, sOn;
     int n_valid;
+    long long* trace;          // perf triage only: per-role clock64 timestamps of CTA 0 (null = off)
     int debug;                 // TLB200_TC_DEBUG bitmask (perf triage only): 1 skip KR math, 2 skip MMAs, 4 skip TMEM stores, 8 skip epilogue loads
 };
 
 struct TcStreamLaunch {
     TcStreamParams p;
     CUtensorMap x_map;         // see tc_stream.cu for the dims per layout
-    CUtensorMap bhi_map, blo_map;   // TC_B_MAT only
+    CUtensorMap bhi_map, blo_map;   // pre-split small operand: [RP rows][Kpad] hi / lo, box {32, RP}, SWIZZLE_128B
     int rp;                    // 32 or 64
     int x_layout;              // TcXLayout
     int b_mode;                // TcBMode

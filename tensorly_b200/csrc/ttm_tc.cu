@@ -122,7 +122,7 @@ int ttm_tc_launch(const float* x, int64_t L, int64_t J, int64_t T, const float* 
     p.k_ranges = g.A;                         // one item per (row tile, batch): all of K
     p.chunks_per_range = p.chunks_per_a;
     p.group_units = tc_group_units();
-    p.P = nullptr; p.Q = nullptr;
+    p.P = nullptr;
     p.out = out;
     if (g.layout == TC_X_MMAJOR) { p.sOk = I * T; p.sOm = 1; p.sOn = T; }
     else                         { p.sOk = 0; p.sOm = I; p.sOn = 1; }
