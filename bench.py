@@ -351,7 +351,7 @@ def run_ours(args):
     if rank_id == 0:
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if world == 1 and os.path.exists(tp):      # the ncu capture is of the 1-GPU launch of this workload
             try:
                 traffic = json.load(open(tp)).get(args.workload, {}).get(path_used)
             except Exception:

@@ -96,16 +96,17 @@ gram_reduce_kernel(const T* __restrict__ partial, int nblk, int RR, T* __restric
 constexpr int kSolveRows = 64;   // rows of M per CTA
 constexpr int kSolveThreads = 256;
 
-// A = V^T in shared memory (ld = R + 1); perm[] row permutation.  All threads of the CTA.
+// A = V^T in shared memory (ld = R + 1); perm[] row permutation.  All 256 threads of the CTA, arranged
+// as 8 warps: lane = column offset, warp = row offset (no integer divisions in the O(R^3) part).
 template <typename T>
 __device__ void lu_factor_smem(T* A, int* perm, int R, int ld, int* s_piv) {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     for (int k = 0; k < R; ++k) {
-        // pivot search by warp 0
-        if (tid < 32) {
+        // pivot search by warp 0 (partial pivoting, first maximum like LAPACK's idamax)
+        if (ty == 0) {
             T best = T(-1);
             int bi = k;
-            for (int i = k + tid; i < R; i += 32) {
+            for (int i = k + tx; i < R; i += 32) {
                 T v = A[i * ld + k];
                 v = v < T(0) ? -v : v;
                 if (v > best) { best = v; bi = i; }
@@ -116,27 +117,24 @@ __device__ void lu_factor_smem(T* A, int* perm, int R, int ld, int* s_piv) {
                 int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                 if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
             }
-            if (tid == 0) *s_piv = bi;
+            if (tx == 0) *s_piv = bi;
         }
         __syncthreads();
         const int piv = *s_piv;
-        if (piv != k) {
-            for (int c = tid; c < R; c += blockDim.x) {
+        if (piv != k && ty == 0) {
+            for (int c = tx; c < R; c += 32) {
                 T t = A[k * ld + c]; A[k * ld + c] = A[piv * ld + c]; A[piv * ld + c] = t;
             }
-            if (tid == 0) { int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t; }
+            if (tx == 0) { int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t; }
         }
         __syncthreads();
-        const T pivot = A[k * ld + k];
-        const T inv = T(1) / pivot;
-        // multipliers
-        for (int i = k + 1 + tid; i < R; i += blockDim.x) A[i * ld + k] *= inv;
-        __syncthreads();
-        // trailing update
-        const int n = R - k - 1;
-        for (int e = tid; e < n * n; e += blockDim.x) {
-            const int i = k + 1 + e / n, j = k + 1 + e % n;
-            A[i * ld + j] -= A[i * ld + k] * A[k * ld + j];
+        const T inv = T(1) / A[k * ld + k];
+        // row i is owned by one warp: all lanes read A[i][k], then lane 0 overwrites it with the multiplier
+        for (int i = k + 1 + ty; i < R; i += 8) {
+            const T m = A[i * ld + k] * inv;
+            for (int j = k + 1 + tx; j < R; j += 32) A[i * ld + j] -= m * A[k * ld + j];
+            __syncwarp();
+            if (tx == 0) A[i * ld + k] = m;
         }
         __syncthreads();
     }
