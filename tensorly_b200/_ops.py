@@ -87,8 +87,25 @@ class _Device:
             torch.cuda.set_device(self.prev)
 
 
+# Scratch buffers are cached per (device, stream) and only ever grow: calls on one stream are serialised, so
+# reusing the buffer is safe, and it keeps 100 MB-sized cudaMalloc/cudaFree pairs out of the hot loop.
+# (Under CUDA-graph capture the capture stream is a different key, so the buffer comes from the graph's pool.)
+_WS_CACHE: dict = {}
+
+
 def _workspace(nbytes: int, like: torch.Tensor) -> torch.Tensor:
-    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=like.device)
+    nbytes = max(int(nbytes), 256)
+    key = (like.device.index, torch.cuda.current_stream(like.device).cuda_stream)
+    buf = _WS_CACHE.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=like.device)
+        _WS_CACHE[key] = buf
+    return buf
+
+
+def release_workspaces() -> None:
+    """Drop the cached scratch buffers (they are re-created on demand)."""
+    _WS_CACHE.clear()
 
 
 def _prod(xs: Iterable[int]) -> int:

@@ -25,6 +25,7 @@ GPUs, gloo in the CPU tests.
 from __future__ import annotations
 
 import math
+import os
 from typing import Callable, List, Optional, Sequence
 
 import numpy as np
@@ -190,8 +191,11 @@ class CPALS:
         """One ALS sweep.  On a single GPU the first sweep runs eagerly (lazy one-time
         initialisation), the second is captured into a CUDA graph, and every later sweep
         replays that graph: one launch per sweep instead of ~20."""
+        # The sharded sweep stays eager by default: capturing the NCCL all-reduces works and is ~4 % faster at
+        # 2 GPUs, but process-group teardown then hung in our runs (torch 2.11 / NCCL 2.28).  TLB200_DIST_GRAPH=1 opts in.
         graphable = (use_graph and getattr(self.ops, "supports_graphs", False) and self.x.is_cuda
-                     and not self.comm.active)
+                     and (not self.comm.active or os.environ.get("TLB200_DIST_GRAPH", "0") == "1")
+                     and not (self.comm.active and self.shard_mode == self.ndim - 1))
         if not graphable:
             self.sweep_eager(with_error)
             return
