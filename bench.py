@@ -195,6 +195,9 @@ def run_ours(args):
     device = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the sharded sweep (MTTKRP + NCCL all-reduce + solve, 3 modes) is replayed from one CUDA graph;
+        # the graph is destroyed before the process group at the end (the reverse order hangs in teardown)
+        os.environ.setdefault("TLB200_DIST_GRAPH", "1")
         dist.init_process_group("nccl", device_id=device)
     wl = WORKLOADS[args.workload]
     shape, R = wl["shape"], wl["rank"]
@@ -379,6 +382,18 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # teardown must never turn a finished measurement into a hang: drop the CUDA graphs (they hold NCCL
+        # kernels) before the communicator, and bail out hard if the collective teardown stalls anyway
+        import gc
+        def _bail():
+            time.sleep(30)
+            os._exit(0)
+        threading.Thread(target=_bail, daemon=True).start()
+        state._graph = None
+        del state
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

@@ -1,0 +1,8 @@
+#!/bin/bash
+# two-issuer MMA: correctness first, then timings
+timeout 300 python scripts/tc_check.py 2>&1 | tail -12
+timeout 300 python scripts/prof_time.py 1024 32 2>&1 | tail -1
+timeout 300 python scripts/prof_time.py 1280 64 2>&1 | tail -1
+timeout 300 python scripts/prof_time.py 768 64 2>&1 | tail -1
+timeout 300 python scripts/ttm_check.py 2>&1 | tail -8
+timeout 900 python -m pytest tests -m gpu -x -q -p no:cacheprovider 2>&1 | tail -5

@@ -10,6 +10,8 @@
 #include "mttkrp_tc.cuh"
 #include "tc_stream.cuh"
 
+#include <cstdlib>
+
 namespace tlb200 {
 
 static int layout_for(const tlb200_mttkrp_plan_t& pl) {
@@ -33,14 +35,20 @@ void mttkrp_tc_fill_plan(tlb200_mttkrp_plan_t* pl, int64_t rank) {
     const int ks = tc_chunk_k(layout_for(*pl));
     const int64_t m_tiles = ceil_div(pl->J, 128);
     const int64_t total = pl->A * ceil_div(pl->B, ks);
-    // persistent CTAs: aim at 148*w equal items, w in [1,4], at least ~16 chunks per item
-    int64_t w = (m_tiles * total) / ((int64_t)kNumSMs * 64);
-    if (w < 1) w = 1;
-    if (w > 4) w = 4;
-    int64_t splits = ceil_div((int64_t)kNumSMs * w, m_tiles);
-    if (splits > total / 4) splits = total / 4;
-    if (splits < 1) splits = 1;
-    const int64_t per = ceil_div(total, splits);
+    // Persistent CTAs (one per SM) take work items (row tile, K range) round-robin.  Pick the split-K factor
+    // whose item count fills whole rounds of 148 best; among equally good ones the smallest (longer items,
+    // fewer partials), but at least 8 tiles per item and at most 8 rounds.
+    int64_t best = 1;
+    double best_eff = -1.0;
+    const int64_t s_max = total / 8 > 0 ? total / 8 : 1;
+    for (int64_t s = 1; s <= s_max && m_tiles * s <= (int64_t)kNumSMs * 8; ++s) {
+        const int64_t per = ceil_div(total, s);
+        const int64_t items = m_tiles * ceil_div(total, per);
+        const double eff = (double)items / (double)(ceil_div(items, kNumSMs) * kNumSMs);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+    }
+    if (const char* e = getenv("TLB200_TC_SPLITS")) { const int64_t v = atoll(e); if (v >= 1 && v <= total) best = v; }
+    const int64_t per = ceil_div(total, best);
     pl->splits = ceil_div(total, per);
 }
 

@@ -97,6 +97,21 @@ __device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t parity_a, u
         if (++spins > SPIN_LIMIT) asm volatile("trap;");
     }
 }
+// three barriers at once (A tile + both B units of a tile)
+__device__ __forceinline__ void mbar_wait3(uint64_t* bar_a, uint32_t pa, uint64_t* bar_b, uint32_t pb, uint64_t* bar_c, uint32_t pc) {
+    uint32_t da = 0, db = 0, dc = 0, spins = 0;
+    const uint32_t aa = smem_u32(bar_a), ab = smem_u32(bar_b), ac = smem_u32(bar_c);
+    while (true) {
+        if (!da) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                              : "=r"(da) : "r"(aa), "r"(pa) : "memory");
+        if (!db) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                              : "=r"(db) : "r"(ab), "r"(pb) : "memory");
+        if (!dc) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                              : "=r"(dc) : "r"(ac), "r"(pc) : "memory");
+        if (da && db && dc) break;
+        if (++spins > SPIN_LIMIT) asm volatile("trap;");
+    }
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -185,7 +200,7 @@ struct Cfg {
     static constexpr int OFF_X = 0;
     static constexpr int OFF_B = OFF_X + XS * X_STAGE;
     static constexpr int OFF_BAR = OFF_B + BS * B_UNIT;
-    static constexpr int NUM_BARS = 2 * XS + 2 * AS + 2 * BS + 4;
+    static constexpr int NUM_BARS = 2 * XS + 2 * AS + 2 * BS + 4 + 2;   // + the two MMA-issuer turn tokens
     static constexpr int SMEM = OFF_BAR + NUM_BARS * 8 + 16;
     static constexpr int TMEM_COLS = 2 * D_COLS + AS * A_COLS;
     static_assert(AS >= 2 && AS % KO == 0, "A ring must hold whole tiles");
@@ -212,7 +227,8 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     uint64_t* b_empty = b_full + BS;
     uint64_t* d_full = b_empty + BS;
     uint64_t* d_empty = d_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
+    uint64_t* tok = d_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tok + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n_items = (int64_t)p.m_tiles * p.k_ranges;
@@ -223,7 +239,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         for (int i = 0; i < XS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 128); }
         for (int i = 0; i < AS; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 128); mbar_init(&tok[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -273,9 +289,14 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 }
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer (whole warp runs the loop, one elected lane issues) =================
+    } else if (warp == 1 || warp == 11) {
+        // ================= MMA issuers (two warps take alternate tiles; whole warp loops, one elected lane issues) ====
+        // While one warp's MMAs execute, the other has already polled the barriers of the next tile and only waits
+        // for its turn, so the tensor pipe no longer idles through the ~250 clk barrier round trips.
         {
+            const int mw = warp == 1 ? 0 : 1;       // this issuer takes tiles with (global tile index & 1) == mw
+            uint32_t gt = 0;                        // global tile index (per CTA)
+            uint32_t own = 0;                       // tiles issued by this warp so far
             constexpr uint32_t idesc1 = idesc_tf32(TM, 2 * RP);   // A_hi x [B_hi | B_lo] -> columns [0, 2RP)
             constexpr uint32_t idesc2 = idesc_tf32(TM, RP);       // A_lo x B_hi          -> columns [RP, 2RP)
             Ring ar, br;
@@ -293,30 +314,49 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 const int n = (int)(c_end - c_begin);           // tiles (chunks) of this item, KO units each
                 int ug = 0;
                 int bc = (int)(c_begin % p.chunks_per_a);       // tile index within the current `a`
-                for (int i = 0; i < n; ++i) {
+                for (int i = 0; i < n; ++i, ++gt) {
                     const bool a_end = p.P != nullptr && bc + 1 == (int)p.chunks_per_a;   // last tile of this `a`
                     if (++bc == (int)p.chunks_per_a) bc = 0;
+                    const bool mine = (gt & 1u) == (uint32_t)mw;
+                    // group bookkeeping runs for every tile in both issuers; only the owner waits and issues
+                    bool first[KO], gend[KO];
+                    uint32_t dbuf[KO];
+#pragma unroll
+                    for (int u = 0; u < KO; ++u) {
+                        dbuf[u] = G & 1u;
+                        first[u] = ug == 0;
+                        if (mine && first[u] && G >= 2) mbar_wait(&d_empty[dbuf[u]], ((G >> 1) - 1) & 1u);
+                        gend[u] = (ug + 1 == GU) || ((i == n - 1 || a_end) && u == KO - 1);
+                        if (gend[u]) { ++G; ug = 0; } else { ++ug; }
+                    }
                     // one A barrier pair per tile: both units of a tile are stored and published together
                     const int as0 = ar.idx;
                     const uint32_t aph = ar.phase;
+                    const Ring b0 = br;
+                    Ring b1 = br;
+                    if constexpr (KO == 2) b1.advance(BS);
 #pragma unroll
-                    for (int u = 0; u < KO; ++u) {
-                        const uint32_t buf = G & 1u;
-                        if (ug == 0 && G >= 2) mbar_wait(&d_empty[buf], ((G >> 1) - 1) & 1u);
-                        TLB_TRACE(1, tri, 0);
-                        if (u == 0) mbar_wait2(&a_full[as0], aph, &b_full[br.idx], br.phase);
-                        else        mbar_wait(&b_full[br.idx], br.phase);
-                        TLB_TRACE(1, tri, 2);
-                        tc_fence_after();
-                        const uint32_t d1 = d_base + buf * C::D_COLS;
-                        const uint32_t d2 = d1 + RP;
-                        const uint32_t a_hi = a_base + ar.idx * C::A_COLS;       // a_lo = a_hi + 32
-                        const uint32_t blo = bdesc_lo0 + br.idx * (C::B_UNIT >> 4); // low word of the K-major SW128 descriptor
-                        const bool group_end = (ug + 1 == GU) || ((i == n - 1 || a_end) && u == KO - 1);
-                        if (elect_one_sync()) {
-                            if (!(p.debug & 2)) {
+                    for (int u = 0; u < KO; ++u) { ar.advance(AS); br.advance(BS); }
+                    if (!mine) continue;
+                    TLB_TRACE(1 + 2 * mw, tri, 0);
+                    // one overlapped wait per tile: the A tile and its B unit(s)
+                    if constexpr (KO == 2) mbar_wait3(&a_full[as0], aph, &b_full[b0.idx], b0.phase, &b_full[b1.idx], b1.phase);
+                    else mbar_wait2(&a_full[as0], aph, &b_full[b0.idx], b0.phase);
+                    // my turn: the other issuer has put its tile into the pipe (accumulate order within a group)
+                    if (mw == 1) mbar_wait(&tok[1], own & 1u);
+                    else if (own > 0) mbar_wait(&tok[0], (own - 1) & 1u);
+                    TLB_TRACE(1 + 2 * mw, tri, 2);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        if (!(p.debug & 2)) {
+#pragma unroll
+                            for (int u = 0; u < KO; ++u) {
+                                const uint32_t d1 = d_base + dbuf[u] * C::D_COLS;
+                                const uint32_t d2 = d1 + RP;
+                                const uint32_t a_hi = a_base + (as0 + u) * C::A_COLS;       // a_lo = a_hi + 32
+                                const uint32_t blo = bdesc_lo0 + (u == 0 ? b0.idx : b1.idx) * (C::B_UNIT >> 4); // low descriptor word
                                 // first K step of a group overwrites the accumulators, everything else accumulates
-                                mma_ts_tf32(d1, a_hi, ((uint64_t)bdesc_hi << 32) | blo, idesc1, ug == 0 ? 0u : 1u);
+                                mma_ts_tf32(d1, a_hi, ((uint64_t)bdesc_hi << 32) | blo, idesc1, first[u] ? 0u : 1u);
                                 mma_ts_tf32_acc(d2, a_hi + 32, ((uint64_t)bdesc_hi << 32) | blo, idesc2);
 #pragma unroll
                                 for (int ks = 1; ks < 4; ++ks) {
@@ -325,16 +365,20 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                                     mma_ts_tf32_acc(d2, a_hi + 32 + ks * 8, db, idesc2);
                                 }
                             }
-                            tc_commit(&b_empty[br.idx]);
-                            if (u == KO - 1) tc_commit(&a_empty[as0]);
-                            if (group_end) tc_commit(&d_full[buf]);
                         }
-                        __syncwarp();
-                        TLB_TRACE(1, tri, 3); ++tri;
-                        ar.advance(AS);
-                        br.advance(BS);
-                        if (group_end) { ++G; ug = 0; } else { ++ug; }
+                        // hand the turn over before the (slower) commits
+                        tc_fence_before();
+                        mbar_arrive(&tok[mw ^ 1]);
+                        tc_commit(&b_empty[b0.idx]);
+                        if constexpr (KO == 2) tc_commit(&b_empty[b1.idx]);
+                        tc_commit(&a_empty[as0]);
+#pragma unroll
+                        for (int u = 0; u < KO; ++u)
+                            if (gend[u]) tc_commit(&d_full[dbuf[u]]);
                     }
+                    __syncwarp();
+                    TLB_TRACE(1 + 2 * mw, tri, 3); ++tri;
+                    ++own;
                 }
             }
         }
