@@ -5,8 +5,9 @@
 //                        multiple of 32 each TMA box fetches two adjacent 128-byte lines per row
 //                        (4-D map {32, B/32, J, A}), the DRAM-friendly shape; otherwise one line.
 //   kept mode last     : X[a][b][j], j contiguous  -> rows = j, tiles of 64 b-rows x 128 j.
-// Split-K: item (j-tile, split) covers a contiguous range of K chunks; partials are summed by
-// the deterministic reduction kernel of mttkrp.cu.
+// Split-K: item (j-tile, b block, a range): the b block's rows of the inner Khatri-Rao table stay resident in
+// shared memory while the item streams X over its `a` range (no per-tile reload through L2); every item
+// writes one partial, summed by the deterministic reduction kernel of mttkrp.cu.
 #include "mttkrp_tc.cuh"
 #include "tc_stream.cuh"
 
@@ -30,26 +31,41 @@ bool mttkrp_tc_supported(const tlb200_mttkrp_plan_t& pl, int64_t rank, int dtype
     return tc_available();
 }
 
+// chunks of the inner Khatri-Rao table one work item keeps resident in shared memory
+static int block_chunks(const tlb200_mttkrp_plan_t& pl, int64_t rank_padded) {
+    const int ks = tc_chunk_k(layout_for(pl));
+    return tc_b_slots((int)rank_padded) * 32 / ks;
+}
+
 void mttkrp_tc_fill_plan(tlb200_mttkrp_plan_t* pl, int64_t rank) {
     pl->rank_padded = rank <= 32 ? 32 : 64;
     const int ks = tc_chunk_k(layout_for(*pl));
+    const int nb = block_chunks(*pl, pl->rank_padded);
     const int64_t m_tiles = ceil_div(pl->J, 128);
-    const int64_t total = pl->A * ceil_div(pl->B, ks);
-    // Persistent CTAs (one per SM) take work items (row tile, K range) round-robin.  Pick the split-K factor
-    // whose item count fills whole rounds of 148 best; among equally good ones the smallest (longer items,
-    // fewer partials), but at least 8 tiles per item and at most 8 rounds.
+    const int64_t cpa = ceil_div(pl->B, ks);
+    const int64_t n_bblocks = ceil_div(cpa, nb);
+    // Persistent CTAs (one per SM) take work items (row tile, b block, a range) round-robin.  Every item
+    // writes one partial result (one X tile's worth of traffic at rank 64) and pays a pipeline fill of a few
+    // tiles, so score = how well the items fill whole rounds of 148 CTAs x the useful share of an item.
     int64_t best = 1;
-    double best_eff = -1.0;
-    const int64_t s_max = total / 8 > 0 ? total / 8 : 1;
-    for (int64_t s = 1; s <= s_max && m_tiles * s <= (int64_t)kNumSMs * 8; ++s) {
-        const int64_t per = ceil_div(total, s);
-        const int64_t items = m_tiles * ceil_div(total, per);
+    double best_score = -1.0;
+    const double per_item = 2.5 + 2.0 * (double)pl->rank_padded / 64.0;
+    for (int64_t s = 1; s <= pl->A; ++s) {
+        const int64_t apr = ceil_div(pl->A, s);
+        const int64_t k = ceil_div(pl->A, apr);
+        if (k != s) continue;                                  // same partition as a smaller s
+        const int64_t items = m_tiles * n_bblocks * k;
+        if (items > (int64_t)kNumSMs * 8 && s > 1) break;
+        const double tiles = (double)apr * (double)(cpa < nb ? cpa : nb);
         const double eff = (double)items / (double)(ceil_div(items, kNumSMs) * kNumSMs);
-        if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+        const double score = eff * tiles / (tiles + per_item);
+        if (score > best_score + 1e-9) { best_score = score; best = k; }
     }
-    if (const char* e = getenv("TLB200_TC_SPLITS")) { const int64_t v = atoll(e); if (v >= 1 && v <= total) best = v; }
-    const int64_t per = ceil_div(total, best);
-    pl->splits = ceil_div(total, per);
+    if (const char* e = getenv("TLB200_TC_SPLITS")) {
+        const int64_t v = atoll(e);
+        if (v >= 1 && v <= pl->A) best = ceil_div(pl->A, ceil_div(pl->A, v));
+    }
+    pl->splits = best * n_bblocks;         // number of partial results
 }
 
 size_t mttkrp_tc_extra_workspace(const tlb200_mttkrp_plan_t&) { return 0; }
@@ -95,10 +111,13 @@ int mttkrp_tc_launch(const float* x, const tlb200_mttkrp_plan_t& pl, int64_t /*r
     TcStreamParams& p = l.p;
     p.M = pl.J; p.A = pl.A; p.B = pl.B;
     p.chunks_per_a = ceil_div(pl.B, ks);
-    p.total_chunks = pl.A * p.chunks_per_a;
     p.m_tiles = (int)ceil_div(pl.J, 128);
-    p.k_ranges = pl.splits;
-    p.chunks_per_range = ceil_div(p.total_chunks, pl.splits);
+    p.nb = block_chunks(pl, pl.rank_padded);
+    p.n_bblocks = (int)ceil_div(p.chunks_per_a, p.nb);
+    p.k_ranges = pl.splits / p.n_bblocks;
+    if (p.k_ranges < 1 || p.k_ranges * p.n_bblocks != pl.splits) return TLB200_EINVAL;
+    p.a_per_range = ceil_div(pl.A, p.k_ranges);
+    p.b_resident = 1;
     p.group_units = tc_group_units();
     p.P = P;     // outer Khatri-Rao table: applied per `a` by the epilogue
     p.out = partial;

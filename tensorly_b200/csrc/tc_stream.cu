@@ -165,6 +165,12 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
                    "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),        \
                    "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                      \
                  : "r"(taddr))
+#define TLB_TMEM_LD16(taddr, r)                                                                                          \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                             \
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                                      \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),    \
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])                       \
+                 : "r"(taddr))
 #define TLB_TMEM_ST32(taddr, r)                                                                                          \
     asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                        \
                  "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" \
@@ -185,18 +191,40 @@ struct Ring {
     __device__ __forceinline__ void advance(int n) { if (++idx == n) { idx = 0; phase ^= 1u; } }
 };
 
+// work item = (row tile, b block, a range); consecutive items differ in the row tile first
+struct TcItem {
+    int mt;          // row tile
+    int a0, a1;      // range of the outer K index
+    int bc0, bc1;    // range of K chunks (KS elements each) inside every `a`
+    int64_t part;    // index of the partial result this item writes
+};
+__device__ __forceinline__ TcItem tc_item(const TcStreamParams& p, int64_t it) {
+    TcItem t;
+    t.mt = (int)(it % p.m_tiles);
+    const int64_t r = it / p.m_tiles;
+    const int bb = (int)(r % p.n_bblocks);
+    const int64_t kr = r / p.n_bblocks;
+    t.part = r;
+    t.a0 = (int)min(p.A, kr * p.a_per_range);
+    t.a1 = (int)min(p.A, (int64_t)t.a0 + p.a_per_range);
+    t.bc0 = bb * p.nb;
+    t.bc1 = (int)min(p.chunks_per_a, (int64_t)t.bc0 + p.nb);
+    return t;
+}
+
 // ---- compile-time configuration per (RP, X layout) -------------------------------------
 template <int RP, int XL>
 struct Cfg {
     static constexpr int KS = XL == TC_X_KMAJOR_1 ? 32 : 64;        // K extent of one X stage
     static constexpr int KO = KS / 32;                              // 32-element units per X stage
     static constexpr int X_STAGE = TM * KS * 4;
-    static constexpr int XS = KS == 32 ? 8 : (RP == 32 ? 5 : 4);     // bytes in flight per SM hide HBM latency
+    static constexpr int XS = KS == 32 ? 8 : 4;                     // bytes in flight per SM hide HBM latency
     static constexpr int D_COLS = 2 * RP;                           // per accumulator set: [hi*hi (RP) | hi*lo + lo*hi (RP)]
     static constexpr int A_COLS = 64;                               // TMEM columns per A unit: [hi 32 | lo 32]
     static constexpr int AS = RP == 32 ? 6 : 4;
     static constexpr int B_UNIT = 2 * RP * 128;                     // [hi RP rows | lo RP rows] x 128 B, K-major SW128
-    static constexpr int BS = 4;                                    // B-operand ring (32-element units)
+    static constexpr int BS = RP == 32 ? 8 : 6;                     // B-operand slots (32-element units): 64 / 96 KB, a ring
+                                                                    // (streamed B) or one resident b block per item
     static constexpr int OFF_X = 0;
     static constexpr int OFF_B = OFF_X + XS * X_STAGE;
     static constexpr int OFF_BAR = OFF_B + BS * B_UNIT;
@@ -205,6 +233,9 @@ struct Cfg {
     static constexpr int TMEM_COLS = 2 * D_COLS + AS * A_COLS;
     static_assert(AS >= 2 && AS % KO == 0, "A ring must hold whole tiles");
     static_assert(TMEM_COLS <= 512, "TMEM budget");
+    // the two convert sets take alternate tiles: with an even ring every stage always belongs to the same set,
+    // so a set observes every phase of the barriers it waits on (an odd ring would alias phase parities)
+    static_assert(XS % 2 == 0, "X ring must be even");
     static_assert(SMEM + 1024 <= 227 * 1024, "smem budget");
 };
 
@@ -231,7 +262,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tok + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t n_items = (int64_t)p.m_tiles * p.k_ranges;
+    const int64_t n_items = (int64_t)p.m_tiles * p.n_bblocks * p.k_ranges;
     const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0;
     int tri = 0;   // trace iteration counter of this role
 
@@ -265,27 +296,23 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         {
             Ring xr;
             for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-                const int mt = (int)(it % p.m_tiles);
-                const int64_t kr = it / p.m_tiles;
-                const int64_t c_begin = kr * p.chunks_per_range;
-                const int64_t c_end = min(p.total_chunks, c_begin + p.chunks_per_range);
-                int a = (int)(c_begin / p.chunks_per_a);
-                int bc = (int)(c_begin - (int64_t)a * p.chunks_per_a);
-                const int m0 = mt * TM;
-                for (int64_t c = c_begin; c < c_end; ++c) {
-                    mbar_wait(&x_empty[xr.idx], xr.phase ^ 1u);
-                    TLB_TRACE(0, tri, 0);
-                    if (elect_one_sync()) {
-                        mbar_expect_tx(&x_full[xr.idx], C::X_STAGE);
-                        unsigned char* dst = x_smem + xr.idx * C::X_STAGE;
-                        if constexpr (XL == TC_X_KMAJOR_1)      tma_load_3d(dst, &xmap, &x_full[xr.idx], bc * 32, m0, a);
-                        else if constexpr (XL == TC_X_KMAJOR_2) tma_load_4d(dst, &xmap, &x_full[xr.idx], 0, bc * 2, m0, a);
-                        else                                    tma_load_3d(dst, &xmap, &x_full[xr.idx], m0, bc * 64, a);
+                const TcItem t = tc_item(p, it);
+                const int m0 = t.mt * TM;
+                for (int a = t.a0; a < t.a1; ++a) {
+                    for (int bc = t.bc0; bc < t.bc1; ++bc) {
+                        mbar_wait(&x_empty[xr.idx], xr.phase ^ 1u);
+                        TLB_TRACE(0, tri, 0);
+                        if (elect_one_sync()) {
+                            mbar_expect_tx(&x_full[xr.idx], C::X_STAGE);
+                            unsigned char* dst = x_smem + xr.idx * C::X_STAGE;
+                            if constexpr (XL == TC_X_KMAJOR_1)      tma_load_3d(dst, &xmap, &x_full[xr.idx], bc * 32, m0, a);
+                            else if constexpr (XL == TC_X_KMAJOR_2) tma_load_4d(dst, &xmap, &x_full[xr.idx], 0, bc * 2, m0, a);
+                            else                                    tma_load_3d(dst, &xmap, &x_full[xr.idx], m0, bc * 64, a);
+                        }
+                        __syncwarp();
+                        TLB_TRACE(0, tri, 1); ++tri;
+                        xr.advance(XS);
                     }
-                    __syncwarp();
-                    TLB_TRACE(0, tri, 1); ++tri;
-                    xr.advance(XS);
-                    if (++bc == (int)p.chunks_per_a) { bc = 0; ++a; }
                 }
             }
         }
@@ -307,16 +334,17 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             const uint32_t a_base = tmem_base + a_col0;
             const uint64_t d0 = desc_kmajor_sw128(smem_u32(b_smem));
             const uint32_t bdesc_lo0 = (uint32_t)d0, bdesc_hi = (uint32_t)(d0 >> 32);
+            uint32_t bphase = 0;     // resident B: phase bit per slot
             for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-                const int64_t kr = it / p.m_tiles;
-                const int64_t c_begin = kr * p.chunks_per_range;
-                const int64_t c_end = min(p.total_chunks, c_begin + p.chunks_per_range);
-                const int n = (int)(c_end - c_begin);           // tiles (chunks) of this item, KO units each
+                const TcItem t = tc_item(p, it);
+                const int nbc = t.bc1 - t.bc0;                  // tiles per `a` row of this item, KO units each
+                if (t.a1 <= t.a0 || nbc <= 0) continue;
                 int ug = 0;
-                int bc = (int)(c_begin % p.chunks_per_a);       // tile index within the current `a`
-                for (int i = 0; i < n; ++i, ++gt) {
-                    const bool a_end = p.P != nullptr && bc + 1 == (int)p.chunks_per_a;   // last tile of this `a`
-                    if (++bc == (int)p.chunks_per_a) bc = 0;
+                for (int a = t.a0; a < t.a1; ++a)
+                for (int j = 0; j < nbc; ++j, ++gt) {
+                    const bool last_a = a + 1 == t.a1;
+                    const bool row_end = j + 1 == nbc;
+                    const bool cut = (last_a && row_end) || (p.P != nullptr && row_end);   // group may not continue past this tile
                     const bool mine = (gt & 1u) == (uint32_t)mw;
                     // group bookkeeping runs for every tile in both issuers; only the owner waits and issues
                     bool first[KO], gend[KO];
@@ -326,17 +354,21 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                         dbuf[u] = G & 1u;
                         first[u] = ug == 0;
                         if (mine && first[u] && G >= 2) mbar_wait(&d_empty[dbuf[u]], ((G >> 1) - 1) & 1u);
-                        gend[u] = (ug + 1 == GU) || ((i == n - 1 || a_end) && u == KO - 1);
+                        gend[u] = (ug + 1 == GU) || (cut && u == KO - 1);
                         if (gend[u]) { ++G; ug = 0; } else { ++ug; }
                     }
                     // one A barrier pair per tile: both units of a tile are stored and published together
                     const int as0 = ar.idx;
                     const uint32_t aph = ar.phase;
-                    const Ring b0 = br;
+                    Ring b0 = br;
                     Ring b1 = br;
                     if constexpr (KO == 2) b1.advance(BS);
 #pragma unroll
                     for (int u = 0; u < KO; ++u) { ar.advance(AS); br.advance(BS); }
+                    if (p.b_resident) {      // slot = position inside the item's b block, one phase per item
+                        b0.idx = j * KO; b0.phase = (bphase >> b0.idx) & 1u;
+                        b1.idx = j * KO + (KO - 1); b1.phase = (bphase >> b1.idx) & 1u;
+                    }
                     if (!mine) continue;
                     TLB_TRACE(1 + 2 * mw, tri, 0);
                     // one overlapped wait per tile: the A tile and its B unit(s)
@@ -369,8 +401,10 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                         // hand the turn over before the (slower) commits
                         tc_fence_before();
                         mbar_arrive(&tok[mw ^ 1]);
-                        tc_commit(&b_empty[b0.idx]);
-                        if constexpr (KO == 2) tc_commit(&b_empty[b1.idx]);
+                        if (!p.b_resident || last_a) {     // a resident B slot is released by its last reader only
+                            tc_commit(&b_empty[b0.idx]);
+                            if constexpr (KO == 2) tc_commit(&b_empty[b1.idx]);
+                        }
                         tc_commit(&a_empty[as0]);
 #pragma unroll
                         for (int u = 0; u < KO; ++u)
@@ -380,6 +414,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                     TLB_TRACE(1 + 2 * mw, tri, 3); ++tri;
                     ++own;
                 }
+                bphase ^= (1u << (nbc * KO)) - 1u;
             }
         }
     } else if (warp < 10) {
@@ -392,10 +427,8 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         int pub_slot[2] = {0, 0};  // A slots stored but not yet published
         int unpublished = 0;       // A units whose tcgen05.st have been issued but not yet waited for
         for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-            const int64_t kr = it / p.m_tiles;
-            const int64_t c_begin = kr * p.chunks_per_range;
-            const int64_t c_end = min(p.total_chunks, c_begin + p.chunks_per_range);
-            const int n = (int)(c_end - c_begin);
+            const TcItem t = tc_item(p, it);
+            const int n = max(0, t.a1 - t.a0) * max(0, t.bc1 - t.bc0);    // tiles of this item
             for (int i = (int)((cset - (int)(cbase & 1u)) & 1); i < n; i += 2) {
                 const uint32_t gc = cbase + (uint32_t)i;                 // global tile index
                 const int xs = (int)(gc % XS);
@@ -524,25 +557,46 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         // ================= B producer: TMA loads of the pre-split small operand, one 32-element unit at a time =========
         if (warp == 10) {
             Ring br;
+            uint32_t bphase = 0;     // resident B: phase bit per slot
+            int nb_loaded = 0;
             for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-                const int64_t kr = it / p.m_tiles;
-                const int64_t c_begin = kr * p.chunks_per_range;
-                const int64_t c_end = min(p.total_chunks, c_begin + p.chunks_per_range);
-                int bc = (int)(c_begin % p.chunks_per_a);
-                for (int64_t c = c_begin; c < c_end; ++c) {
+                const TcItem t = tc_item(p, it);
+                const int nbc = t.bc1 - t.bc0;
+                if (t.a1 <= t.a0 || nbc <= 0) continue;
+                if (p.b_resident) {
+                    // the item's b block is loaded once and stays in shared memory for all of its `a` rows
+                    for (int sl = 0; sl < nbc * KO; ++sl) {
+                        mbar_wait(&b_empty[sl], ((bphase >> sl) & 1u) ^ 1u);
+                        if (elect_one_sync()) {
+                            mbar_expect_tx(&b_full[sl], C::B_UNIT);
+                            unsigned char* dst = b_smem + sl * C::B_UNIT;
+                            tma_load_2d(dst, &bhi_map, &b_full[sl], t.bc0 * KS + sl * 32, 0);
+                            tma_load_2d(dst + RP * 128, &blo_map, &b_full[sl], t.bc0 * KS + sl * 32, 0);
+                        }
+                        __syncwarp();
+                    }
+                    bphase ^= (1u << (nbc * KO)) - 1u;
+                    continue;
+                }
+                for (int a = t.a0; a < t.a1; ++a)
+                for (int bc = t.bc0; bc < t.bc1; ++bc) {
 #pragma unroll
                     for (int u = 0; u < KO; ++u) {
                         mbar_wait(&b_empty[br.idx], br.phase ^ 1u);
                         if (elect_one_sync()) {
-                            mbar_expect_tx(&b_full[br.idx], C::B_UNIT);
-                            unsigned char* dst = b_smem + br.idx * C::B_UNIT;
-                            tma_load_2d(dst, &bhi_map, &b_full[br.idx], bc * KS + u * 32, 0);
-                            tma_load_2d(dst + RP * 128, &blo_map, &b_full[br.idx], bc * KS + u * 32, 0);
+                            if ((p.debug & 8) && nb_loaded >= BS) {
+                                mbar_arrive(&b_full[br.idx]);      // perf triage: reuse the stale tile, no L2 traffic
+                            } else {
+                                mbar_expect_tx(&b_full[br.idx], C::B_UNIT);
+                                unsigned char* dst = b_smem + br.idx * C::B_UNIT;
+                                tma_load_2d(dst, &bhi_map, &b_full[br.idx], bc * KS + u * 32, 0);
+                                tma_load_2d(dst + RP * 128, &blo_map, &b_full[br.idx], bc * KS + u * 32, 0);
+                            }
                         }
+                        ++nb_loaded;
                         __syncwarp();
                         br.advance(BS);
                     }
-                    if (++bc == (int)p.chunks_per_a) bc = 0;
                 }
             }
         }
@@ -553,14 +607,12 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t G = 0;
         for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-            const int mt = (int)(it % p.m_tiles);
-            const int64_t kr = it / p.m_tiles;
-            const int64_t c_begin = kr * p.chunks_per_range;
-            const int64_t c_end = min(p.total_chunks, c_begin + p.chunks_per_range);
-            const int n = (int)(c_end - c_begin) * KO;                    // 32-element units of this item
-            const int units_per_a = (int)p.chunks_per_a * KO;
-            int a = (int)(c_begin / p.chunks_per_a);
-            int bu = (int)(c_begin - (int64_t)a * p.chunks_per_a) * KO;   // unit index within the current `a`
+            const TcItem t = tc_item(p, it);
+            const int mt = t.mt;
+            const int units_per_a = max(0, t.bc1 - t.bc0) * KO;           // 32-element units per `a` row of this item
+            const int n = max(0, t.a1 - t.a0) * units_per_a;              // units of this item (0: the partial is zero)
+            int a = t.a0;
+            int bu = 0;                                                   // unit index within the current `a` row
             float acc[RP];
 #pragma unroll
             for (int c = 0; c < RP; ++c) acc[c] = 0.f;
@@ -574,25 +626,43 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 mbar_wait(&d_full[buf], (G >> 1) & 1u);
                 if (warp == 12) TLB_TRACE(4, tri, 1);
                 tc_fence_after();
-                float part[RP];
+                // 16-column chunks at rank 64 keep accumulators + staging inside the register budget (no spills);
+                // the P row of this `a` is fetched while the TMEM load is in flight
+                constexpr int CW = 16;
+                const float4* prow4 = p.P != nullptr ? reinterpret_cast<const float4*>(p.P + (int64_t)a * RP) : nullptr;
 #pragma unroll
-                for (int c0 = 0; c0 < RP; c0 += 32) {
-                    uint32_t r0[32], r1[32];
-                    TLB_TMEM_LD32(lane_addr + buf * C::D_COLS + c0, r0);            // hi*hi block
-                    TLB_TMEM_LD32(lane_addr + buf * C::D_COLS + RP + c0, r1);       // cross-term block
+                for (int c0 = 0; c0 < RP; c0 += CW) {
+                    uint32_t r0[CW], r1[CW];
+                    if constexpr (CW == 32) {
+                        TLB_TMEM_LD32(lane_addr + buf * C::D_COLS + c0, r0);            // hi*hi block
+                        TLB_TMEM_LD32(lane_addr + buf * C::D_COLS + RP + c0, r1);       // cross-term block
+                    } else {
+                        TLB_TMEM_LD16(lane_addr + buf * C::D_COLS + c0, r0);
+                        TLB_TMEM_LD16(lane_addr + buf * C::D_COLS + RP + c0, r1);
+                    }
+                    float4 pv[CW / 4];
+                    if (prow4 != nullptr) {
+#pragma unroll
+                        for (int k = 0; k < CW / 4; ++k) pv[k] = __ldg(prow4 + c0 / 4 + k);
+                    }
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (c0 + CW == RP) {            // every column of the buffer has been read
+                        tc_fence_before();
+                        mbar_arrive(&d_empty[buf]);
+                    }
+                    if (prow4 != nullptr) {
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) part[c0 + c] = __uint_as_float(r0[c]) + __uint_as_float(r1[c]);
-                }
-                tc_fence_before();
-                mbar_arrive(&d_empty[buf]);
-                if (p.P != nullptr) {
-                    const float* prow = p.P + (int64_t)a * RP;              // Khatri-Rao outer factor of this `a`
+                        for (int k = 0; k < CW / 4; ++k) {
+                            const int c = c0 + 4 * k;
+                            acc[c + 0] = fmaf(pv[k].x, __uint_as_float(r0[4 * k + 0]) + __uint_as_float(r1[4 * k + 0]), acc[c + 0]);
+                            acc[c + 1] = fmaf(pv[k].y, __uint_as_float(r0[4 * k + 1]) + __uint_as_float(r1[4 * k + 1]), acc[c + 1]);
+                            acc[c + 2] = fmaf(pv[k].z, __uint_as_float(r0[4 * k + 2]) + __uint_as_float(r1[4 * k + 2]), acc[c + 2]);
+                            acc[c + 3] = fmaf(pv[k].w, __uint_as_float(r0[4 * k + 3]) + __uint_as_float(r1[4 * k + 3]), acc[c + 3]);
+                        }
+                    } else {
 #pragma unroll
-                    for (int c = 0; c < RP; ++c) acc[c] = fmaf(__ldg(prow + c), part[c], acc[c]);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < RP; ++c) acc[c] += part[c];
+                        for (int c = 0; c < CW; ++c) acc[c0 + c] += __uint_as_float(r0[c]) + __uint_as_float(r1[c]);
+                    }
                 }
                 if (warp == 12) { TLB_TRACE(4, tri, 2); ++tri; }
                 ++G;
@@ -602,7 +672,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             }
             const int64_t gm = (int64_t)mt * TM + row;
             if (gm < p.M) {
-                float* dst = p.out + kr * p.sOk + gm * p.sOm;
+                float* dst = p.out + t.part * p.sOk + gm * p.sOm;
                 if (p.sOn == 1 && (p.n_valid & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
                     for (int c = 0; c < RP / 4; ++c)
@@ -653,7 +723,7 @@ int launch_cfg(const TcStreamLaunch& l, cudaStream_t stream) {
             return TLB200_ECUDA;
         attr = true;
     }
-    int64_t n_items = (int64_t)l.p.m_tiles * l.p.k_ranges;
+    int64_t n_items = (int64_t)l.p.m_tiles * l.p.n_bblocks * l.p.k_ranges;
     if (n_items <= 0) return TLB200_OK;
     static int grid_cap = -1;
     if (grid_cap < 0) { const char* e = getenv("TLB200_TC_GRID"); grid_cap = e ? atoi(e) : kNumSMs; if (grid_cap < 1) grid_cap = kNumSMs; }

@@ -25,12 +25,16 @@ struct TcStreamParams {
     int64_t M;                 // extent of the streamed (row) dim
     int64_t A, B;
     int64_t chunks_per_a;      // ceil(B / KS)
-    int64_t total_chunks;      // A * chunks_per_a
-    // items: (mt, kr) with mt < m_tiles, kr < k_ranges; item kr covers chunks
-    // [kr * chunks_per_range, min(total, (kr+1) * chunks_per_range))
+    // items: (mt, bb, kr) with mt < m_tiles, bb < n_bblocks, kr < k_ranges; item (bb, kr) covers the chunks
+    // [bb * nb, min(chunks_per_a, (bb+1) * nb)) of every a in [kr * a_per_range, min(A, (kr+1) * a_per_range))
+    // and writes partial result number kr * n_bblocks + bb
     int m_tiles;
+    int nb, n_bblocks;
     int64_t k_ranges;
-    int64_t chunks_per_range;
+    int64_t a_per_range;
+    // 1: the b block of an item (nb chunks of the small operand) is loaded once and stays in shared memory
+    //    (needs nb * KS / 32 <= tc_b_slots(rp)); 0: the small operand is streamed with the tiles
+    int b_resident;
     int group_units;           // 32-element K units per TMEM accumulation group (RZ accumulate => keep short)
     // optional per-`a` scaling of the result (MTTKRP: the outer Khatri-Rao table), applied by the epilogue
     const float* P;            // [A][RP] or null
@@ -60,5 +64,7 @@ int tc_stream_launch(const TcStreamLaunch& l, cudaStream_t stream);
 // K extent of one chunk for a layout
 inline int tc_chunk_k(int x_layout) { return x_layout == TC_X_KMAJOR_1 ? 32 : 64; }
 int tc_group_units();
+// shared-memory slots (32-element units) for the small operand
+inline int tc_b_slots(int rp) { return rp == 32 ? 8 : 6; }
 
 }  // namespace tlb200

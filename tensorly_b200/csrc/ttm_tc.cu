@@ -117,10 +117,11 @@ int ttm_tc_launch(const float* x, int64_t L, int64_t J, int64_t T, const float* 
     TcStreamParams& p = l.p;
     p.M = g.M; p.A = g.A; p.B = g.B;
     p.chunks_per_a = ceil_div(g.B, g.ks);
-    p.total_chunks = g.A * p.chunks_per_a;
     p.m_tiles = (int)ceil_div(g.M, 128);
     p.k_ranges = g.A;                         // one item per (row tile, batch): all of K
-    p.chunks_per_range = p.chunks_per_a;
+    p.a_per_range = 1;
+    p.nb = (int)p.chunks_per_a; p.n_bblocks = 1;
+    p.b_resident = 0;                         // the matrix is streamed with the tiles (re-read from L2 per item)
     p.group_units = tc_group_units();
     p.P = nullptr;
     p.out = out;
