@@ -13,6 +13,13 @@ namespace {
 
 constexpr int kMaxRank = 128;
 
+#ifdef TLB_CP_TRACE   // probes/cp_update_probe.cu: phase timestamps of CTA 0
+__device__ long long g_cp_trace[16];
+#define CP_TRACE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_cp_trace[i] = clock64(); } while (0)
+#else
+#define CP_TRACE(i) do { } while (0)
+#endif
+
 template <typename T>
 struct GramList {
     const T* g[TLB200_MAX_NDIM];
@@ -140,8 +147,227 @@ __device__ void lu_factor_smem(T* A, int* perm, int R, int ld, int* s_piv) {
     }
 }
 
+// ---- fast solve for R <= RM (RM = 32, or 64 in fp32): everything latency-critical lives in registers ----------
+//
+// LU: thread t of the first RM threads owns row t of A = V^T in registers.  Partial pivoting is implicit (a pivot
+// row is marked used instead of being swapped: same pivots and arithmetic as the swapping form).  The row is kept
+// ROTATED so that the current column is always register 0: the step loop stays a real loop (~100 instructions
+// of code) while every register index is static.  Step k: the unused row with the largest |a[0]| (one redux +
+// ballot in fp32) publishes its rotated row as Urot[k] through shared memory (vector stores); everyone else
+// eliminates against it and shifts left.  Multipliers go to Lraw[original row][k].
+// Substitution: one thread per right-hand side, the vector in registers and rotated the same way (axpy form,
+// like trsm): no shuffles, no barriers, no shared-memory round trip on the dependency chain.
+template <int RM>
+__device__ __forceinline__ void lu_barrier() {
+    if constexpr (RM > 32) asm volatile("bar.sync 1, %0;" ::"n"(RM) : "memory");
+    else __syncwarp();
+}
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> { using type = float4; };
+template <> struct Vec4<double> { using type = double4; };
+
+template <typename T, int RM>
+__device__ __forceinline__ void store_row(T* dst, const T (&a)[RM]) {
+    using V = typename Vec4<T>::type;
+#pragma unroll
+    for (int j = 0; j < RM / 4; ++j) {
+        V v; v.x = a[4 * j]; v.y = a[4 * j + 1]; v.z = a[4 * j + 2]; v.w = a[4 * j + 3];
+        reinterpret_cast<V*>(dst)[j] = v;
+    }
+}
+// b[j-1] = b[j] - c[j] * s for j = 1..RM-1 (c read with vector loads), b[RM-1] = 0; `keep`: rotate only
+template <typename T, int RM>
+__device__ __forceinline__ void axpy_rotate(T (&b)[RM], const T* c, T s, bool keep) {
+    using V = typename Vec4<T>::type;
+    T cj[RM];
+#pragma unroll
+    for (int j = 0; j < RM / 4; ++j) {
+        const V v = reinterpret_cast<const V*>(c)[j];
+        cj[4 * j] = v.x; cj[4 * j + 1] = v.y; cj[4 * j + 2] = v.z; cj[4 * j + 3] = v.w;
+    }
+#pragma unroll
+    for (int j = 1; j < RM; ++j) b[j - 1] = keep ? b[j] : b[j] - cj[j] * s;
+    b[RM - 1] = T(0);
+}
+
+template <typename T, int RM>
+struct SolveSmem {
+    T* A;       // [R][ld]   V^T staging
+    T* Y;       // [kSolveRows][ld] right-hand sides, then solutions
+    T* Lraw;    // [R][ld]   multipliers by original row
+    T* Urot;    // [R][RM]   Urot[k][j] = U[k][k+j]
+    T* Lcol;    // [R][RM]   Lcol[k][j] = L[k+j][k], j >= 1
+    T* Ucol;    // [R][RM]   Ucol[k][j] = U[k-j][k], j >= 1
+    T* s_val;   // [4]
+    int* perm;  // [R]
+    int* s_idx; // [4]
+    unsigned* s_key;  // [4]
+    __host__ __device__ static size_t elems(int R) { return (size_t)(2 * R + 64) * (R + 1) + 3 + (size_t)3 * R * RM + 4; }
+    __host__ __device__ static size_t bytes(int R) { return sizeof(T) * elems(R) + sizeof(int) * (R + 8); }
+    __device__ SolveSmem(unsigned char* raw, int R) {
+        const int ld = R + 1;
+        A = reinterpret_cast<T*>(raw);
+        Y = A + R * ld;
+        Lraw = Y + 64 * ld;
+        size_t off = (size_t)(2 * R + 64) * ld;
+        off = (off + 3) & ~(size_t)3;                 // vector rows: 4-element aligned
+        Urot = A + off;
+        Lcol = Urot + R * RM;
+        Ucol = Lcol + R * RM;
+        s_val = Ucol + R * RM;
+        perm = reinterpret_cast<int*>(s_val + 4);
+        s_idx = perm + R;
+        s_key = reinterpret_cast<unsigned*>(s_idx + 4);
+    }
+};
+
+template <typename T, int RM>
+__device__ __forceinline__ void lu_factor_rot(int R, const SolveSmem<T, RM>& sm, int ld) {
+    const int row = threadIdx.x;            // < RM
+    const int lane = row & 31;
+    T a[RM];
+#pragma unroll
+    for (int j = 0; j < RM; ++j) a[j] = (row < R && j < R) ? sm.A[row * ld + j] : T(0);
+    bool used = row >= R;
+#pragma unroll 2
+    for (int k = 0; k < R; ++k) {
+        // ---- pivot: unused row with the largest |a[0]|, lowest row on ties; every thread learns its value
+        int bi;
+        T piv;
+        if constexpr (sizeof(T) == 4) {
+            // non-negative floats order like their bit patterns; +1 so that even a zero beats a used row
+            const unsigned key = used ? 0u : (__float_as_uint(fabsf((float)a[0])) + 1u);
+            unsigned mx = __reduce_max_sync(0xffffffffu, key);
+            const unsigned bal = __ballot_sync(0xffffffffu, key == mx);
+            const unsigned neg = __ballot_sync(0xffffffffu, a[0] < T(0));
+            const int pl = __ffs(bal) - 1;
+            bi = (row & ~31) | pl;
+            float pv = __uint_as_float(mx - 1u);
+            if ((neg >> pl) & 1u) pv = -pv;
+            if constexpr (RM > 32) {
+                const int slot = (k & 1) * 2;
+                if (lane == 0) { sm.s_key[slot + (row >> 5)] = mx; sm.s_idx[slot + (row >> 5)] = bi; sm.s_val[slot + (row >> 5)] = (T)pv; }
+                lu_barrier<RM>();
+                const int pick = sm.s_key[slot + 1] > sm.s_key[slot] ? 1 : 0;      // ties: the lower row (warp 0)
+                bi = sm.s_idx[slot + pick];
+                pv = (float)sm.s_val[slot + pick];
+            }
+            piv = (T)pv;
+        } else {
+            T best = used ? T(-1) : (a[0] < T(0) ? -a[0] : a[0]);
+            bi = row;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const T ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            piv = __shfl_sync(0xffffffffu, a[0], bi & 31);      // fp64: RM == 32, one warp
+        }
+        const T m = a[0] * (T(1) / piv);
+        T* pr = sm.Urot + k * RM;
+        if (row == bi) {
+            used = true;
+            sm.perm[k] = row;
+            store_row<T, RM>(pr, a);
+        }
+        lu_barrier<RM>();
+        if (!used) sm.Lraw[row * ld + k] = m;
+        // eliminate and rotate left in one pass (used rows only rotate; their values are never read again)
+        axpy_rotate<T, RM>(a, pr, m, used);
+    }
+}
+
+// One CTA: factor V^T, then solve kSolveRows right-hand sides (rows of M).  `tmp` = this thread's share of the
+// right-hand sides, fetched by the caller before the factorisation so the loads are long done.
+template <typename T, int RM>
+__device__ __forceinline__ void solve_fast(unsigned char* raw, const GramList<T>& gl, int mode, int R, const T* __restrict__ w,
+                                           T l2, const T* __restrict__ m, int64_t m_ld, int64_t rows, T* __restrict__ out,
+                                           int64_t out_ld) {
+    constexpr int kRows = 64;
+    const SolveSmem<T, RM> sm(raw, R);
+    const int ld = R + 1;
+    const int tid = threadIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * kRows;
+    constexpr int kPer = kRows * RM / 256;
+    T tmp[kPer];
+    CP_TRACE(0);
+#pragma unroll
+    for (int it = 0; it < kPer; ++it) {
+        const int e = tid + it * 256;
+        const int rr = e / R, c = e - rr * R;
+        const int64_t gr = row0 + rr;
+        tmp[it] = (e < kRows * R && gr < rows) ? m[gr * m_ld + c] : T(0);
+    }
+    {   // V^T into shared memory: same evaluation order as form_v, Gram pointers in registers, loads batched
+        const T* gp[TLB200_MAX_NDIM];
+#pragma unroll
+        for (int i = 0; i < TLB200_MAX_NDIM; ++i) gp[i] = (i < gl.n && i != mode) ? gl.g[i] : nullptr;
+#pragma unroll 4
+        for (int e = tid; e < R * R; e += 256) {
+            const int r = e / R, s2 = e - r * R;
+            T v = T(1);
+#pragma unroll
+            for (int i = 0; i < TLB200_MAX_NDIM; ++i)
+                if (gp[i] != nullptr) v = v * __ldg(gp[i] + e);
+            if (r == s2) v += l2;
+            if (w) v = (__ldg(w + r) * v) * __ldg(w + s2);
+            sm.A[s2 * ld + r] = v;
+        }
+    }
+    __syncthreads();
+    CP_TRACE(1);
+    if (tid < RM) lu_factor_rot<T, RM>(R, sm, ld);
+#pragma unroll
+    for (int it = 0; it < kPer; ++it) {
+        const int e = tid + it * 256;
+        const int rr = e / R, c = e - rr * R;
+        if (e < kRows * R) sm.Y[rr * ld + c] = tmp[it];
+    }
+    CP_TRACE(2);
+    __syncthreads();
+    // substitution operands: columns of L below / of U above the diagonal, contiguous and zero padded
+    for (int e = tid; e < R * RM; e += 256) {
+        const int k = e / RM, j = e - k * RM;
+        sm.Lcol[e] = (j >= 1 && k + j < R) ? sm.Lraw[sm.perm[k + j] * ld + k] : T(0);
+        sm.Ucol[e] = (j >= 1 && j <= k) ? sm.Urot[(k - j) * RM + j] : T(0);
+    }
+    __syncthreads();
+    CP_TRACE(3);
+    if (tid < kRows) {
+        T* y = sm.Y + tid * ld;
+        T b[RM];
+#pragma unroll
+        for (int j = 0; j < RM; ++j) b[j] = j < R ? y[sm.perm[j]] : T(0);      // P * rhs
+        // forward substitution, unit lower triangular
+        for (int k = 0; k < R; ++k) {
+            const T yk = b[0];
+            y[k] = yk;
+            axpy_rotate<T, RM>(b, sm.Lcol + k * RM, yk, false);
+        }
+        CP_TRACE(4);
+#pragma unroll
+        for (int j = 0; j < RM; ++j) b[j] = j < R ? y[R - 1 - j] : T(0);
+        // back substitution
+        for (int k = R - 1; k >= 0; --k) {
+            const T xk = b[0] / sm.Urot[k * RM];
+            y[k] = xk;
+            axpy_rotate<T, RM>(b, sm.Ucol + k * RM, xk, false);
+        }
+    }
+    CP_TRACE(5);
+    __syncthreads();
+    for (int e = tid; e < kRows * R; e += 256) {
+        const int r2 = e / R, c = e - r2 * R;
+        const int64_t gr = row0 + r2;
+        if (gr < rows) out[gr * out_ld + c] = sm.Y[r2 * ld + c];
+    }
+    CP_TRACE(6);
+}
+
 template <typename T>
-__global__ void __launch_bounds__(kSolveThreads)
+__global__ void __launch_bounds__(kSolveThreads, 1)
 cp_update_kernel(GramList<T> gl, int mode, int R, const T* __restrict__ w, T l2, const T* __restrict__ m, int64_t m_ld,
                  int64_t rows, T* __restrict__ out, int64_t out_ld) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -153,21 +379,27 @@ cp_update_kernel(GramList<T> gl, int mode, int R, const T* __restrict__ w, T l2,
     const int tid = threadIdx.x;
     const int64_t row0 = (int64_t)blockIdx.x * kSolveRows;
 
-    for (int e = tid; e < R * R; e += blockDim.x) {
-        const int r = e / R, s = e - r * R;
-        A[s * ld + r] = form_v<T>(gl, mode, R, w, l2, r, s);   // store V^T
+    if (R <= 32) { solve_fast<T, 32>(smem_raw, gl, mode, R, w, l2, m, m_ld, rows, out, out_ld); return; }
+    if constexpr (sizeof(T) == 4) {
+        if (R <= 64) { solve_fast<T, 64>(smem_raw, gl, mode, R, w, l2, m, m_ld, rows, out, out_ld); return; }
     }
-    for (int i = tid; i < R; i += blockDim.x) perm[i] = i;
-    __syncthreads();
-    lu_factor_smem<T>(A, perm, R, ld, s_piv);
-
-    // load permuted right-hand sides: Y[row][i] = M[row][perm[i]]
-    for (int e = tid; e < kSolveRows * R; e += blockDim.x) {
-        const int rr = e / R, c = e - rr * R;
-        const int64_t gr = row0 + rr;
-        Y[rr * ld + c] = gr < rows ? m[gr * m_ld + perm[c]] : T(0);
+    {
+        for (int e = tid; e < R * R; e += blockDim.x) {
+            const int r = e / R, s = e - r * R;
+            A[s * ld + r] = form_v<T>(gl, mode, R, w, l2, r, s);   // store V^T
+        }
+        for (int i = tid; i < R; i += blockDim.x) perm[i] = i;
+        __syncthreads();
+        lu_factor_smem<T>(A, perm, R, ld, s_piv);
+        // load permuted right-hand sides: Y[row][i] = M[row][perm[i]]
+        for (int e = tid; e < kSolveRows * R; e += blockDim.x) {
+            const int rr = e / R, c = e - rr * R;
+            const int64_t gr = row0 + rr;
+            Y[rr * ld + c] = gr < rows ? m[gr * m_ld + perm[c]] : T(0);
+        }
+        __syncthreads();
     }
-    __syncthreads();
+    CP_TRACE(3);
     // 4 threads per row: thread q of a row owns the partial dot products of columns
     // j = q, q+4, ... ; the running solution lives in shared memory.
     const int rr = tid >> 2, q = tid & 3;
@@ -181,6 +413,7 @@ cp_update_kernel(GramList<T> gl, int mode, int R, const T* __restrict__ w, T l2,
         if (q == 0) y[i] -= s;
         __syncwarp();
     }
+    CP_TRACE(4);
     // back substitution
     for (int i = R - 1; i >= 0; --i) {
         T s = T(0);
@@ -190,12 +423,14 @@ cp_update_kernel(GramList<T> gl, int mode, int R, const T* __restrict__ w, T l2,
         if (q == 0) y[i] = (y[i] - s) / A[i * ld + i];
         __syncwarp();
     }
+    CP_TRACE(5);
     __syncthreads();
     for (int e = tid; e < kSolveRows * R; e += blockDim.x) {
         const int r2 = e / R, c = e - r2 * R;
         const int64_t gr = row0 + r2;
         if (gr < rows) out[gr * out_ld + c] = Y[r2 * ld + c];
     }
+    CP_TRACE(6);
 }
 
 // ---- NN-CP multiplicative update -------------------------------------------------------
@@ -372,7 +607,9 @@ int cp_update_launch(const void* const* grams, int nmodes, int mode, int64_t R, 
     int st = fill_grams<T>(&gl, grams, nmodes, mode);
     if (st) return st;
     const int ld = (int)R + 1;
-    const size_t smem = sizeof(T) * ((size_t)R * ld + (size_t)kSolveRows * ld) + sizeof(int) * (R + 1);
+    size_t smem = sizeof(T) * ((size_t)R * ld + (size_t)kSolveRows * ld) + sizeof(int) * (R + 1);
+    if (R <= 32) smem = SolveSmem<T, 32>::bytes((int)R);
+    else if (sizeof(T) == 4 && R <= 64) smem = SolveSmem<T, 64>::bytes((int)R);
     static bool attr_set[2] = {false, false};
     const int ti = sizeof(T) == 8;
     if (!attr_set[ti]) {
