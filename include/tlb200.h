@@ -182,6 +182,20 @@ int tlb200_cp_update(const void* const* grams, int nmodes, int mode, int64_t ran
                      const void* weights, double l2_reg, const void* m, int64_t m_ld,
                      int64_t rows, int dtype, void* out, int64_t out_ld, void* stream);
 
+/* tlb200_cp_update followed by tlb200_gram of the updated rows, in one launch: the solved rows
+ * are still in shared memory when their Gram partials are formed (no second pass over the
+ * factor, no extra launches).  gram_out (rank x rank) may be grams[mode].  The first 4 bytes of
+ * `workspace` are a ticket counter: they must be zero before the first call and are left zero
+ * by every call, so one zero-initialised workspace can be reused forever on one stream.
+ * Replaces tensorly/decomposition/_cp.py:411-428 plus the later recomputation of
+ * `tl.dot(tl.conj(tl.transpose(factor)), factor)` for this factor at _cp.py:413-416. */
+size_t tlb200_cp_update_gram_workspace_bytes(int64_t rows, int64_t rank, int dtype);
+
+int tlb200_cp_update_gram(const void* const* grams, int nmodes, int mode, int64_t rank,
+                          const void* weights, double l2_reg, const void* m, int64_t m_ld,
+                          int64_t rows, int dtype, void* out, int64_t out_ld, void* gram_out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* Fast CP reconstruction error — replaces error_calc's MTTKRP shortcut
  * (tensorly/decomposition/_cp.py:217-225 with cp_norm, tensorly/cp_tensor.py:614-644):
  *   iprod = sum(M_last o F_last);  norm_cp^2 = sum_{r,s} w_r w_s prod_n G_n[r,s];

@@ -1,0 +1,4 @@
+#!/bin/bash
+timeout 900 python -m pytest tests -m gpu -x -q -p no:cacheprovider 2>&1 | tail -5
+timeout 300 python scripts/prof_sweep.py 1024 32 2>&1 | grep -v "Warn\|warn"
+timeout 300 python scripts/prof_sweep.py 768 64 2>&1 | grep "graph sweep\|cp_update\|splitk\|error"

@@ -66,6 +66,9 @@ SIGNATURES = {
     "tlb200_gram": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tlb200_cp_update": (c_int, [_VPP, c_int, c_int, c_int64, c_void_p, c_double, c_void_p, c_int64, c_int64, c_int,
                                  c_void_p, c_int64, c_void_p]),
+    "tlb200_cp_update_gram_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "tlb200_cp_update_gram": (c_int, [_VPP, c_int, c_int, c_int64, c_void_p, c_double, c_void_p, c_int64, c_int64, c_int,
+                                      c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tlb200_cp_error": (c_int, [_VPP, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64,
                                 c_void_p, c_int, c_void_p, c_void_p]),
     "tlb200_sumsq_workspace_bytes": (c_size_t, [c_int64, c_int]),

@@ -103,9 +103,24 @@ def _workspace(nbytes: int, like: torch.Tensor) -> torch.Tensor:
     return buf
 
 
+# Zero-initialised scratch for kernels that keep a self-resetting ticket counter in it (cp_update with a fused Gram).
+_ZWS_CACHE: dict = {}
+
+
+def _zero_workspace(nbytes: int, like: torch.Tensor) -> torch.Tensor:
+    nbytes = max(int(nbytes), 256)
+    key = (like.device.index, torch.cuda.current_stream(like.device).cuda_stream)
+    buf = _ZWS_CACHE.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(nbytes, dtype=torch.uint8, device=like.device)
+        _ZWS_CACHE[key] = buf
+    return buf
+
+
 def release_workspaces() -> None:
     """Drop the cached scratch buffers (they are re-created on demand)."""
     _WS_CACHE.clear()
+    _ZWS_CACHE.clear()
 
 
 def _prod(xs: Iterable[int]) -> int:
@@ -464,9 +479,10 @@ def _gram_ptrs(grams, skip):
 
 
 def cp_update(grams, mode: int, weights, mttkrp: torch.Tensor, l2_reg: float = 0.0,
-              out: torch.Tensor | None = None) -> torch.Tensor:
+              out: torch.Tensor | None = None, gram_out: torch.Tensor | None = None) -> torch.Tensor:
     """ALS factor update: solve(V^T, M^T)^T with V = (w w^T) o prod_{i != mode} G_i + l2 I
-    (tensorly/decomposition/_cp.py:411-428)."""
+    (tensorly/decomposition/_cp.py:411-428).  With `gram_out` (rank x rank, may be grams[mode]) the same
+    launch also writes the Gram matrix of the updated factor."""
     _check_tensor(mttkrp, "mttkrp")
     rows, rank = mttkrp.shape
     if mttkrp.stride(1) != 1:
@@ -474,6 +490,20 @@ def cp_update(grams, mode: int, weights, mttkrp: torch.Tensor, l2_reg: float = 0
     if out is None:
         out = torch.empty((rows, rank), dtype=mttkrp.dtype, device=mttkrp.device)
     lib = _lib.load()
+    if gram_out is not None and rows > 0:
+        _check_tensor(gram_out, "gram_out", mttkrp)
+        if tuple(gram_out.shape) != (rank, rank) or not gram_out.is_contiguous():
+            raise ValueError("gram_out must be a contiguous (rank, rank) tensor")
+        dt = _DTYPES[mttkrp.dtype]
+        with _Device(mttkrp):
+            nbytes = lib.tlb200_cp_update_gram_workspace_bytes(rows, rank, dt)
+            ws = _zero_workspace(nbytes, mttkrp)
+            st = lib.tlb200_cp_update_gram(_gram_ptrs(grams, mode), len(grams), mode, rank,
+                                           weights.data_ptr() if weights is not None else None, float(l2_reg or 0.0),
+                                           mttkrp.data_ptr(), mttkrp.stride(0), rows, dt, out.data_ptr(), out.stride(0),
+                                           gram_out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(mttkrp))
+        _lib.check(st, "cp_update_gram")
+        return out
     with _Device(mttkrp):
         st = lib.tlb200_cp_update(_gram_ptrs(grams, mode), len(grams), mode, rank,
                                   weights.data_ptr() if weights is not None else None, float(l2_reg or 0.0),

@@ -70,6 +70,7 @@ class CudaOps:
     mttkrp = staticmethod(_ops.unfolding_dot_khatri_rao)
     gram = staticmethod(_ops.gram)
     cp_update = staticmethod(_ops.cp_update)
+    fused_gram = True        # cp_update(..., gram_out=) also writes the Gram of the updated factor
     nncp_update = staticmethod(_ops.nncp_update)
     cp_error = staticmethod(_ops.cp_error)
     sumsq = staticmethod(_ops.sumsq)
@@ -160,11 +161,18 @@ class CPALS:
         m = self.ops.mttkrp(self.x, (self.weights, self.factors), mode)
         if self.shard_mode is not None and mode != self.shard_mode:
             self.comm.all_reduce(m)          # partial sums over the slabs
-        if self.update == "ls":
-            self.ops.cp_update(self.grams, mode, self.weights, m, self.l2_reg, out=self.factors[mode])
+        if self.update == "ls" and getattr(self.ops, "fused_gram", False):
+            # one launch: solve + Gram of the new rows (partial over this rank's rows when the mode is sharded)
+            self.ops.cp_update(self.grams, mode, self.weights, m, self.l2_reg, out=self.factors[mode],
+                               gram_out=self.grams[mode])
+            if self.shard_mode == mode:
+                self.comm.all_reduce(self.grams[mode])
         else:
-            self.ops.nncp_update(self.grams, mode, self.weights, m, self.factors[mode], self.eps)
-        self._refresh_gram(mode)
+            if self.update == "ls":
+                self.ops.cp_update(self.grams, mode, self.weights, m, self.l2_reg, out=self.factors[mode])
+            else:
+                self.ops.nncp_update(self.grams, mode, self.weights, m, self.factors[mode], self.eps)
+            self._refresh_gram(mode)
         self.mttkrp_last = m
 
     def _error(self) -> None:

@@ -147,6 +147,70 @@ __device__ void lu_factor_smem(T* A, int* perm, int R, int ld, int* s_piv) {
     }
 }
 
+// Optional tail of cp_update: Gram of the freshly solved factor rows (still in shared memory) without a second
+// pass over the factor.  Every CTA writes its R x R partial; the last CTA to arrive (ticket counter, left at zero
+// again) adds the partials in block order, so the result does not depend on scheduling.
+template <typename T>
+struct GramTail {
+    T* partial;          // [gridDim.x][R*R] or null = no Gram requested
+    T* gram;             // [R][R]
+    unsigned* counter;   // zero on entry, zero on exit
+};
+
+// Y^T Y of the CTA's rows, 256 threads as a 16 x 16 grid, thread (tr, tc) owning the TS x TS outputs
+// (tr + 16a, tc + 16b): per row TS + TS shared-memory reads (conflict-free / broadcast) feed TS*TS FMAs.
+template <typename T, int TS>
+__device__ __forceinline__ void gram_tile(const T* Y, int ld, int R, int nrows, T* __restrict__ dst) {
+    const int tc = threadIdx.x & 15, tr = threadIdx.x >> 4;
+    T acc[TS][TS];
+#pragma unroll
+    for (int a = 0; a < TS; ++a)
+#pragma unroll
+        for (int b = 0; b < TS; ++b) acc[a][b] = T(0);
+    for (int i = 0; i < nrows; ++i) {
+        const T* y = Y + i * ld;
+        T yr[TS], yc[TS];
+#pragma unroll
+        for (int a = 0; a < TS; ++a) {
+            yr[a] = tr + 16 * a < R ? y[tr + 16 * a] : T(0);
+            yc[a] = tc + 16 * a < R ? y[tc + 16 * a] : T(0);
+        }
+#pragma unroll
+        for (int a = 0; a < TS; ++a)
+#pragma unroll
+            for (int b = 0; b < TS; ++b) acc[a][b] += yr[a] * yc[b];
+    }
+#pragma unroll
+    for (int a = 0; a < TS; ++a)
+#pragma unroll
+        for (int b = 0; b < TS; ++b)
+            if (tr + 16 * a < R && tc + 16 * b < R) dst[(tr + 16 * a) * R + tc + 16 * b] = acc[a][b];
+}
+
+template <typename T>
+__device__ __forceinline__ void gram_tail(const GramTail<T>& gt, const T* Y, int ld, int R, int nrows) {
+    if (gt.partial == nullptr) return;
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    T* mine = gt.partial + (size_t)blockIdx.x * R * R;
+    if (R <= 16) gram_tile<T, 1>(Y, ld, R, nrows, mine);
+    else if (R <= 32) gram_tile<T, 2>(Y, ld, R, nrows, mine);
+    else if (R <= 64) gram_tile<T, 4>(Y, ld, R, nrows, mine);
+    else gram_tile<T, 8>(Y, ld, R, nrows, mine);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(gt.counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int e = tid; e < R * R; e += blockDim.x) {
+        T acc = T(0);
+        for (unsigned b = 0; b < gridDim.x; ++b) acc += __ldcg(gt.partial + (size_t)b * R * R + e);
+        gt.gram[e] = acc;
+    }
+    if (tid == 0) *gt.counter = 0u;
+}
+
 // ---- fast solve for R <= RM (RM = 32, or 64 in fp32): everything latency-critical lives in registers ----------
 //
 // LU: thread t of the first RM threads owns row t of A = V^T in registers.  Partial pivoting is implicit (a pivot
@@ -284,7 +348,7 @@ __device__ __forceinline__ void lu_factor_rot(int R, const SolveSmem<T, RM>& sm,
 template <typename T, int RM>
 __device__ __forceinline__ void solve_fast(unsigned char* raw, const GramList<T>& gl, int mode, int R, const T* __restrict__ w,
                                            T l2, const T* __restrict__ m, int64_t m_ld, int64_t rows, T* __restrict__ out,
-                                           int64_t out_ld) {
+                                           int64_t out_ld, const GramTail<T>& gtail) {
     constexpr int kRows = 64;
     const SolveSmem<T, RM> sm(raw, R);
     const int ld = R + 1;
@@ -364,12 +428,13 @@ __device__ __forceinline__ void solve_fast(unsigned char* raw, const GramList<T>
         if (gr < rows) out[gr * out_ld + c] = sm.Y[r2 * ld + c];
     }
     CP_TRACE(6);
+    gram_tail<T>(gtail, sm.Y, ld, R, (int)min((int64_t)kRows, rows - row0));
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kSolveThreads, 1)
 cp_update_kernel(GramList<T> gl, int mode, int R, const T* __restrict__ w, T l2, const T* __restrict__ m, int64_t m_ld,
-                 int64_t rows, T* __restrict__ out, int64_t out_ld) {
+                 int64_t rows, T* __restrict__ out, int64_t out_ld, GramTail<T> gtail) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ld = R + 1;
     T* A = reinterpret_cast<T*>(smem_raw);            // [R][ld]   = V^T, then its LU factors
@@ -379,9 +444,9 @@ cp_update_kernel(GramList<T> gl, int mode, int R, const T* __restrict__ w, T l2,
     const int tid = threadIdx.x;
     const int64_t row0 = (int64_t)blockIdx.x * kSolveRows;
 
-    if (R <= 32) { solve_fast<T, 32>(smem_raw, gl, mode, R, w, l2, m, m_ld, rows, out, out_ld); return; }
+    if (R <= 32) { solve_fast<T, 32>(smem_raw, gl, mode, R, w, l2, m, m_ld, rows, out, out_ld, gtail); return; }
     if constexpr (sizeof(T) == 4) {
-        if (R <= 64) { solve_fast<T, 64>(smem_raw, gl, mode, R, w, l2, m, m_ld, rows, out, out_ld); return; }
+        if (R <= 64) { solve_fast<T, 64>(smem_raw, gl, mode, R, w, l2, m, m_ld, rows, out, out_ld, gtail); return; }
     }
     {
         for (int e = tid; e < R * R; e += blockDim.x) {
@@ -431,6 +496,7 @@ cp_update_kernel(GramList<T> gl, int mode, int R, const T* __restrict__ w, T l2,
         if (gr < rows) out[gr * out_ld + c] = Y[r2 * ld + c];
     }
     CP_TRACE(6);
+    gram_tail<T>(gtail, Y, ld, R, (int)min((int64_t)kSolveRows, rows - row0));
 }
 
 // ---- NN-CP multiplicative update -------------------------------------------------------
@@ -477,9 +543,19 @@ cp_error_kernel(GramList<T> gl, int R, const T* __restrict__ w, const T* __restr
     const int tid = threadIdx.x;
     double iprod = 0.0, ncp = 0.0;
     const int64_t total = rows * R;
-    for (int64_t e = tid; e < total; e += blockDim.x) {
-        const int64_t i = e / R, r = e - i * R;
-        iprod += (double)m[i * m_ld + r] * (double)f[i * frs + r * fcs];
+    if (total < (1LL << 31)) {
+        // 32-bit index arithmetic and four independent loads in flight: this single CTA is pure latency
+        const int tot = (int)total, step = (int)blockDim.x;
+#pragma unroll 4
+        for (int e = tid; e < tot; e += step) {
+            const int i = e / R, r = e - i * R;
+            iprod += (double)__ldg(m + (int64_t)i * m_ld + r) * (double)__ldg(f + (int64_t)i * frs + (int64_t)r * fcs);
+        }
+    } else {
+        for (int64_t e = tid; e < total; e += blockDim.x) {
+            const int64_t i = e / R, r = e - i * R;
+            iprod += (double)m[i * m_ld + r] * (double)f[i * frs + r * fcs];
+        }
     }
     for (int e = tid; e < R * R; e += blockDim.x) {
         const int r = e / R, s = e - r * R;
@@ -602,7 +678,7 @@ int fill_grams(GramList<T>* gl, const void* const* grams, int nmodes, int skip) 
 
 template <typename T>
 int cp_update_launch(const void* const* grams, int nmodes, int mode, int64_t R, const T* w, double l2, const T* m,
-                     int64_t m_ld, int64_t rows, T* out, int64_t out_ld, cudaStream_t stream) {
+                     int64_t m_ld, int64_t rows, T* out, int64_t out_ld, T* gram_out, void* workspace, cudaStream_t stream) {
     GramList<T> gl;
     int st = fill_grams<T>(&gl, grams, nmodes, mode);
     if (st) return st;
@@ -620,7 +696,13 @@ int cp_update_launch(const void* const* grams, int nmodes, int mode, int64_t R, 
     if (smem > 200 * 1024) return TLB200_EUNSUPPORTED;
     const int nblk = (int)ceil_div(rows, kSolveRows);
     if (nblk == 0) return TLB200_OK;
-    cp_update_kernel<T><<<nblk, kSolveThreads, smem, stream>>>(gl, mode, (int)R, w, (T)l2, m, m_ld, rows, out, out_ld);
+    GramTail<T> gt;
+    gt.partial = nullptr; gt.gram = gram_out; gt.counter = nullptr;
+    if (gram_out != nullptr) {      // workspace: [ticket counter, 256 bytes][nblk][R*R]
+        gt.counter = static_cast<unsigned*>(workspace);
+        gt.partial = reinterpret_cast<T*>(static_cast<char*>(workspace) + 256);
+    }
+    cp_update_kernel<T><<<nblk, kSolveThreads, smem, stream>>>(gl, mode, (int)R, w, (T)l2, m, m_ld, rows, out, out_ld, gt);
     TLB_CHECK_LAUNCH();
     return TLB200_OK;
 }
@@ -677,9 +759,30 @@ extern "C" int tlb200_cp_update(const void* const* grams, int nmodes, int mode, 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == TLB200_F32)
         return cp_update_launch<float>(grams, nmodes, mode, rank, (const float*)weights, l2_reg, (const float*)m, m_ld, rows,
-                                       (float*)out, out_ld, s);
+                                       (float*)out, out_ld, nullptr, nullptr, s);
     return cp_update_launch<double>(grams, nmodes, mode, rank, (const double*)weights, l2_reg, (const double*)m, m_ld, rows,
-                                    (double*)out, out_ld, s);
+                                    (double*)out, out_ld, nullptr, nullptr, s);
+}
+
+extern "C" size_t tlb200_cp_update_gram_workspace_bytes(int64_t rows, int64_t rank, int dtype) {
+    if (rows < 0 || rank < 1 || !dtype_valid(dtype)) return 0;
+    return 256 + align_up((size_t)ceil_div(rows > 0 ? rows : 1, kSolveRows) * rank * rank * dtype_size(dtype), 256);
+}
+
+extern "C" int tlb200_cp_update_gram(const void* const* grams, int nmodes, int mode, int64_t rank, const void* weights,
+                                     double l2_reg, const void* m, int64_t m_ld, int64_t rows, int dtype, void* out,
+                                     int64_t out_ld, void* gram_out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!m || !out || !gram_out || !workspace || rank < 1 || rank > kMaxRank || rows < 1 || mode < 0 || mode >= nmodes ||
+        m_ld < rank || out_ld < rank || !dtype_valid(dtype))
+        return TLB200_EINVAL;
+    if (workspace_bytes < tlb200_cp_update_gram_workspace_bytes(rows, rank, dtype)) return TLB200_EWORKSPACE;
+    set_last_path("simt");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == TLB200_F32)
+        return cp_update_launch<float>(grams, nmodes, mode, rank, (const float*)weights, l2_reg, (const float*)m, m_ld, rows,
+                                       (float*)out, out_ld, (float*)gram_out, workspace, s);
+    return cp_update_launch<double>(grams, nmodes, mode, rank, (const double*)weights, l2_reg, (const double*)m, m_ld, rows,
+                                    (double*)out, out_ld, (double*)gram_out, workspace, s);
 }
 
 extern "C" int tlb200_nncp_update(const void* const* grams, int nmodes, int mode, int64_t rank, const void* weights,

