@@ -271,6 +271,46 @@ def run_ours(args):
     value = args.steps / (total_ms * 1e-3)
     rel_err = float(state.err[0].item())
 
+    # ---- the same sweeps with one full MTTKRP per mode (N tensor passes, the reference's call pattern) ----
+    three_pass = None
+    ttm_pass = None
+    if state.dimtree:
+        st3 = CPALS(x, weights, factors, comm=comm, shard_mode=0, dimtree=False)
+        n3 = max(3, min(args.steps, 30))
+        for _ in range(3):
+            st3.sweep(True)
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(n3):
+            st3.sweep(True)
+        b1.record()
+        barrier()
+        ms3 = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
+        three_pass = {"value": n3 / (float(ms3.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(ms3.item()) / n3,
+                      "steps": n3, "final_rel_error": float(st3.err[0].item()),
+                      "what": "same sweeps with a full MTTKRP per mode (no dimension-tree reuse): the call pattern "
+                              "SURVEY 8(d)'s 12.89 GB/sweep model describes"}
+        st3._graph = None
+        del st3
+        # the TTM pass that feeds the dimension tree (same tcgen05 engine): bytes = tensor read + T written
+        last = len(shape) - 1
+        for _ in range(3):
+            tb.mode_dot(x, state.factors[last], last, transpose=True)
+        c0_, c1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        c0_.record()
+        for _ in range(5):
+            tb.mode_dot(x, state.factors[last], last, transpose=True)
+        c1_.record()
+        torch.cuda.synchronize()
+        t_ms = c0_.elapsed_time(c1_) / 5
+        t_bytes = esize * (elems_local + elems_local // local_shape[last] * R + R * local_shape[last])
+        ttm_pass = {"ms_per_launch": t_ms, "algorithmic_bytes_per_launch": t_bytes, "achieved": t_bytes / (t_ms * 1e-3) / 1e9,
+                    "unit": "GB/s", "kernel": f"mode_dot(X, F_last^T, last) ({tb.last_kernel_path()})"}
+
     # ---- e2e: same sweep through the public API with HOST buffers ------------------------
     e2e = None
     if not args.no_e2e:
@@ -365,13 +405,20 @@ def run_ours(args):
             "dtype": "f32" if dtype == torch.float32 else "f64", "data": "synthetic",
             "config": {"workload": wl["name"], "shape": list(shape), "rank": R, "sharding": f"mode-0 slabs over {world} GPU(s)",
                        "l2": "inputs larger than L2 (tensor slab %.2f GB per GPU >> 126 MB)" % (esize * elems_local / 1e9),
-                       "kernel_path": path_used, "sweep": "3 x (MTTKRP + Gram-Hadamard LU solve + Gram) + error, CUDA graph"
-                       if world == 1 else "3 x (MTTKRP + all_reduce + solve + Gram) + error"},
+                       "kernel_path": path_used,
+                       "sweep": ("dimension-tree ALS sweep: T = X x_last F_last^T (one tensor pass) -> MTTKRP of every earlier "
+                                 "mode from T, full MTTKRP for the last mode (second tensor pass); identical factor updates, "
+                                 "parity-tested against the N-pass sweep" if state.dimtree else
+                                 "one full MTTKRP per mode") +
+                                (" + Gram-Hadamard LU solve + Gram per mode + error, one CUDA graph" if world == 1 else
+                                 " + all_reduce + solve + Gram per mode + error, one CUDA graph")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": f"MTTKRP ({path_used})",
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": avg_ms,
                          "per_mode_gbs": [alg_bytes / (m * 1e-3) / 1e9 for m in mttkrp_ms],
                          "frac_of_nominal_8TBs": achieved / 8000.0},
+            "three_pass": three_pass,
+            "ttm_pass": ttm_pass,
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(launches_per_sweep * args.steps),

@@ -121,6 +121,22 @@ typedef struct {
 int tlb200_mttkrp_plan(const int64_t* shape, int ndim, int mode, int64_t rank,
                        int dtype, int path, tlb200_mttkrp_plan_t* plan);
 
+/* Dimension-tree reuse inside one ALS sweep (the caller side of the MTTKRP path,
+ * tensorly/decomposition/_cp.py:407-428 calls unfolding_dot_khatri_rao once per mode):
+ * with T = mode_dot(x, F_{N-1}^T, N-1), shape (I_0, .., I_{N-2}, rank), C-contiguous,
+ *   tlb200_mttkrp_from_ttm(t, mode)[j, r] = w_r * sum T[.., j, .., r] * prod_{n != mode, n < N-1} F_n[i_n, r]
+ * equals tlb200_mttkrp(x, mode) for every mode < N-1 as long as F_{N-1} is unchanged, at
+ * rank / I_{N-1} of the memory traffic.  lead_shape = (I_0, .., I_{N-2}), nlead = N-1 >= 2;
+ * factors / strides have nlead entries (entry `mode` ignored). */
+size_t tlb200_mttkrp_from_ttm_workspace_bytes(const int64_t* lead_shape, int nlead, int mode,
+                                              int64_t rank, int dtype);
+
+int tlb200_mttkrp_from_ttm(const void* t, const int64_t* lead_shape, int nlead, int mode,
+                           const void* const* factors, const int64_t* f_row_stride,
+                           const int64_t* f_col_stride, int64_t rank, const void* weights,
+                           int dtype, void* out, int64_t out_ld, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------
  * mode_dot — replaces tensorly.tenalg.core_tenalg.mode_dot for a matrix operand
  * (tensorly/tenalg/core_tenalg/n_mode_product.py:5-76):

@@ -14,7 +14,7 @@ All arithmetic runs in hand-written CUDA kernels behind the C ABI of include/tlb
 there is no CPU fallback — a missing libtlb200.so raises at first use.
 """
 from ._ops import (cp_error, cp_update, fold, get_kernel_path, gram, khatri_rao, last_kernel_path, launch_count, mode_dot,
-                   mttkrp_plan, multi_mode_dot, nncp_update, release_workspaces, set_kernel_path, sumsq, unfold,
+                   mttkrp_from_ttm, mttkrp_plan, multi_mode_dot, nncp_update, release_workspaces, set_kernel_path, sumsq, unfold,
                    unfolding_dot_khatri_rao)
 from .backend import BACKEND_NAME, import_tensorly, register, use
 from .cp_als import CPALS, CPResult, non_negative_parafac, parafac, shard_bounds
@@ -23,7 +23,7 @@ __version__ = "0.1.0"
 __all__ = [
     "unfold", "fold", "khatri_rao", "unfolding_dot_khatri_rao", "mode_dot", "multi_mode_dot",
     "parafac", "non_negative_parafac", "CPALS", "CPResult", "shard_bounds",
-    "gram", "cp_update", "nncp_update", "cp_error", "sumsq", "mttkrp_plan",
+    "gram", "cp_update", "nncp_update", "cp_error", "sumsq", "mttkrp_plan", "mttkrp_from_ttm",
     "set_kernel_path", "get_kernel_path", "last_kernel_path", "launch_count", "release_workspaces",
     "register", "use", "import_tensorly", "BACKEND_NAME",
 ]

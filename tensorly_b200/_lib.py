@@ -57,6 +57,9 @@ SIGNATURES = {
                               c_int64, c_void_p, c_size_t, c_int, c_void_p]),
     "tlb200_mttkrp_plan": (c_int, [_I64P, c_int, c_int, c_int64, c_int, c_int, POINTER(MttkrpPlan)]),
     "tlb200_mode_dot_workspace_bytes": (c_size_t, [_I64P, c_int, c_int, c_int64, c_int, c_int]),
+    "tlb200_mttkrp_from_ttm_workspace_bytes": (c_size_t, [_I64P, c_int, c_int, c_int64, c_int]),
+    "tlb200_mttkrp_from_ttm": (c_int, [c_void_p, _I64P, c_int, c_int, _VPP, _I64P, _I64P, c_int64, c_void_p, c_int, c_void_p,
+                                       c_int64, c_void_p, c_size_t, c_void_p]),
     "tlb200_mode_dot": (c_int, [c_void_p, _I64P, c_int, c_int, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p,
                                 c_void_p, c_size_t, c_int, c_void_p]),
     "tlb200_multi_mode_dot_workspace_bytes": (c_size_t, [_I64P, c_int, _INTP, _I64P, c_int, c_int, c_int]),

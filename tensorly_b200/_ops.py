@@ -313,6 +313,56 @@ def unfolding_dot_khatri_rao(tensor: torch.Tensor, cp_tensor, mode: int) -> torc
     return out
 
 
+def mttkrp_from_ttm(contracted: torch.Tensor, cp_tensor, mode: int) -> torch.Tensor:
+    """MTTKRP of mode `mode` < N-1 from T = mode_dot(tensor, factors[N-1], N-1, transpose=True)
+    (shape I_0 x .. x I_{N-2} x rank): equals unfolding_dot_khatri_rao(tensor, cp_tensor, mode) while
+    factors[N-1] is unchanged, reading T (rank / I_{N-1} of the tensor) instead of the tensor.
+    `cp_tensor` = (weights | None, factors) with all N factors (entries `mode` and N-1 are not read)."""
+    _check_tensor(contracted, "contracted")
+    weights, factors = cp_tensor
+    factors = list(factors)
+    nlead = contracted.dim() - 1
+    if nlead < 2 or nlead + 1 > _lib.MAX_NDIM:
+        raise ValueError(f"mttkrp_from_ttm needs a 3..{_lib.MAX_NDIM}-way problem, got {nlead + 1}")
+    if len(factors) != nlead + 1:
+        raise ValueError(f"got {len(factors)} factors for a {nlead + 1}-way tensor")
+    if not 0 <= mode < nlead:
+        raise ValueError(f"mode {mode} must be one of the first {nlead} modes")
+    rank = contracted.shape[-1]
+    for i in range(nlead):
+        if i == mode:
+            continue
+        f = factors[i]
+        _check_tensor(f, f"factors[{i}]", contracted)
+        if f.dim() != 2 or f.shape[0] != contracted.shape[i] or f.shape[1] != rank:
+            raise ValueError(f"factors[{i}] must be ({contracted.shape[i]}, {rank}), got {tuple(f.shape)}")
+    w = None
+    if weights is not None:
+        w = torch.as_tensor(weights, dtype=contracted.dtype, device=contracted.device).reshape(-1).contiguous()
+        if w.numel() != rank:
+            raise ValueError(f"weights has {w.numel()} entries but the factors have {rank} columns")
+    t = contracted if contracted.is_contiguous() else contracted.contiguous()
+    out = torch.empty((t.shape[mode], rank), dtype=t.dtype, device=t.device)
+    if t.numel() == 0:
+        return out.zero_()
+    lib = _lib.load()
+    dt = _DTYPES[t.dtype]
+    lead = _lib.i64_array(t.shape[:nlead])
+    nbytes = lib.tlb200_mttkrp_from_ttm_workspace_bytes(lead, nlead, mode, rank, dt)
+    if nbytes == 0:
+        raise ValueError(f"mttkrp_from_ttm: unsupported problem shape={tuple(t.shape)} mode={mode}")
+    ws = _workspace(nbytes, t)
+    ptrs = [0 if i == mode else factors[i].data_ptr() for i in range(nlead)]
+    rs = [0 if i == mode else factors[i].stride(0) for i in range(nlead)]
+    cs = [0 if i == mode else factors[i].stride(1) for i in range(nlead)]
+    with _Device(t):
+        st = lib.tlb200_mttkrp_from_ttm(t.data_ptr(), lead, nlead, mode, _lib.ptr_array(ptrs), _lib.i64_array(rs),
+                                        _lib.i64_array(cs), rank, w.data_ptr() if w is not None else None, dt,
+                                        out.data_ptr(), rank, ws.data_ptr(), ws.numel(), _stream(t))
+    _lib.check(st, "mttkrp_from_ttm")
+    return out
+
+
 # --------------------------------------------------------------------------- TTM
 def mode_dot(tensor: torch.Tensor, matrix_or_vector: torch.Tensor, mode: int, transpose: bool = False) -> torch.Tensor:
     """n-mode product with a matrix or a vector (n_mode_product.py:5-76).

@@ -68,6 +68,8 @@ class CudaOps:
     """The product compute path: every call is a tlb200 kernel launch."""
 
     mttkrp = staticmethod(_ops.unfolding_dot_khatri_rao)
+    mode_dot = staticmethod(_ops.mode_dot)
+    mttkrp_from_ttm = staticmethod(_ops.mttkrp_from_ttm)   # dimension-tree reuse (see CPALS.dimtree)
     gram = staticmethod(_ops.gram)
     cp_update = staticmethod(_ops.cp_update)
     fused_gram = True        # cp_update(..., gram_out=) also writes the Gram of the updated factor
@@ -119,7 +121,7 @@ class CPALS:
 
     def __init__(self, tensor_local: torch.Tensor, weights: torch.Tensor, factors: Sequence[torch.Tensor],
                  l2_reg: float = 0.0, update: str = "ls", fixed_modes: Sequence[int] = (), comm: Optional[_Comm] = None,
-                 shard_mode: int = 0, ops=CudaOps, eps: Optional[float] = None):
+                 shard_mode: int = 0, ops=CudaOps, eps: Optional[float] = None, dimtree: Optional[bool] = None):
         self.x = tensor_local
         self.ops = ops
         self.comm = comm or _Comm()
@@ -145,6 +147,15 @@ class CPALS:
         self._graph = None
         self._graph_key = None
         self._eager_runs = 0
+        # Dimension-tree reuse: T = X x_{N-1} F_{N-1}^T is formed once per sweep and serves the MTTKRPs of all
+        # modes before the last, so the tensor is streamed twice per sweep instead of N times (same updates, the
+        # last factor is only changed after T's last use).  Worth it from two served modes on.
+        served = [m for m in self.modes if m < self.ndim - 1]
+        can = hasattr(self.ops, "mttkrp_from_ttm") and self.ndim >= 3 and len(served) >= 2
+        if dimtree is None:
+            dimtree = os.environ.get("TLB200_DIMTREE", "1") != "0"
+        self.dimtree = bool(dimtree) and can
+        self._contracted: Optional[torch.Tensor] = None
         # ||X||^2 (all-reduced over slabs) and the initial Grams
         self.ops.sumsq(self.x, out=self.norm_x2)
         self.comm.all_reduce(self.norm_x2)
@@ -158,7 +169,10 @@ class CPALS:
             self.comm.all_reduce(self.grams[n])
 
     def _update_mode(self, mode: int) -> None:
-        m = self.ops.mttkrp(self.x, (self.weights, self.factors), mode)
+        if self._contracted is not None and mode < self.ndim - 1:
+            m = self.ops.mttkrp_from_ttm(self._contracted, (self.weights, self.factors), mode)
+        else:
+            m = self.ops.mttkrp(self.x, (self.weights, self.factors), mode)
         if self.shard_mode is not None and mode != self.shard_mode:
             self.comm.all_reduce(m)          # partial sums over the slabs
         if self.update == "ls" and getattr(self.ops, "fused_gram", False):
@@ -185,8 +199,13 @@ class CPALS:
             self.err[0] = torch.sqrt(torch.abs(nx2 + self.err[2] - 2 * self.err[1])) / torch.sqrt(nx2)
 
     def sweep_eager(self, with_error: bool = True) -> None:
+        if self.dimtree:
+            self._contracted = self.ops.mode_dot(self.x, self.factors[-1], self.ndim - 1, transpose=True)
         for mode in self.modes:
+            if mode == self.ndim - 1:
+                self._contracted = None       # the last factor changes now: T is stale (and its memory is free again)
             self._update_mode(mode)
+        self._contracted = None
         if with_error:
             if self.modes[-1] != self.ndim - 1:
                 # the fast error needs the last mode's MTTKRP with the current factors

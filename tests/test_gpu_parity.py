@@ -169,6 +169,35 @@ def test_mttkrp_vs_oracle(shape, rank, dtype, path):
         assert tb.last_kernel_path() in ("simt", "tcgen05")
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape,rank", [((64, 48, 80), 32), ((130, 70, 45), 10), ((256, 64, 96), 64), ((33, 257, 19), 7),
+                                        ((40, 24, 20, 12), 16), ((12, 10, 9, 8, 6), 5), ((96, 160, 64), 100),
+                                        ((512, 256, 128), 32)])
+def test_mttkrp_from_ttm_vs_oracle(shape, rank, dtype):
+    """Dimension-tree reuse: the MTTKRP of every mode before the last, from T = X x_{N-1} F_{N-1}^T, meets the
+    same gate against the oracle's full MTTKRP."""
+    rng = np.random.RandomState(hash((shape, rank, 7)) % (2 ** 31))
+    x = rng.random_sample(shape).astype(dtype)
+    fs = [rng.random_sample((s, rank)).astype(dtype) for s in shape]
+    w = (rng.random_sample(rank) + 0.5).astype(dtype)
+    xd, wd = dev(x), dev(w)
+    fd = [dev(f) for f in fs]
+    fd[0] = dev(np.ascontiguousarray(fs[0].T)).T          # a column-major factor
+    t = tb.mode_dot(xd, fd[-1], len(shape) - 1, transpose=True)
+    assert tuple(t.shape) == tuple(shape[:-1]) + (rank,)
+    for mode in range(len(shape) - 1):
+        ref = O.unfolding_dot_khatri_rao(x, (w, fs), mode)
+        out = host(tb.mttkrp_from_ttm(t, (wd, fd), mode))
+        err = rel_fro(out, ref)
+        assert err <= TOL[np.dtype(dtype)], (shape, rank, mode, err)
+        out_now = host(tb.mttkrp_from_ttm(t, (None, fd), mode))
+        assert rel_fro(out_now, O.unfolding_dot_khatri_rao(x, (None, fs), mode)) <= TOL[np.dtype(dtype)]
+    with pytest.raises(ValueError):
+        tb.mttkrp_from_ttm(t, (wd, fd), len(shape) - 1)
+    with pytest.raises(ValueError):
+        tb.mttkrp_from_ttm(t, (wd, fd[:-1]), 0)
+
+
 @pytest.mark.parametrize("path", PATHS)
 def test_mttkrp_zero_mean_data(path):
     """Zero-mean data does not average rounding bias away: a plain-TF32
@@ -408,6 +437,28 @@ def test_parafac_driver_vs_reference(golden, tag, use_graph):
         assert rel <= 1e-9
         for a, b in zip(cp[1], g.arrays(tag, "f")):
             assert rel_fro(host(a), b) <= 1e-6
+
+
+@pytest.mark.parametrize("shape,rank", [((96, 80, 112), 16), ((40, 24, 20, 12), 8)])
+def test_parafac_dimtree_same_trajectory(shape, rank):
+    """Two tensor passes per sweep (dimension tree) vs N passes: same ALS trajectory."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.rand(shape, generator=g, device="cuda")
+    fs = [torch.rand(s, rank, generator=g, device="cuda") for s in shape]
+    w = torch.ones(rank, device="cuda")
+    runs = []
+    for dimtree in (False, True):
+        st = tb.CPALS(x, w, fs, dimtree=dimtree)
+        assert st.dimtree == dimtree
+        errs = []
+        for _ in range(6):
+            st.sweep(True)
+            errs.append(float(st.err[0]))
+        runs.append((errs, [f.clone() for f in st.factors]))
+    dev_err = max(abs(a - b) / b for a, b in zip(*[r[0] for r in runs]))
+    assert dev_err <= 1e-5, dev_err
+    for a, b in zip(runs[0][1], runs[1][1]):
+        assert float(torch.linalg.norm(a - b) / torch.linalg.norm(b)) <= 1e-3
 
 
 def test_parafac_config1_fp64(golden):
