@@ -39,6 +39,9 @@ if which in ("all", "c3"):
     print("C3 tucker reference GPU path (core):  %.2f sweeps/s" % sweeps_per_s(run_t, 1, 3), flush=True)
     tb.use()
     print("C3 tucker on b200 tenalg:             %.2f sweeps/s" % sweeps_per_s(run_t, 1, 3), flush=True)
+    tb.use_gram_svd()
+    print("C3 tucker on b200 tenalg + gram_svd:  %.2f sweeps/s" % sweeps_per_s(run_t, 1, 5), flush=True)
+    tb.use_default_svd()
     us = [torch.randn(512, 64, generator=g, device="cuda").t().contiguous().t() for _ in range(3)]
     for name, be in (("core", "core"), ("b200", "b200")):
         tl.tenalg.set_backend(be)

@@ -16,8 +16,9 @@ there is no CPU fallback — a missing libtlb200.so raises at first use.
 from ._ops import (cp_error, cp_update, fold, get_kernel_path, gram, khatri_rao, last_kernel_path, launch_count, mode_dot,
                    mttkrp_from_ttm, mttkrp_plan, multi_mode_dot, nncp_update, release_workspaces, set_kernel_path, sumsq, unfold,
                    unfolding_dot_khatri_rao)
-from .backend import BACKEND_NAME, import_tensorly, register, use
+from .backend import BACKEND_NAME, import_tensorly, register, set_dimension_tree, use
 from .cp_als import CPALS, CPResult, non_negative_parafac, parafac, shard_bounds
+from .svd import gram_svd, use_default_svd, use_gram_svd
 
 __version__ = "0.1.0"
 __all__ = [
@@ -25,5 +26,6 @@ __all__ = [
     "parafac", "non_negative_parafac", "CPALS", "CPResult", "shard_bounds",
     "gram", "cp_update", "nncp_update", "cp_error", "sumsq", "mttkrp_plan", "mttkrp_from_ttm",
     "set_kernel_path", "get_kernel_path", "last_kernel_path", "launch_count", "release_workspaces",
-    "register", "use", "import_tensorly", "BACKEND_NAME",
+    "register", "use", "set_dimension_tree", "import_tensorly", "BACKEND_NAME",
+    "gram_svd", "use_gram_svd", "use_default_svd",
 ]

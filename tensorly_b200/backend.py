@@ -20,12 +20,58 @@ from __future__ import annotations
 
 import os
 import sys
+import threading
 
 from . import _ops
 
 BACKEND_NAME = "b200"
+
+# ---- optional dimension-tree reuse behind the stateless tenalg API --------------------------------------------
+# The reference's ALS loops call unfolding_dot_khatri_rao(tensor, (weights, factors), mode) for mode = 0, 1, ..,
+# N-1 with the SAME tensor object and — until the last mode — the same last-factor object
+# (tensorly/decomposition/_cp.py:407-428).  With the cache on, the mode-0 call forms
+# T = tensor x_{N-1} factors[-1]^T once and the calls for 0 <= mode < N-1 are answered from T
+# (tlb200_mttkrp_from_ttm) for as long as `tensor` and `factors[-1]` are the very same objects at the same
+# torch `_version` (so an in-place edit or a new tensor is a miss, never a stale hit; the cache holds references,
+# so their storage cannot be recycled under it).  Off by default: tensorly_b200.use(dimension_tree=True) or
+# TLB200_BACKEND_DIMTREE=1 turn it on.
+_dimtree = {"on": os.environ.get("TLB200_BACKEND_DIMTREE", "0") == "1"}
+_cache = threading.local()
+
+
+def set_dimension_tree(flag: bool) -> None:
+    """Enable/disable the per-sweep reuse of the last-mode contraction in `unfolding_dot_khatri_rao`."""
+    _dimtree["on"] = bool(flag)
+    _cache.entry = None
+
+
+def _unfolding_dot_khatri_rao(tensor, cp_tensor, mode):
+    if not _dimtree["on"]:
+        return _ops.unfolding_dot_khatri_rao(tensor, cp_tensor, mode)
+    import torch
+    weights, factors = cp_tensor
+    factors = list(factors)
+    ndim = tensor.dim() if torch.is_tensor(tensor) else 0
+    if ndim >= 3 and len(factors) == ndim and -ndim <= mode < ndim and torch.is_tensor(factors[-1]):
+        mode %= ndim
+        last = factors[-1]
+        if mode < ndim - 1:
+            e = getattr(_cache, "entry", None)
+            hit = (e is not None and e[0] is tensor and e[1] == tensor._version and e[2] is last and e[3] == last._version)
+            if not hit and mode == 0:        # a sweep starts: one pass over the tensor serves modes 0 .. N-2
+                t = _ops.mode_dot(tensor, last, ndim - 1, transpose=True)
+                e = (tensor, tensor._version, last, last._version, t)
+                _cache.entry = e
+                hit = True
+            if hit:
+                return _ops.mttkrp_from_ttm(e[4], (weights, factors), mode)
+        else:
+            _cache.entry = None              # the last factor is about to change: free T
+    return _ops.unfolding_dot_khatri_rao(tensor, cp_tensor, mode)
+
+
 _OURS = {
-    "unfolding_dot_khatri_rao": _ops.unfolding_dot_khatri_rao,
+    "unfolding_dot_khatri_rao": _unfolding_dot_khatri_rao,
     "khatri_rao": _ops.khatri_rao,
     "mode_dot": _ops.mode_dot,
     "multi_mode_dot": _ops.multi_mode_dot,
@@ -79,9 +125,12 @@ def register():
     return B200TenalgBackend
 
 
-def use():
-    """register() and select the backend (process-wide default + this thread)."""
+def use(dimension_tree=None):
+    """register() and select the backend (process-wide default + this thread).  `dimension_tree=True/False`
+    also switches the per-sweep reuse described above (None leaves it as it is)."""
     register()
+    if dimension_tree is not None:
+        set_dimension_tree(dimension_tree)
     tl = import_tensorly()
     tl.tenalg.set_backend(BACKEND_NAME)
     return tl

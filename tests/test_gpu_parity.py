@@ -537,6 +537,37 @@ def test_reference_parafac_runs_unmodified_on_backend(tl_b200, golden):
         assert tb.last_kernel_path() in ("simt", "tcgen05")
 
 
+def test_reference_parafac_on_backend_with_dimension_tree_cache(tl_b200, golden):
+    """The opt-in reuse behind the stateless API: same trajectories as the reference, T formed once per sweep,
+    and never a stale hit (new tensor object / in-place edit of the last factor are misses)."""
+    from tensorly.cp_tensor import CPTensor
+    from tensorly.decomposition import parafac
+    from tensorly.tenalg import unfolding_dot_khatri_rao as tl_mttkrp
+    g = golden("als")
+    tb.set_dimension_tree(True)
+    try:
+        for tag in ("p32", "p64", "p4way"):
+            x = g[f"{tag}/x"]
+            rank, iters = int(g[f"{tag}/rank"]), int(g[f"{tag}/iters"])
+            init = CPTensor((torch.ones(rank, dtype=dev(x).dtype, device="cuda"), [dev(f) for f in g.arrays(tag, "init")]))
+            cp, errs = parafac(dev(x), rank, n_iter_max=iters, init=init, tol=0, return_errors=True)
+            ref = g[f"{tag}/errors"]
+            got = np.array([float(e) for e in errs])
+            assert np.max(np.abs(got - ref) / ref) <= 1e-4
+        # staleness: edit the last factor in place between two calls for the same tensor
+        rng = np.random.RandomState(5)
+        x = dev(rng.random_sample((40, 30, 20)).astype(np.float32))
+        fs = [dev(rng.random_sample((s, 6)).astype(np.float32)) for s in (40, 30, 20)]
+        m0 = tl_mttkrp(x, (None, fs), 0)
+        assert rel_fro(host(tl_mttkrp(x, (None, fs), 1)), O.unfolding_dot_khatri_rao(host(x), (None, [host(f) for f in fs]), 1)) <= 1e-5
+        fs[2].mul_(2.0)
+        got = host(tl_mttkrp(x, (None, fs), 1))
+        assert rel_fro(got, O.unfolding_dot_khatri_rao(host(x), (None, [host(f) for f in fs]), 1)) <= 1e-5
+        assert rel_fro(host(m0), O.unfolding_dot_khatri_rao(host(x), (None, [host(fs[0]), host(fs[1]), host(fs[2]) / 2]), 0)) <= 1e-5
+    finally:
+        tb.set_dimension_tree(False)
+
+
 def test_reference_nn_parafac_and_tucker_run_unmodified_on_backend(tl_b200, golden):
     from tensorly.cp_tensor import CPTensor
     from tensorly.decomposition import non_negative_parafac, partial_tucker, tucker
@@ -555,6 +586,22 @@ def test_reference_nn_parafac_and_tucker_run_unmodified_on_backend(tl_b200, gold
     (core2, factors2), errs2 = partial_tucker(dev(x), ranks[:2], modes=[0, 1], n_iter_max=3, init="svd", tol=0)
     assert tuple(core2.shape) == (ranks[0], ranks[1], x.shape[2])
     assert tb.last_kernel_path() in ("simt", "tcgen05")
+
+
+def test_reference_tucker_with_gram_svd_plugin(tl_b200, golden):
+    """HOOI with the Gram + eigh SVD plug-in follows the reference trajectory."""
+    from tensorly.decomposition import tucker
+    g = golden("als")
+    x = g["tucker/x"]
+    ranks = [int(r) for r in g["tucker/ranks"]]
+    tb.use_gram_svd()
+    try:
+        (core, factors), errs = tucker(dev(x), ranks, n_iter_max=5, init="random", random_state=1, tol=0, return_errors=True)
+    finally:
+        tb.use_default_svd()
+    ref = g["tucker/errors"]
+    assert np.max(np.abs(np.array([float(e) for e in errs]) - ref) / ref) <= 1e-4
+    assert abs(float(torch.linalg.norm(core)) - float(g["tucker/core_norm"])) <= 1e-5 * float(g["tucker/core_norm"])
 
 
 def test_reference_reconstruction_uses_backend(tl_b200):

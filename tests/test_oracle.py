@@ -198,3 +198,22 @@ def test_lowrank_nn_tucker_vs_reference(golden):
     (core, _), errs = O.tucker_hooi(x, ranks, g.arrays("tucker", "init"), n_iter_max=5)
     assert np.max(np.abs(np.array(errs) - g["tucker/errors"])) <= 1e-10
     assert abs(O.tensor_norm(core) - float(g["tucker/core_norm"])) <= 1e-9
+
+
+def test_gram_svd_plugin_matches_lapack_svd():
+    """tensorly_b200.gram_svd (host-side plug-in, library GEMM + eigh): singular triplets of short-fat and
+    tall-skinny matrices agree with LAPACK's SVD; full_matrices=True defers to the previous svd."""
+    import torch
+    from tensorly_b200.svd import gram_svd
+    rng = np.random.RandomState(3)
+    for shape in [(20, 300), (300, 20), (16, 16)]:
+        a = torch.as_tensor(rng.standard_normal(shape))
+        u, s, vh = gram_svd(a, full_matrices=False)
+        _, s_ref, _ = torch.linalg.svd(a, full_matrices=False)
+        k = min(shape)
+        assert u.shape == (shape[0], k) and s.shape == (k,) and vh.shape == (k, shape[1])
+        assert float((s - s_ref).abs().max() / s_ref.max()) < 1e-12
+        assert float(torch.linalg.norm((u * s) @ vh - a) / torch.linalg.norm(a)) < 1e-10
+        assert float(torch.linalg.norm(u.T @ u - torch.eye(k, dtype=a.dtype))) < 1e-8
+    u, s, vh = gram_svd(torch.as_tensor(rng.standard_normal((6, 9))), full_matrices=True)
+    assert u.shape == (6, 6) and vh.shape == (9, 9)
