@@ -32,6 +32,28 @@ class OracleOps:
         return torch.from_numpy(np.ascontiguousarray(O.unfolding_dot_khatri_rao(_np(x), (_np(w), [_np(f) for f in fs]), mode)))
 
     @staticmethod
+    def mode_dot(x, m, mode, transpose=False):
+        return torch.from_numpy(np.ascontiguousarray(O.mode_dot(_np(x), _np(m), mode, transpose=transpose)))
+
+    @staticmethod
+    def mttkrp_from_ttm(t, cp, mode):
+        """MTTKRP of a mode before the last from T = X x_last F_last^T: the same sum, written as an einsum
+        over T (leading modes i_0..i_{N-2}, trailing r) and the other leading factors."""
+        w, fs = cp
+        t = _np(t)
+        nlead = t.ndim - 1
+        letters = "abcdefg"[:nlead]
+        operands, subs = [t], [letters + "r"]
+        for i in range(nlead):
+            if i != mode:
+                operands.append(_np(fs[i]))
+                subs.append(letters[i] + "r")
+        out = np.einsum(",".join(subs) + "->" + letters[mode] + "r", *operands)
+        if w is not None:
+            out = out * _np(w)[None, :]
+        return torch.from_numpy(np.ascontiguousarray(out.astype(t.dtype)))
+
+    @staticmethod
     def gram(f, out=None):
         g = torch.from_numpy(_np(f).T @ _np(f))
         return g if out is None else out.copy_(g)

@@ -92,3 +92,33 @@ def test_sharded_parafac_last_mode_and_four_way():
 @pytest.mark.timeout(300)
 def test_sharded_non_negative_parafac():
     _run((8, 7, 6), 3, shard_mode=0, update="mu", iters=5)
+
+
+def test_dimension_tree_sweep_equals_n_pass_sweep_on_cpu_ops():
+    """Host logic of the dimension-tree sweep (when T is formed, which modes it serves, when it is dropped),
+    with oracle-backed ops in fp64: identical trajectory to the sweep with a full MTTKRP per mode."""
+    import tensorly_b200 as tb
+    from oracle import oracle as O
+    from oracle_ops import OracleOps
+    for shape, fixed in (((9, 8, 7), ()), ((6, 5, 4, 7), ()), ((6, 5, 4, 7), (1,))):
+        x = torch.from_numpy(O.random_tensor(shape, 0))
+        w, fs = O.random_cp_factors(shape, 3, 1)
+        runs = []
+        for dimtree in (True, False):
+            st = tb.CPALS(x, torch.from_numpy(w.copy()), [torch.from_numpy(f.copy()) for f in fs], ops=OracleOps,
+                          fixed_modes=fixed, dimtree=dimtree)
+            assert st.dimtree == dimtree
+            errs = []
+            for _ in range(4):
+                st.sweep(True)
+                errs.append(float(st.err[0]))
+                assert st._contracted is None            # T never outlives a sweep
+            runs.append((errs, st.factors))
+        assert np.allclose(runs[0][0], runs[1][0], rtol=1e-12, atol=0)
+        for a, b in zip(runs[0][1], runs[1][1]):
+            assert np.allclose(a.numpy(), b.numpy(), rtol=1e-9, atol=1e-12)
+    # fewer than two served modes: the reuse cannot pay off and stays off
+    x = torch.from_numpy(O.random_tensor((5, 4, 3), 0))
+    w, fs = O.random_cp_factors((5, 4, 3), 2, 1)
+    st = tb.CPALS(x, torch.from_numpy(w), [torch.from_numpy(f) for f in fs], ops=OracleOps, fixed_modes=(0,), dimtree=True)
+    assert st.dimtree is False
