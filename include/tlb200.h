@@ -116,6 +116,9 @@ typedef struct {
     int64_t rank_padded;      /* column count of the P/Q/partials tables    */
     int64_t splits;           /* split-K factor (deterministic 2-pass sum)  */
     int     path;             /* resolved tlb200_path                       */
+    int     rank_passes;      /* passes over the tensor: 1, or ceil(rank/64) column blocks
+                                 on the tcgen05 path when rank > 64 (the other fields then
+                                 describe the first pass)                   */
 } tlb200_mttkrp_plan_t;
 
 int tlb200_mttkrp_plan(const int64_t* shape, int ndim, int mode, int64_t rank,

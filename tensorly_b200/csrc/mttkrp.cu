@@ -19,8 +19,8 @@
 
 namespace tlb200 {
 
-static int make_plan(const int64_t* shape, int ndim, int mode, int64_t rank, int dtype, int path,
-                     tlb200_mttkrp_plan_t* pl) {
+static int make_plan_one(const int64_t* shape, int ndim, int mode, int64_t rank, int dtype, int path,
+                         tlb200_mttkrp_plan_t* pl) {
     if (!shape || !pl || ndim < 2 || ndim > TLB200_MAX_NDIM || mode < 0 || mode >= ndim || rank < 1 ||
         !dtype_valid(dtype) || path < TLB200_PATH_AUTO || path > TLB200_PATH_TCGEN05)
         return TLB200_EINVAL;
@@ -71,6 +71,7 @@ static int make_plan(const int64_t* shape, int ndim, int mode, int64_t rank, int
     if (path != TLB200_PATH_SIMT && mttkrp_tc_supported(*pl, rank, dtype)) resolved = TLB200_PATH_TCGEN05;
     if (path == TLB200_PATH_TCGEN05 && resolved != TLB200_PATH_TCGEN05) return TLB200_EUNSUPPORTED;
     pl->path = resolved;
+    pl->rank_passes = 1;
 
     if (resolved == TLB200_PATH_TCGEN05) {
         mttkrp_tc_fill_plan(pl, rank);
@@ -89,6 +90,25 @@ static int make_plan(const int64_t* shape, int ndim, int mode, int64_t rank, int
         pl->splits = ceil_div(total_chunks, per);
     }
     return TLB200_OK;
+}
+
+constexpr int64_t kTcRankChunk = 64;      // widest column block the tcgen05 engine takes in one pass
+
+// Rank > 64 on the tensor-core engine: ceil(rank / 64) passes over the tensor, each producing a block of 64
+// columns (factor column slices are pointer offsets).  Two to four passes at ~5 TB/s still beat the SIMT kernel,
+// which is FMA-bound at such ranks (0.25 TB/s at rank 100).  The returned plan describes the first pass.
+static int make_plan(const int64_t* shape, int ndim, int mode, int64_t rank, int dtype, int path,
+                     tlb200_mttkrp_plan_t* pl) {
+    if (rank > kTcRankChunk && dtype == TLB200_F32 && path != TLB200_PATH_SIMT) {
+        tlb200_mttkrp_plan_t chunk;
+        const int st = make_plan_one(shape, ndim, mode, kTcRankChunk, dtype, path, &chunk);
+        if (st == TLB200_OK && chunk.path == TLB200_PATH_TCGEN05) {
+            *pl = chunk;
+            pl->rank_passes = (int)ceil_div(rank, kTcRankChunk);
+            return TLB200_OK;
+        }
+    }
+    return make_plan_one(shape, ndim, mode, rank, dtype, path, pl);
 }
 
 static size_t workspace_for(const tlb200_mttkrp_plan_t& pl, int dtype) {
@@ -195,6 +215,13 @@ extern "C" size_t tlb200_mttkrp_workspace_bytes(const int64_t* shape, int ndim, 
     tlb200_mttkrp_plan_t pl;
     if (make_plan(shape, ndim, mode, rank, dtype, path, &pl)) return 0;
     size_t need = workspace_for(pl, dtype);
+    if (pl.rank_passes > 1 && rank % kTcRankChunk) {       // the last, narrower pass may plan differently
+        tlb200_mttkrp_plan_t tail;
+        if (!make_plan_one(shape, ndim, mode, rank % kTcRankChunk, dtype, path, &tail)) {
+            const size_t t = workspace_for(tail, dtype);
+            if (t > need) need = t;
+        }
+    }
     if (path == TLB200_PATH_AUTO && pl.path == TLB200_PATH_TCGEN05) {
         // AUTO may still have to take the SIMT path at launch time (e.g. a tensor pointer that
         // is not 16-byte aligned cannot be described to TMA): size for both.
@@ -225,6 +252,23 @@ extern "C" int tlb200_mttkrp(const void* x, const int64_t* shape, int ndim, int 
     if (workspace_bytes < workspace_for(pl, dtype)) return TLB200_EWORKSPACE;
     if (reinterpret_cast<uintptr_t>(workspace) % 256) return TLB200_EINVAL;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (pl.rank_passes > 1) {
+        // column blocks of 64: same tensor, factor columns [c0, c0 + rc) (pointer offsets), output columns alike
+        const float* fptr[TLB200_MAX_NDIM];
+        for (int64_t c0 = 0; c0 < rank; c0 += kTcRankChunk) {
+            const int64_t rc = rank - c0 < kTcRankChunk ? rank - c0 : kTcRankChunk;
+            tlb200_mttkrp_plan_t cpl;
+            st = make_plan_one(shape, ndim, mode, rc, dtype, path, &cpl);
+            if (st) return st;
+            if (workspace_bytes < workspace_for(cpl, dtype)) return TLB200_EWORKSPACE;
+            for (int i = 0; i < ndim; ++i)
+                fptr[i] = i == mode ? nullptr : static_cast<const float*>(factors[i]) + c0 * f_col_stride[i];
+            st = run<float>((const float*)x, shape, ndim, mode, fptr, f_row_stride, f_col_stride, rc,
+                            weights ? (const float*)weights + c0 : nullptr, (float*)out + c0, out_ld, workspace, cpl, s);
+            if (st) return st;
+        }
+        return TLB200_OK;
+    }
     if (dtype == TLB200_F32)
         return run<float>((const float*)x, shape, ndim, mode, reinterpret_cast<const float* const*>(factors), f_row_stride,
                           f_col_stride, rank, (const float*)weights, (float*)out, out_ld, workspace, pl, s);

@@ -26,6 +26,8 @@ split_matrix_kernel(const float* __restrict__ m, int64_t I, int64_t J, int64_t m
     }
 }
 
+constexpr int64_t kTtmRowBlock = 64;   // output rows (accumulator columns) per pass
+
 struct TtmGeom {
     int layout;
     int64_t M, A, B;       // engine extents: rows, batch, contraction
@@ -56,19 +58,21 @@ bool geom(int64_t L, int64_t J, int64_t T, int64_t I, TtmGeom* g) {
 
 bool ttm_tc_supported(int64_t L, int64_t J, int64_t T, int64_t I) {
     TtmGeom g;
-    if (!geom(L, J, T, I, &g)) return false;
+    if (I < 1 || I > 4 * kTtmRowBlock) return false;      // beyond 4 passes the SIMT kernel's single pass wins
+    if (!geom(L, J, T, I < kTtmRowBlock ? I : kTtmRowBlock, &g)) return false;
     if (L * J * T < (1 << 18) || g.M < 32 || J < 16) return false;   // launch-bound sizes: SIMT
     return tc_available();
 }
 
 size_t ttm_tc_workspace(int64_t L, int64_t J, int64_t T, int64_t I) {
     TtmGeom g;
-    if (!geom(L, J, T, I, &g)) return 0;
+    if (!geom(L, J, T, I < kTtmRowBlock ? I : kTtmRowBlock, &g)) return 0;
     return 2 * align_up((size_t)g.rp * g.kpad * 4, 256) + 256;
 }
 
-int ttm_tc_launch(const float* x, int64_t L, int64_t J, int64_t T, const float* m, int64_t I, int64_t mrs, int64_t mcs,
-                  float* out, void* workspace, cudaStream_t stream) {
+// one pass: rows [0, I) of `m` (I <= 64) into output rows of an array whose mode extent is I_total
+static int ttm_tc_launch_block(const float* x, int64_t L, int64_t J, int64_t T, const float* m, int64_t I, int64_t I_total,
+                               int64_t mrs, int64_t mcs, float* out, void* workspace, cudaStream_t stream) {
     TtmGeom g;
     if (!geom(L, J, T, I, &g) || !workspace) return TLB200_EUNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(x) % 16) return TLB200_EUNSUPPORTED;
@@ -125,10 +129,23 @@ int ttm_tc_launch(const float* x, int64_t L, int64_t J, int64_t T, const float* 
     p.group_units = tc_group_units();
     p.P = nullptr;
     p.out = out;
-    if (g.layout == TC_X_MMAJOR) { p.sOk = I * T; p.sOm = 1; p.sOn = T; }
-    else                         { p.sOk = 0; p.sOm = I; p.sOn = 1; }
+    if (g.layout == TC_X_MMAJOR) { p.sOk = I_total * T; p.sOm = 1; p.sOn = T; }
+    else                         { p.sOk = 0; p.sOm = I_total; p.sOn = 1; }
     p.n_valid = (int)I;
     return tc_stream_launch(l, stream);
+}
+
+// More than 64 output rows: one pass over the tensor per block of 64 rows of the matrix (row blocks of `m` and of
+// the output are pointer offsets).  2-4 passes at several TB/s still beat the FMA-bound SIMT kernel.
+int ttm_tc_launch(const float* x, int64_t L, int64_t J, int64_t T, const float* m, int64_t I, int64_t mrs, int64_t mcs,
+                  float* out, void* workspace, cudaStream_t stream) {
+    for (int64_t c0 = 0; c0 < I; c0 += kTtmRowBlock) {
+        const int64_t rc = I - c0 < kTtmRowBlock ? I - c0 : kTtmRowBlock;
+        float* dst = out + (T >= 32 ? c0 * T : c0);
+        const int st = ttm_tc_launch_block(x, L, J, T, m + c0 * mrs, rc, I, mrs, mcs, dst, workspace, stream);
+        if (st) return st;
+    }
+    return TLB200_OK;
 }
 
 }  // namespace tlb200

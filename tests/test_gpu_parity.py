@@ -146,6 +146,7 @@ MTTKRP_CASES = [
     ((12, 10, 9, 8, 6), 5),
     ((300, 200), 12),
     ((96, 160, 64), 100),
+    ((128, 96, 160), 130),       # three column blocks on the tensor-core path
     ((16, 16, 4096), 32),
     ((4096, 16, 16), 32),
 ]
@@ -280,6 +281,7 @@ def test_mode_dot_golden(golden, path):
 @pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("shape,J", [((64, 96, 128), 32), ((128, 128, 128), 64), ((50, 33, 70), 17), ((20, 12, 10, 16), 8),
+                                     ((64, 96, 128), 100), ((128, 128, 128), 150),
                                      ((256, 40), 24), ((8, 512, 64), 64), ((64, 64, 3), 5)])
 def test_mode_dot_vs_oracle(shape, J, dtype, path):
     tb.set_kernel_path(path)
