@@ -26,7 +26,8 @@ constexpr int kThreads = 256;
 template <typename T, int VW>
 __global__ void __launch_bounds__(kThreads)
 from_ttm_inner_kernel(const T* __restrict__ t, int64_t A, int64_t J, int64_t B, int R, const T* __restrict__ P,
-                      const T* __restrict__ Q, int64_t a_per_split, T* __restrict__ out, int64_t out_ld, int64_t out_split) {
+                      const T* __restrict__ Q, int64_t a_per_split, int b_splits, int64_t b_per_split, T* __restrict__ out,
+                      int64_t out_ld, int64_t out_split) {
     using V = Vec<T, VW>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     V* red = reinterpret_cast<V*>(smem_raw);
@@ -34,8 +35,10 @@ from_ttm_inner_kernel(const T* __restrict__ t, int64_t A, int64_t J, int64_t B, 
     const int nbl = kThreads / RV;
     const int rv = threadIdx.x % RV, bl = threadIdx.x / RV;
     const int64_t j = blockIdx.x;
-    const int64_t a0 = (int64_t)blockIdx.y * a_per_split;
+    const int64_t a0 = (int64_t)(blockIdx.y / b_splits) * a_per_split;      // split = (a range, b range)
     const int64_t a1 = min(A, a0 + a_per_split);
+    const int64_t b0 = (int64_t)(blockIdx.y % b_splits) * b_per_split;
+    const int64_t b1 = min(B, b0 + b_per_split);
     V acc;
 #pragma unroll
     for (int c = 0; c < VW; ++c) acc.v[c] = T(0);
@@ -46,7 +49,7 @@ from_ttm_inner_kernel(const T* __restrict__ t, int64_t A, int64_t J, int64_t B, 
 #pragma unroll
             for (int c = 0; c < VW; ++c) tmp.v[c] = T(0);
 #pragma unroll 4
-            for (int64_t b = bl; b < B; b += nbl) {
+            for (int64_t b = b0 + bl; b < b1; b += nbl) {
                 const V x = row[b * RV];
                 const V q = reinterpret_cast<const V*>(Q + b * R)[rv];
 #pragma unroll
@@ -109,7 +112,8 @@ from_ttm_outer_kernel(const T* __restrict__ t, int64_t A, int64_t J, int R, cons
 struct Geometry {
     int64_t A, J, B;
     int pf, pc, qf, qc;
-    int64_t splits, a_per_split;
+    int64_t splits, a_per_split;       // splits = a_splits * b_splits partial results
+    int64_t b_splits, b_per_split;
 };
 
 int make_geometry(const int64_t* lead_shape, int nlead, int mode, int64_t rank, int dtype, Geometry* g) {
@@ -129,10 +133,22 @@ int make_geometry(const int64_t* lead_shape, int nlead, int mode, int64_t rank, 
     const int64_t j_per_cta = kThreads / rv > 0 ? kThreads / rv : 1;
     const int64_t ctas_per_split = g->B > 1 ? g->J : ceil_div(g->J, j_per_cta);
     int64_t s = ceil_div((int64_t)kNumSMs * 8, ctas_per_split);
-    if (s > g->A) s = g->A;
     if (s < 1) s = 1;
-    g->a_per_split = ceil_div(g->A, s);
-    g->splits = ceil_div(g->A, g->a_per_split);
+    int64_t sa = s > g->A ? g->A : s;
+    g->a_per_split = ceil_div(g->A, sa);
+    sa = ceil_div(g->A, g->a_per_split);
+    // still too few CTAs (a short outer range): split the inner range too, in pieces of at least 8 rows per lane
+    g->b_splits = 1;
+    g->b_per_split = g->B;
+    if (g->B > 1 && sa < s) {
+        const int64_t lanes = kThreads / rv > 0 ? kThreads / rv : 1;
+        int64_t sb = ceil_div(s, sa);
+        const int64_t sb_max = g->B / (lanes * 8) > 0 ? g->B / (lanes * 8) : 1;
+        if (sb > sb_max) sb = sb_max;
+        g->b_per_split = ceil_div(g->B, sb);
+        g->b_splits = ceil_div(g->B, g->b_per_split);
+    }
+    g->splits = sa * g->b_splits;
     return TLB200_OK;
 }
 
@@ -152,8 +168,8 @@ int launch(const T* t, const Geometry& g, int R, const T* P, const T* Q, T* dst,
     if (g.B > 1) {
         const size_t smem = sizeof(T) * VW * (size_t)(kThreads / RV) * RV;
         dim3 grid((unsigned)g.J, (unsigned)g.splits);
-        from_ttm_inner_kernel<T, VW><<<grid, kThreads, smem, stream>>>(t, g.A, g.J, g.B, R, P, Q, g.a_per_split, dst, dst_ld,
-                                                                        dst_split);
+        from_ttm_inner_kernel<T, VW><<<grid, kThreads, smem, stream>>>(t, g.A, g.J, g.B, R, P, Q, g.a_per_split, (int)g.b_splits,
+                                                                        g.b_per_split, dst, dst_ld, dst_split);
     } else {
         const int njl = kThreads / RV;
         dim3 grid((unsigned)ceil_div(g.J, njl), (unsigned)g.splits);
