@@ -236,6 +236,7 @@ struct Cfg {
     // the two convert sets take alternate tiles: with an even ring every stage always belongs to the same set,
     // so a set observes every phase of the barriers it waits on (an odd ring would alias phase parities)
     static_assert(XS % 2 == 0, "X ring must be even");
+    static_assert(BS % KO == 0, "B ring must hold whole tiles");
     static_assert(SMEM + 1024 <= 227 * 1024, "smem budget");
 };
 
@@ -245,6 +246,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                  const __grid_constant__ CUtensorMap blo_map, const TcStreamParams p) {
     using C = Cfg<RP, XL>;
     constexpr int KS = C::KS, KO = C::KO, XS = C::XS, AS = C::AS, BS = C::BS;
+    constexpr bool kUnitRelease = RP == 64 && KO == 2;     // A-ring slots are handed back unit by unit
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* x_smem = smem + C::OFF_X;
@@ -339,37 +341,37 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 const TcItem t = tc_item(p, it);
                 const int nbc = t.bc1 - t.bc0;                  // tiles per `a` row of this item, KO units each
                 if (t.a1 <= t.a0 || nbc <= 0) continue;
-                int ug = 0;
+                int ug = 0;              // units already in the open accumulation group (a multiple of KO: GU % KO == 0)
+                const bool scaled = p.P != nullptr;
                 for (int a = t.a0; a < t.a1; ++a)
                 for (int j = 0; j < nbc; ++j, ++gt) {
+                    // Both issuers walk every tile; this part runs twice per issued tile on a single latency-bound
+                    // instruction stream (it was 1100 clk per own tile before it was pared down), so only the state
+                    // that must advance for the other issuer's tiles is touched before the `continue`.
                     const bool last_a = a + 1 == t.a1;
-                    const bool row_end = j + 1 == nbc;
-                    const bool cut = (last_a && row_end) || (p.P != nullptr && row_end);   // group may not continue past this tile
-                    const bool mine = (gt & 1u) == (uint32_t)mw;
-                    // group bookkeeping runs for every tile in both issuers; only the owner waits and issues
-                    bool first[KO], gend[KO];
-                    uint32_t dbuf[KO];
-#pragma unroll
-                    for (int u = 0; u < KO; ++u) {
-                        dbuf[u] = G & 1u;
-                        first[u] = ug == 0;
-                        if (mine && first[u] && G >= 2) mbar_wait(&d_empty[dbuf[u]], ((G >> 1) - 1) & 1u);
-                        gend[u] = (ug + 1 == GU) || (cut && u == KO - 1);
-                        if (gend[u]) { ++G; ug = 0; } else { ++ug; }
-                    }
-                    // one A barrier pair per tile: both units of a tile are stored and published together
+                    const bool cut = j + 1 == nbc && (last_a || scaled);     // the group may not continue past this tile
+                    const bool first = ug == 0;                              // this tile opens a group
+                    const bool gend = ug + KO == GU || cut;                  // ... closes it
+                    const uint32_t Gc = G;
+                    if (gend) { ++G; ug = 0; } else { ug += KO; }
                     const int as0 = ar.idx;
                     const uint32_t aph = ar.phase;
-                    Ring b0 = br;
-                    Ring b1 = br;
-                    if constexpr (KO == 2) b1.advance(BS);
-#pragma unroll
-                    for (int u = 0; u < KO; ++u) { ar.advance(AS); br.advance(BS); }
+                    ar.idx += KO;
+                    if (ar.idx == AS) { ar.idx = 0; ar.phase ^= 1u; }
+                    const Ring bs0 = br;                                      // streamed B: ring position of unit 0
+                    br.idx += KO;
+                    if (br.idx == BS) { br.idx = 0; br.phase ^= 1u; }
+                    if (((gt ^ (uint32_t)mw) & 1u) != 0) continue;            // the other issuer's tile
+                    TLB_TRACE(1 + 2 * mw, tri, 4);
+                    const uint32_t dbuf = Gc & 1u;
+                    if (first && Gc >= 2) mbar_wait(&d_empty[dbuf], ((Gc >> 1) - 1) & 1u);
+                    Ring b0 = bs0, b1 = bs0;
                     if (p.b_resident) {      // slot = position inside the item's b block, one phase per item
                         b0.idx = j * KO; b0.phase = (bphase >> b0.idx) & 1u;
                         b1.idx = j * KO + (KO - 1); b1.phase = (bphase >> b1.idx) & 1u;
+                    } else if constexpr (KO == 2) {
+                        b1.idx = bs0.idx + 1;                                 // BS is even: a tile never wraps inside
                     }
-                    if (!mine) continue;
                     TLB_TRACE(1 + 2 * mw, tri, 0);
                     // one overlapped wait per tile: the A tile and its B unit(s)
                     if constexpr (KO == 2) mbar_wait3(&a_full[as0], aph, &b_full[b0.idx], b0.phase, &b_full[b1.idx], b1.phase);
@@ -383,18 +385,24 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                         if (!(p.debug & 2)) {
 #pragma unroll
                             for (int u = 0; u < KO; ++u) {
-                                const uint32_t d1 = d_base + dbuf[u] * C::D_COLS;
+                                const uint32_t d1 = d_base + dbuf * C::D_COLS;
                                 const uint32_t d2 = d1 + RP;
                                 const uint32_t a_hi = a_base + (as0 + u) * C::A_COLS;       // a_lo = a_hi + 32
                                 const uint32_t blo = bdesc_lo0 + (u == 0 ? b0.idx : b1.idx) * (C::B_UNIT >> 4); // low descriptor word
                                 // first K step of a group overwrites the accumulators, everything else accumulates
-                                mma_ts_tf32(d1, a_hi, ((uint64_t)bdesc_hi << 32) | blo, idesc1, first[u] ? 0u : 1u);
+                                mma_ts_tf32(d1, a_hi, ((uint64_t)bdesc_hi << 32) | blo, idesc1, (first && u == 0) ? 0u : 1u);
                                 mma_ts_tf32_acc(d2, a_hi + 32, ((uint64_t)bdesc_hi << 32) | blo, idesc2);
 #pragma unroll
                                 for (int ks = 1; ks < 4; ++ks) {
                                     const uint64_t db = ((uint64_t)bdesc_hi << 32) | (blo + ks * 2);   // +32 bytes per K step
                                     mma_ts_tf32_acc(d1, a_hi + ks * 8, db, idesc1);
                                     mma_ts_tf32_acc(d2, a_hi + 32 + ks * 8, db, idesc2);
+                                }
+                                // rank 64: the A ring holds only two tiles (TMEM budget), so convert and MMA take turns on
+                                // a slot; releasing the first unit before the second one is issued lets the converters
+                                // refill it while the second unit's MMAs execute (measured cycle per slot 2200 -> 1800 clk)
+                                if constexpr (kUnitRelease) {
+                                    if (u == 0) tc_commit(&a_empty[as0]);
                                 }
                             }
                         }
@@ -405,10 +413,9 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                             tc_commit(&b_empty[b0.idx]);
                             if constexpr (KO == 2) tc_commit(&b_empty[b1.idx]);
                         }
-                        tc_commit(&a_empty[as0]);
-#pragma unroll
-                        for (int u = 0; u < KO; ++u)
-                            if (gend[u]) tc_commit(&d_full[dbuf[u]]);
+                        if (kUnitRelease && (p.debug & 2)) tc_commit(&a_empty[as0]);      // perf triage: MMAs skipped
+                        tc_commit(&a_empty[kUnitRelease ? as0 + KO - 1 : as0]);
+                        if (gend) tc_commit(&d_full[dbuf]);
                     }
                     __syncwarp();
                     TLB_TRACE(1 + 2 * mw, tri, 3); ++tri;
@@ -511,7 +518,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 for (int u = 0; u < KO; ++u) {
                     const uint32_t gu = gc * KO + u;                      // global unit index
                     const int as = (int)(gu % AS);
-                    if (u == 0) {                                         // one barrier pair per tile (slot of unit 0)
+                    if (u == 0 || kUnitRelease) {                         // one release per tile (slot of unit 0) or per unit
                         mbar_wait(&a_empty[as], ((gu / AS) & 1u) ^ 1u);
                         tc_fence_after();
                     }
