@@ -256,6 +256,43 @@ def test_mttkrp_argument_conventions():
         tb.unfolding_dot_khatri_rao(xd, (None, [f.double() for f in fcm]), 0)
 
 
+def test_mttkrp_edge_cases():
+    """Ragged / degenerate inputs: storage that TMA cannot describe (falls back to the SIMT kernel under AUTO and
+    refuses under a forced tcgen05 path), rank 1, unit extents, extents far from any tile size."""
+    rng = np.random.RandomState(11)
+    # a contiguous tensor whose storage starts 4 bytes off a 16-byte boundary
+    shape, rank = (128, 64, 96), 32
+    flat = torch.empty(int(np.prod(shape)) + 1, dtype=torch.float32, device="cuda")
+    x = rng.random_sample(shape).astype(np.float32)
+    xd = flat[1:].view(shape)
+    xd.copy_(dev(x))
+    assert xd.data_ptr() % 16 == 4 and xd.is_contiguous()
+    fs = [rng.random_sample((s, rank)).astype(np.float32) for s in shape]
+    fd = [dev(f) for f in fs]
+    for mode in range(3):
+        out = host(tb.unfolding_dot_khatri_rao(xd, (None, fd), mode))
+        assert tb.last_kernel_path() == "simt"
+        assert rel_fro(out, O.unfolding_dot_khatri_rao(x, (None, fs), mode)) <= 1e-5
+    tb.set_kernel_path("tcgen05")
+    with pytest.raises(RuntimeError):
+        tb.unfolding_dot_khatri_rao(xd, (None, fd), 0)
+    tb.set_kernel_path("auto")
+    # the same tensor, aligned: tensor cores
+    tb.unfolding_dot_khatri_rao(dev(x), (None, fd), 0)
+    assert tb.last_kernel_path() == "tcgen05"
+    # rank 1, unit extents, primes
+    for shp, r in (((64, 48, 80), 1), ((1, 37, 41), 3), ((37, 1, 41), 3), ((37, 41, 1), 3), ((7, 11, 13, 5), 2), ((2, 3), 1)):
+        for dtype in (np.float32, np.float64):
+            xx = rng.standard_normal(shp).astype(dtype)
+            ff = [rng.standard_normal((s_, r)).astype(dtype) for s_ in shp]
+            ww = (rng.random_sample(r) + 0.5).astype(dtype)
+            for mode in range(len(shp)):
+                got = host(tb.unfolding_dot_khatri_rao(dev(xx), (dev(ww), [dev(f) for f in ff]), mode))
+                ref = O.unfolding_dot_khatri_rao(xx, (ww, ff), mode)
+                assert got.shape == ref.shape
+                assert rel_fro(got, ref) <= TOL[np.dtype(dtype)] * 4, (shp, r, mode)
+
+
 # --------------------------------------------------------------------------- mode_dot / multi_mode_dot
 @pytest.mark.parametrize("path", PATHS)
 def test_mode_dot_golden(golden, path):
