@@ -55,6 +55,76 @@ khatri_rao_kernel(KrArgs<T> a, int64_t total_rows, int64_t rank, int64_t pad_col
     }
 }
 
+// Large outputs: the row of the result with prefix index p (all matrices but the last, last fastest) and index il
+// of the last matrix is  pre[p, :] * F_last[il, :]  where pre = the left fold over the first nmats-1 matrices —
+// exactly the reference's association.  A CTA computes PB prefix rows once into shared memory and then streams
+// PB x LB output rows: per 16 bytes written one shared-memory load, VW rounded multiplies and one vector store,
+// instead of an index decomposition with 64-bit divisions per element.  Threads run along the columns first, so
+// every warp writes whole contiguous 512-byte pieces.
+template <typename T, int VW>
+struct alignas(sizeof(T) * VW) KrVec {
+    T v[VW];
+};
+
+template <typename T, int VW>
+__global__ void __launch_bounds__(256)
+khatri_rao_fast_kernel(KrArgs<T> a, int64_t prefix_rows, int64_t last_rows, int rank, int PB, int64_t LB,
+                       const T* __restrict__ weights, const T* __restrict__ mask, T* __restrict__ out, int64_t out_ld) {
+    extern __shared__ __align__(16) unsigned char kr_smem[];
+    T* pre = reinterpret_cast<T*>(kr_smem);          // [PB][rank]
+    using V = KrVec<T, VW>;
+    const int tid = threadIdx.x;
+    const int64_t p0 = (int64_t)blockIdx.x * PB;
+    const int npb = (int)min((int64_t)PB, prefix_rows - p0);
+    const int last = a.nmats - 1;
+    for (int e = tid; e < npb * rank; e += 256) {
+        const int pb = e / rank, c = e - pb * rank;
+        int64_t rem = p0 + pb;
+        int64_t idx[TLB200_MAX_NDIM];
+#pragma unroll
+        for (int i = TLB200_MAX_NDIM - 2; i >= 0; --i) {
+            if (i < last) {
+                const int64_t q = rem / a.rows[i];
+                idx[i] = rem - q * a.rows[i];
+                rem = q;
+            }
+        }
+        T v = a.mat[0][idx[0] * a.rs[0] + c * a.cs[0]];
+        if (weights) v = mul_rn(v, weights[c]);
+#pragma unroll
+        for (int i = 1; i < TLB200_MAX_NDIM - 1; ++i)
+            if (i < last) v = mul_rn(v, a.mat[i][idx[i] * a.rs[i] + c * a.cs[i]]);
+        pre[pb * rank + c] = v;
+    }
+    __syncthreads();
+    const int RV = rank / VW, NR = 256 / RV;
+    const int rv = tid % RV, rl = tid / RV;
+    if (rl >= NR) return;
+    const T* fl_base = a.mat[last];
+    const int64_t frs = a.rs[last], fcs = a.cs[last];
+    const int64_t l_begin = (int64_t)blockIdx.y * LB;
+    const int64_t l_end = min(last_rows, l_begin + LB);
+    for (int64_t il = l_begin + rl; il < l_end; il += NR) {
+        T fl[VW];
+#pragma unroll
+        for (int c = 0; c < VW; ++c) fl[c] = fl_base[il * frs + (int64_t)(rv * VW + c) * fcs];
+#pragma unroll 4
+        for (int pb = 0; pb < npb; ++pb) {
+            const int64_t row = (p0 + pb) * last_rows + il;
+            const V pv = *reinterpret_cast<const V*>(pre + pb * rank + rv * VW);
+            V o;
+#pragma unroll
+            for (int c = 0; c < VW; ++c) o.v[c] = mul_rn(pv.v[c], fl[c]);
+            if (mask) {
+                const T mk = mask[row];
+#pragma unroll
+                for (int c = 0; c < VW; ++c) o.v[c] = mul_rn(o.v[c], mk);
+            }
+            *reinterpret_cast<V*>(out + row * out_ld + rv * VW) = o;
+        }
+    }
+}
+
 // Transposed, zero-padded variant for the tcgen05 engine: out[c * out_ld + row] for row < rows_padded
 // (rows >= total_rows and columns >= rank are written as zero); with out_lo the value is split into its
 // tf32 truncation (out) and the exact remainder (out_lo).  blockDim = (32, 8): x runs over rows
@@ -140,6 +210,24 @@ int launch_khatri_rao(const T* const* mats, const int64_t* rows, const int64_t* 
     }
     for (int i = nmats; i < TLB200_MAX_NDIM; ++i) { a.mat[i] = nullptr; a.rows[i] = 1; a.rs[i] = 0; a.cs[i] = 0; }
     if (total == 0 || pad_cols == 0) return TLB200_OK;
+    {   // streaming kernel for large, vectorisable outputs (everything the public khatri_rao is used for at scale)
+        constexpr int VW = sizeof(T) == 4 ? 4 : 2;
+        const int64_t last_rows = rows[nmats - 1];
+        if (nmats >= 2 && pad_cols == rank && rank % VW == 0 && rank / VW <= 256 && out_ld % VW == 0 &&
+            reinterpret_cast<uintptr_t>(out) % 16 == 0 && last_rows >= 16 && total >= 4096 && last_rows > 0) {
+            const int64_t prefix_rows = total / last_rows;
+            const int PB = 8;
+            const int64_t LB = 512;
+            const int64_t gx = ceil_div(prefix_rows, PB), gy = ceil_div(last_rows, LB);
+            if (gx <= 0x7fffffffLL && gy <= 65535) {
+                const size_t smem = sizeof(T) * PB * (size_t)rank;
+                khatri_rao_fast_kernel<T, VW><<<dim3((unsigned)gx, (unsigned)gy), 256, smem, stream>>>(
+                    a, prefix_rows, last_rows, (int)rank, PB, LB, weights, mask, out, out_ld);
+                TLB_CHECK_LAUNCH();
+                return TLB200_OK;
+            }
+        }
+    }
     int64_t blocks = ceil_div(total, 8);
     if (blocks > (int64_t)kNumSMs * 64) blocks = (int64_t)kNumSMs * 64;
     khatri_rao_kernel<T><<<(unsigned)blocks, dim3(32, 8), 0, stream>>>(a, total, rank, pad_cols, weights, mask, out, out_ld);

@@ -60,6 +60,47 @@ swap01_tile_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t D0, in
     }
 }
 
+// ---- T == 1: plain 2-D transpose, 64 x 64 tiles through shared memory -------------------
+// in [D0][D1] -> out [D1][D0]; both sides move whole 128/256-byte row pieces.  One-dimensional grid (tiles of the
+// longer dimension can exceed the 65535 limit of grid.y).
+template <typename T>
+__global__ void __launch_bounds__(256)
+transpose64_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t D0, int64_t D1, int64_t tiles1) {
+    __shared__ T tile[64][65];
+    const int64_t b0 = blockIdx.x / tiles1, b1 = blockIdx.x - b0 * tiles1;
+    const int64_t d0_0 = b0 * 64, d1_0 = b1 * 64;
+    const int c = threadIdx.x & 63, r0 = threadIdx.x >> 6;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int r = r0 + 4 * k;
+        if (d0_0 + r < D0 && d1_0 + c < D1) tile[r][c] = __ldg(in + (d0_0 + r) * D1 + d1_0 + c);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int r = r0 + 4 * k;
+        if (d1_0 + r < D1 && d0_0 + c < D0) out[(d1_0 + r) * D0 + d0_0 + c] = tile[c][r];
+    }
+}
+
+// ---- medium inner runs (rows of 128 B .. 2 KB): 8 x 8 rows per CTA ------------------------
+// Copying row by row scatters 256-byte pieces on the write side (output rows of consecutive input rows are
+// D0*T apart).  A CTA that takes 8 values of d0 x 8 values of d1 reads 8 contiguous rows per d0 and writes 8
+// contiguous rows per d1: both sides see runs of 8 rows.  V = 16-byte vector.
+template <typename V>
+__global__ void __launch_bounds__(256)
+swap01_rowtile_kernel(const V* __restrict__ in, V* __restrict__ out, int64_t D0, int64_t D1, int Tv, int64_t tiles1) {
+    const int64_t b0 = blockIdx.x / tiles1, b1 = blockIdx.x - b0 * tiles1;
+    const int64_t d0_0 = b0 * 8, d1_0 = b1 * 8;
+    const int n0 = (int)min((int64_t)8, D0 - d0_0), n1 = (int)min((int64_t)8, D1 - d1_0);
+    const int per0 = n1 * Tv;                  // vectors per d0 (contiguous in the input)
+    for (int e = threadIdx.x; e < n0 * per0; e += 256) {
+        const int i0 = e / per0, q = e - i0 * per0;
+        const int i1 = q / Tv, v = q - i1 * Tv;
+        out[((d1_0 + i1) * D0 + d0_0 + i0) * Tv + v] = __ldg(in + ((d0_0 + i0) * D1 + d1_0) * Tv + q);
+    }
+}
+
 template <typename T>
 int swap01(const T* in, T* out, int64_t D0, int64_t D1, int64_t Tt, cudaStream_t stream) {
     if (D0 == 0 || D1 == 0 || Tt == 0) return TLB200_OK;
@@ -69,6 +110,23 @@ int swap01(const T* in, T* out, int64_t D0, int64_t D1, int64_t Tt, cudaStream_t
                 return TLB200_ECUDA;
         }
         return TLB200_OK;
+    }
+    if (Tt == 1) {
+        const int64_t tiles0 = ceil_div(D0, 64), tiles1 = ceil_div(D1, 64);
+        if (tiles0 * tiles1 > 0x7fffffffLL) return TLB200_EUNSUPPORTED;
+        transpose64_kernel<T><<<(unsigned)(tiles0 * tiles1), 256, 0, stream>>>(in, out, D0, D1, tiles1);
+        TLB_CHECK_LAUNCH();
+        return TLB200_OK;
+    }
+    if (Tt >= 32 && Tt * sizeof(T) < 2048 && (Tt * sizeof(T)) % 16 == 0 && reinterpret_cast<uintptr_t>(in) % 16 == 0 &&
+        reinterpret_cast<uintptr_t>(out) % 16 == 0) {
+        const int64_t tiles0 = ceil_div(D0, 8), tiles1 = ceil_div(D1, 8);
+        if (tiles0 * tiles1 <= 0x7fffffffLL) {
+            swap01_rowtile_kernel<int4><<<(unsigned)(tiles0 * tiles1), 256, 0, stream>>>(
+                reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out), D0, D1, (int)(Tt * sizeof(T) / 16), tiles1);
+            TLB_CHECK_LAUNCH();
+            return TLB200_OK;
+        }
     }
     if (Tt >= 32) {
         const int64_t nrows = D0 * D1;

@@ -90,7 +90,8 @@ def test_khatri_rao_golden_bit_exact(golden):
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_khatri_rao_bit_exact_vs_oracle(dtype):
     rng = np.random.RandomState(3)
-    for rows, rank in (((1024, 64), 32), ((17, 9, 33), 37), ((5, 4, 3, 2, 6), 5), ((300, 1, 7), 64), ((2, 2), 1)):
+    for rows, rank in (((1024, 64), 32), ((17, 9, 33), 37), ((5, 4, 3, 2, 6), 5), ((300, 1, 7), 64), ((2, 2), 1),
+                       ((40, 50, 37), 32), ((9, 700), 64), ((3, 5, 7, 600), 8), ((515, 19), 6), ((64, 64, 16), 128)):
         mats = [(rng.standard_normal((r, rank))).astype(dtype) for r in rows]
         w = rng.standard_normal(rank).astype(dtype)
         for weights in (None, w):
@@ -100,6 +101,10 @@ def test_khatri_rao_bit_exact_vs_oracle(dtype):
         strided = [dev(np.ascontiguousarray(m.T)).T for m in mats]
         assert not strided[0].is_contiguous() or strided[0].shape[1] == 1 or strided[0].shape[0] == 1
         assert np.array_equal(host(tb.khatri_rao(strided, weights=dev(w))), O.khatri_rao(mats, weights=w))
+        total = int(np.prod(rows))
+        mask = (rng.random_sample((total, 1)) > 0.3).astype(dtype) * dtype(1.5)
+        got = tb.khatri_rao([dev(m) for m in mats], weights=dev(w), mask=dev(mask))
+        assert np.array_equal(host(got), O.khatri_rao(mats, weights=w, mask=mask))
 
 
 def test_khatri_rao_reference_semantics():
