@@ -298,6 +298,106 @@ def test_mttkrp_edge_cases():
                 assert rel_fro(got, ref) <= TOL[np.dtype(dtype)] * 4, (shp, r, mode)
 
 
+# --------------------------------------------------------------------------- full-size properties (BASELINE configs)
+def _lowrank_tensor(shape, comps, gen):
+    """X = sum_q a_q o b_q o c_q (+ ...) built on the device, returned with its fp64 factor vectors."""
+    vs = [torch.rand(s, comps, generator=gen, device="cuda", dtype=torch.float64) + 0.1 for s in shape]
+    letters = "ijkl"[:len(shape)]
+    x = torch.einsum(",".join(f"{c}q" for c in letters) + "->" + letters, *[v.float() for v in vs])
+    return x, vs
+
+
+def test_full_size_c2_properties():
+    """C2 (1024^3 fp32, rank 32) is far beyond what the CPU oracle can check directly, so use identities:
+    (i) a tensor with known CP structure has a closed-form MTTKRP (fp64), (ii) MTTKRP is additive over mode-0 slabs
+    (the multi-GPU partition), (iii) the dimension-tree MTTKRP equals the direct one, (iv) unfold/fold round-trip
+    bit-exactly and match torch's own permuting copy, (v) khatri_rao equals the broadcast product bit for bit."""
+    n, R = 1024, 32
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    x, vs = _lowrank_tensor((n, n, n), 3, gen)
+    x += 0.0                                                   # contiguous fp32 tensor, 4.3 GB
+    fs = [torch.rand(n, R, generator=gen, device="cuda") for _ in range(3)]
+    w = torch.rand(R, generator=gen, device="cuda") + 0.5
+    f64 = [f.double() for f in fs]
+    vs32 = [v.float().double() for v in vs]                   # the values that actually went into x
+    for mode in range(3):
+        others = [m for m in range(3) if m != mode]
+        # M[i, r] = w_r * sum_q v_mode[i, q] * prod_{m != mode} (v_m[:, q] . F_m[:, r])
+        inner = torch.ones(3, R, dtype=torch.float64, device="cuda")
+        for m in others:
+            inner = inner * (vs32[m].T @ f64[m])
+        truth = (vs32[mode] @ inner) * w.double()[None, :]
+        got = tb.unfolding_dot_khatri_rao(x, (w, fs), mode)
+        assert tb.last_kernel_path() == "tcgen05"
+        # x itself carries one fp32 rounding per element (~6e-8 relative, averaged down by the sums)
+        err = float(torch.linalg.norm(got.double() - truth) / torch.linalg.norm(truth))
+        assert err <= 1e-5, (mode, err)
+        if mode > 0:                                           # additivity over mode-0 slabs
+            parts = sum(tb.unfolding_dot_khatri_rao(x[lo:lo + 256], (w, [fs[0][lo:lo + 256]] + fs[1:]), mode)
+                        for lo in range(0, n, 256))
+            assert float(torch.linalg.norm(parts.double() - truth) / torch.linalg.norm(truth)) <= 1e-5
+    t = tb.mode_dot(x, fs[2], 2, transpose=True)
+    for mode in range(2):
+        a = tb.mttkrp_from_ttm(t, (w, fs), mode)
+        b = tb.unfolding_dot_khatri_rao(x, (w, fs), mode)
+        assert float(torch.linalg.norm(a.double() - b.double()) / torch.linalg.norm(b.double())) <= 5e-6
+    del t
+    for mode in range(3):
+        u = tb.unfold(x, mode, contiguous=True)
+        assert torch.equal(u, x.movedim(mode, 0).reshape(n, -1))
+        assert torch.equal(tb.fold(u, mode, x.shape), x)
+        del u
+    kr = tb.khatri_rao(fs[:2], weights=w)
+    assert torch.equal(kr, ((fs[0] * w)[:, None, :] * fs[1][None, :, :]).reshape(-1, R))
+
+
+def test_full_size_c4_properties():
+    """C4 (256^4 fp32, rank 64, 17 GB): closed-form MTTKRP of a structured tensor for all four modes (the 4-way
+    P/Q table split, rank-64 engine) and the dimension-tree path."""
+    n, R = 256, 64
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs ~40 GB of free device memory")
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    x, vs = _lowrank_tensor((n, n, n, n), 2, gen)
+    fs = [torch.rand(n, R, generator=gen, device="cuda") for _ in range(4)]
+    w = torch.rand(R, generator=gen, device="cuda") + 0.5
+    f64 = [f.double() for f in fs]
+    vs32 = [v.float().double() for v in vs]
+    t = tb.mode_dot(x, fs[3], 3, transpose=True)
+    for mode in range(4):
+        inner = torch.ones(2, R, dtype=torch.float64, device="cuda")
+        for m in range(4):
+            if m != mode:
+                inner = inner * (vs32[m].T @ f64[m])
+        truth = (vs32[mode] @ inner) * w.double()[None, :]
+        got = tb.unfolding_dot_khatri_rao(x, (w, fs), mode)
+        assert tb.last_kernel_path() == "tcgen05"
+        assert float(torch.linalg.norm(got.double() - truth) / torch.linalg.norm(truth)) <= 1e-5, mode
+        if mode < 3:
+            got = tb.mttkrp_from_ttm(t, (w, fs), mode)
+            assert float(torch.linalg.norm(got.double() - truth) / torch.linalg.norm(truth)) <= 1e-5, mode
+
+
+def test_full_size_c3_ttm_properties():
+    """C3 (512^3 fp32, ranks 64): the HOOI projection of a tensor with known CP structure has a closed form."""
+    n, J = 512, 64
+    gen = torch.Generator(device="cuda").manual_seed(8)
+    x, vs = _lowrank_tensor((n, n, n), 4, gen)
+    us = [torch.randn(n, J, generator=gen, device="cuda").t().contiguous().t() for _ in range(3)]   # column-major, as HOOI passes them
+    vs32 = [v.float().double() for v in vs]
+    proj = [u.double().T @ v for u, v in zip(us, vs32)]                     # (J, comps)
+    truth = torch.einsum("aq,bq,cq->abc", *proj)
+    got = tb.multi_mode_dot(x, us, transpose=True)
+    assert tb.last_kernel_path() == "tcgen05"
+    assert float(torch.linalg.norm(got.double() - truth) / torch.linalg.norm(truth)) <= 1e-5
+    for skip in range(3):
+        got = tb.multi_mode_dot(x, us, skip=skip, transpose=True)
+        ops = [vs32[m] if m == skip else proj[m] for m in range(3)]
+        truth = torch.einsum("aq,bq,cq->abc", *ops)
+        assert float(torch.linalg.norm(got.double() - truth) / torch.linalg.norm(truth)) <= 1e-5
+
+
 # --------------------------------------------------------------------------- mode_dot / multi_mode_dot
 @pytest.mark.parametrize("path", PATHS)
 def test_mode_dot_golden(golden, path):
