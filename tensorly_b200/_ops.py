@@ -251,6 +251,13 @@ def mttkrp_plan(shape: Sequence[int], mode: int, rank: int, dtype=torch.float32,
     return plan
 
 
+def _check_out(out, rows, rank, like):
+    _check_tensor(out, "out", like)
+    if tuple(out.shape) != (rows, rank) or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous ({rows}, {rank}) tensor")
+    return out
+
+
 def unfolding_dot_khatri_rao(tensor: torch.Tensor, cp_tensor, mode: int) -> torch.Tensor:
     """MTTKRP: dot(unfold(tensor, mode), khatri_rao(factors, weights, skip_matrix=mode))
     (tensorly/tenalg/core_tenalg/mttkrp.py:9-50) without materialising either operand.
@@ -258,6 +265,12 @@ def unfolding_dot_khatri_rao(tensor: torch.Tensor, cp_tensor, mode: int) -> torc
     `cp_tensor` is any 2-iterable `(weights | None, factors)`; factors may have arbitrary
     strides.  Returns a new (tensor.shape[mode], rank) tensor.
     """
+    return mttkrp(tensor, cp_tensor, mode)
+
+
+def mttkrp(tensor: torch.Tensor, cp_tensor, mode: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """unfolding_dot_khatri_rao with an optional preallocated contiguous result (rows, rank) — the reference
+    signature has no such argument, the drivers use it to place the result inside a packed all-reduce buffer."""
     _check_tensor(tensor, "tensor")
     weights, factors = cp_tensor
     factors = list(factors)
@@ -291,7 +304,8 @@ def unfolding_dot_khatri_rao(tensor: torch.Tensor, cp_tensor, mode: int) -> torc
         if w.numel() != rank:
             raise ValueError(f"weights has {w.numel()} entries but the factors have {rank} columns")
     x = tensor if tensor.is_contiguous() else tensor.contiguous()
-    out = torch.empty((x.shape[mode], rank), dtype=x.dtype, device=x.device)
+    out = (torch.empty((x.shape[mode], rank), dtype=x.dtype, device=x.device) if out is None
+           else _check_out(out, x.shape[mode], rank, x))
     if x.numel() == 0:
         return out.zero_()
     lib = _lib.load()
@@ -313,7 +327,7 @@ def unfolding_dot_khatri_rao(tensor: torch.Tensor, cp_tensor, mode: int) -> torc
     return out
 
 
-def mttkrp_from_ttm(contracted: torch.Tensor, cp_tensor, mode: int) -> torch.Tensor:
+def mttkrp_from_ttm(contracted: torch.Tensor, cp_tensor, mode: int, out: torch.Tensor | None = None) -> torch.Tensor:
     """MTTKRP of mode `mode` < N-1 from T = mode_dot(tensor, factors[N-1], N-1, transpose=True)
     (shape I_0 x .. x I_{N-2} x rank): equals unfolding_dot_khatri_rao(tensor, cp_tensor, mode) while
     factors[N-1] is unchanged, reading T (rank / I_{N-1} of the tensor) instead of the tensor.
@@ -342,7 +356,8 @@ def mttkrp_from_ttm(contracted: torch.Tensor, cp_tensor, mode: int) -> torch.Ten
         if w.numel() != rank:
             raise ValueError(f"weights has {w.numel()} entries but the factors have {rank} columns")
     t = contracted if contracted.is_contiguous() else contracted.contiguous()
-    out = torch.empty((t.shape[mode], rank), dtype=t.dtype, device=t.device)
+    out = (torch.empty((t.shape[mode], rank), dtype=t.dtype, device=t.device) if out is None
+           else _check_out(out, t.shape[mode], rank, t))
     if t.numel() == 0:
         return out.zero_()
     lib = _lib.load()

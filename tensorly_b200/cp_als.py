@@ -67,7 +67,7 @@ def _wrap(weights, factors):
 class CudaOps:
     """The product compute path: every call is a tlb200 kernel launch."""
 
-    mttkrp = staticmethod(_ops.unfolding_dot_khatri_rao)
+    mttkrp = staticmethod(_ops.mttkrp)
     mode_dot = staticmethod(_ops.mode_dot)
     mttkrp_from_ttm = staticmethod(_ops.mttkrp_from_ttm)   # dimension-tree reuse (see CPALS.dimtree)
     gram = staticmethod(_ops.gram)
@@ -156,6 +156,20 @@ class CPALS:
             dimtree = os.environ.get("TLB200_DIMTREE", "1") != "0"
         self.dimtree = bool(dimtree) and can
         self._contracted: Optional[torch.Tensor] = None
+        # Sharded runs: the Gram of the sharded mode's new rows (R x R partial) and the MTTKRP partial of the NEXT
+        # updated mode are both all-reduced before that mode's solve, so they travel in ONE collective: the Gram
+        # lives at the tail of a packed buffer whose head receives that MTTKRP (one sync point less per sweep).
+        self._pack = None
+        self._pack_mode = None
+        if self.comm.active and self.shard_mode in self.modes and getattr(self.ops, "packed_allreduce", True):
+            k = self.modes.index(self.shard_mode)
+            if k + 1 < len(self.modes):
+                pm = self.modes[k + 1]
+                rows = tensor_local.shape[pm]
+                self._pack = torch.empty(rows * self.rank + self.rank * self.rank, dtype=dt, device=dev)
+                self._pack_mode = pm
+                self._pack_m = self._pack[: rows * self.rank].view(rows, self.rank)
+                self.grams[self.shard_mode] = self._pack[rows * self.rank:].view(self.rank, self.rank)
         # ||X||^2 (all-reduced over slabs) and the initial Grams
         self.ops.sumsq(self.x, out=self.norm_x2)
         self.comm.all_reduce(self.norm_x2)
@@ -163,30 +177,34 @@ class CPALS:
             self._refresh_gram(n)
 
     # -- pieces ---------------------------------------------------------------------------
-    def _refresh_gram(self, n: int) -> None:
+    def _refresh_gram(self, n: int, defer: bool = False) -> None:
         self.ops.gram(self.factors[n], out=self.grams[n])
-        if self.shard_mode == n:
+        if self.shard_mode == n and not defer:
             self.comm.all_reduce(self.grams[n])
 
     def _update_mode(self, mode: int) -> None:
+        packed = self._pack is not None and mode == self._pack_mode
+        out = self._pack_m if packed else None
         if self._contracted is not None and mode < self.ndim - 1:
-            m = self.ops.mttkrp_from_ttm(self._contracted, (self.weights, self.factors), mode)
+            m = self.ops.mttkrp_from_ttm(self._contracted, (self.weights, self.factors), mode, out=out)
         else:
-            m = self.ops.mttkrp(self.x, (self.weights, self.factors), mode)
-        if self.shard_mode is not None and mode != self.shard_mode:
-            self.comm.all_reduce(m)          # partial sums over the slabs
+            m = self.ops.mttkrp(self.x, (self.weights, self.factors), mode, out=out)
+        if packed:
+            self.comm.all_reduce(self._pack)     # this mode's MTTKRP partial + the sharded mode's Gram partial
+        elif self.shard_mode is not None and mode != self.shard_mode:
+            self.comm.all_reduce(m)              # partial sums over the slabs
         if self.update == "ls" and getattr(self.ops, "fused_gram", False):
             # one launch: solve + Gram of the new rows (partial over this rank's rows when the mode is sharded)
             self.ops.cp_update(self.grams, mode, self.weights, m, self.l2_reg, out=self.factors[mode],
                                gram_out=self.grams[mode])
-            if self.shard_mode == mode:
-                self.comm.all_reduce(self.grams[mode])
+            if self.shard_mode == mode and self._pack is None:
+                self.comm.all_reduce(self.grams[mode])     # (packed: reduced together with the next mode's MTTKRP)
         else:
             if self.update == "ls":
                 self.ops.cp_update(self.grams, mode, self.weights, m, self.l2_reg, out=self.factors[mode])
             else:
                 self.ops.nncp_update(self.grams, mode, self.weights, m, self.factors[mode], self.eps)
-            self._refresh_gram(mode)
+            self._refresh_gram(mode, defer=self._pack is not None)   # packed: reduced with the next mode's MTTKRP
         self.mttkrp_last = m
 
     def _error(self) -> None:

@@ -27,16 +27,17 @@ class OracleOps:
     supports_graphs = False
 
     @staticmethod
-    def mttkrp(x, cp, mode):
+    def mttkrp(x, cp, mode, out=None):
         w, fs = cp
-        return torch.from_numpy(np.ascontiguousarray(O.unfolding_dot_khatri_rao(_np(x), (_np(w), [_np(f) for f in fs]), mode)))
+        m = torch.from_numpy(np.ascontiguousarray(O.unfolding_dot_khatri_rao(_np(x), (_np(w), [_np(f) for f in fs]), mode)))
+        return m if out is None else out.copy_(m)
 
     @staticmethod
     def mode_dot(x, m, mode, transpose=False):
         return torch.from_numpy(np.ascontiguousarray(O.mode_dot(_np(x), _np(m), mode, transpose=transpose)))
 
     @staticmethod
-    def mttkrp_from_ttm(t, cp, mode):
+    def mttkrp_from_ttm(t, cp, mode, out=None):
         """MTTKRP of a mode before the last from T = X x_last F_last^T: the same sum, written as an einsum
         over T (leading modes i_0..i_{N-2}, trailing r) and the other leading factors."""
         w, fs = cp
@@ -48,10 +49,11 @@ class OracleOps:
             if i != mode:
                 operands.append(_np(fs[i]))
                 subs.append(letters[i] + "r")
-        out = np.einsum(",".join(subs) + "->" + letters[mode] + "r", *operands)
+        res = np.einsum(",".join(subs) + "->" + letters[mode] + "r", *operands)
         if w is not None:
-            out = out * _np(w)[None, :]
-        return torch.from_numpy(np.ascontiguousarray(out.astype(t.dtype)))
+            res = res * _np(w)[None, :]
+        res = torch.from_numpy(np.ascontiguousarray(res.astype(t.dtype)))
+        return res if out is None else out.copy_(res)
 
     @staticmethod
     def gram(f, out=None):

@@ -37,6 +37,13 @@ def _worker(rank, world, port, shape, cp_rank, shard_mode, update, iters, ret):
         from oracle import oracle as O
         from oracle_ops import OracleOps
 
+        calls = [0]
+        real_all_reduce = dist.all_reduce
+
+        def counting_all_reduce(*a, **k):
+            calls[0] += 1
+            return real_all_reduce(*a, **k)
+        dist.all_reduce = counting_all_reduce
         x = O.random_tensor(shape, 0)
         w, fs = O.random_cp_factors(shape, cp_rank, 1)
         lo, hi = tb.shard_bounds(shape[shard_mode], world, rank)
@@ -55,18 +62,20 @@ def _worker(rank, world, port, shape, cp_rank, shard_mode, update, iters, ret):
         err_dev = float(np.max(np.abs(np.array(errs) - np.array(ref_e)) / np.array(ref_e)))
         fac_dev = max(float(np.linalg.norm(a.numpy() - b) / np.linalg.norm(b)) for a, b in zip(cp[1], ref_f))
         shapes_ok = all(tuple(a.shape) == b.shape for a, b in zip(cp[1], ref_f))
-        ret[rank] = (err_dev, fac_dev, shapes_ok, len(errs))
+        ret[rank] = (err_dev, fac_dev, shapes_ok, len(errs), calls[0])
     finally:
         dist.destroy_process_group()
 
 
-def _run(shape, cp_rank, shard_mode, update="ls", iters=4, world=2):
+def _run(shape, cp_rank, shard_mode, update="ls", iters=4, world=2, all_reduces=None):
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), shape, cp_rank, shard_mode, update, iters, ret), nprocs=world, join=True)
     assert len(ret) == world
     for r in range(world):
-        err_dev, fac_dev, shapes_ok, n = ret[r]
+        err_dev, fac_dev, shapes_ok, n, n_all_reduce = ret[r]
+        if all_reduces is not None:
+            assert n_all_reduce == all_reduces, (r, n_all_reduce)
         assert shapes_ok and n == iters
         assert err_dev <= 1e-9, (r, err_dev)
         assert fac_dev <= 1e-7, (r, fac_dev)
@@ -74,7 +83,9 @@ def _run(shape, cp_rank, shard_mode, update="ls", iters=4, world=2):
 
 @pytest.mark.timeout(300)
 def test_sharded_parafac_mode0_matches_single_process():
-    _run((12, 9, 10), 3, shard_mode=0)
+    # collectives: ||X||^2 + the initial Gram of the sharded mode, then per sweep ONE packed all-reduce (mode-0 Gram
+    # partial + mode-1 MTTKRP partial) and one for the mode-2 MTTKRP: 2 + 4 * 2
+    _run((12, 9, 10), 3, shard_mode=0, all_reduces=10)
 
 
 @pytest.mark.timeout(300)
@@ -85,7 +96,9 @@ def test_sharded_parafac_uneven_slabs_and_middle_mode():
 
 @pytest.mark.timeout(300)
 def test_sharded_parafac_last_mode_and_four_way():
-    _run((5, 6, 9), 2, shard_mode=2)         # iprod is a partial sum -> extra all_reduce
+    # last mode sharded: nothing follows it inside a sweep, so its Gram travels alone, and iprod is a partial sum:
+    # 2 + 4 * (M0, M1, Gram, iprod)
+    _run((5, 6, 9), 2, shard_mode=2, all_reduces=18)
     _run((4, 5, 6, 7), 3, shard_mode=0)
 
 
