@@ -32,14 +32,17 @@
 // 6.8 TB/s vs 4.5 TB/s for one line per row on rows that are megabytes apart).
 //
 // Warp roles (16 warps, 1 CTA per SM, persistent over work items):
-//   warp 0       TMA producer of X tiles (ring of XS stages)
-//   warp 1       MMA issuer (one elected lane)
+//   warp 0       TMA producer of X tiles (ring of XS stages, XS even)
+//   warps 1, 11  MMA issuers (one elected lane each): they take alternate tiles and pass a turn token, so one
+//                polls the barriers of the next tile while the other's MMAs execute; their per-tile bookkeeping
+//                is kept minimal (they share a scheduler with two convert warps and an epilogue warp)
 //   warps 2-9    convert: smem X tile -> registers -> hi/lo -> TMEM A ring; two sets of four
 //                warps (one warp per TMEM lane quarter) take alternate tiles, which hides the
 //                barrier/LDS/tcgen05.st latencies of one tile behind the other
-//   warp 10      B producer: TMA loads of the pre-split (tf32 hi / lo) small operand — the
-//                factor matrix of a TTM, or the inner Khatri-Rao table Q of an MTTKRP — K-major
-//                SWIZZLE_128B, one 32-element unit at a time (warp 11 is idle)
+//   warp 10      B producer: TMA loads of the pre-split (tf32 hi / lo) small operand, K-major SWIZZLE_128B,
+//                one 32-element unit at a time.  MTTKRP (b_resident): the work item's block of the inner
+//                Khatri-Rao table Q is loaded ONCE and stays in shared memory while the item streams its `a`
+//                range; TTM: the factor matrix is streamed with the tiles through the same slots as a ring.
 //   warps 12-15  epilogue: drain TMEM accumulation groups, write C.  For MTTKRP the Khatri-Rao
 //                row is P[a,:] * Q[b,:]: the tensor core contracts with Q only and the epilogue
 //                scales each drained group by P[a,:] (groups never straddle an `a` boundary), so
