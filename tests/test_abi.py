@@ -90,6 +90,28 @@ def test_c_abi_validates_before_launching():
     assert lib.tlb200_gram_workspace_bytes(100, 8, _lib.F64) >= 8 * 8 * 8
     st = lib.tlb200_mode_dot(None, shape, 3, 0, None, 3, 1, 1, _lib.F32, None, None, 0, _lib.PATH_AUTO, None)
     assert st == _lib.TLB200_EINVAL
+    # dimension-tree MTTKRP: lead_shape = the first N-1 extents; only modes < N-1 exist; >= 3-way problems only
+    lead = _lib.i64_array((4, 5))
+    assert lib.tlb200_mttkrp_from_ttm_workspace_bytes(lead, 2, 0, 8, _lib.F32) > 0
+    assert lib.tlb200_mttkrp_from_ttm_workspace_bytes(lead, 2, 2, 8, _lib.F32) == 0
+    assert lib.tlb200_mttkrp_from_ttm_workspace_bytes(lead, 1, 0, 8, _lib.F32) == 0
+    st = lib.tlb200_mttkrp_from_ttm(None, lead, 2, 0, None, None, None, 8, None, _lib.F32, None, 8, None, 0, None)
+    assert st == _lib.TLB200_EINVAL
+    # fused update + Gram: 256 bytes for the ticket counter + one R x R partial per 64 rows
+    assert lib.tlb200_cp_update_gram_workspace_bytes(1024, 32, _lib.F32) >= 256 + 16 * 32 * 32 * 4
+    assert lib.tlb200_cp_update_gram_workspace_bytes(-1, 32, _lib.F32) == 0
+    st = lib.tlb200_cp_update_gram(None, 3, 0, 8, None, 0.0, None, 8, 10, _lib.F32, None, 8, None, None, 0, None)
+    assert st == _lib.TLB200_EINVAL
+
+
+def test_plan_reports_column_block_passes_field():
+    """rank_passes is part of the plan struct: 1 on the SIMT path (all a GPU-less box can plan), ceil(rank / 64)
+    column blocks when the tcgen05 engine is available."""
+    import tensorly_b200 as tb
+    pl = tb.mttkrp_plan((64, 48, 80), 1, 100)
+    assert pl.rank_passes == (2 if pl.path == _lib.PATH_TCGEN05 else 1)
+    assert pl.A * pl.J * pl.B == 64 * 48 * 80
+    assert tb.mttkrp_plan((64, 48, 80), 1, 100, path="simt").rank_passes == 1
 
 
 def test_host_mirror_refuses_cpu_tensors_loudly():
