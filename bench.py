@@ -2,18 +2,30 @@
 """bench.py — CP-ALS sweeps/s and MTTKRP HBM GB/s on B200 (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload c2|c5|c1|small] [--no-e2e]
+                    [--workload c5|c2|c1|small] [--no-e2e] [--no-c2] [--no-cpu] ...
 
-A "step" is one CP-ALS sweep (all modes updated + reconstruction error) of the workload:
-  c2 (default): parafac rank 32 on random 1024^3 fp32  (BASELINE configs[1])
-  c5          : parafac rank 64 on random 2048^3 fp32  (BASELINE configs[4])
-At N > 1 the SAME tensor is sharded along mode 0 over the N ranks (strong scaling); the
-per-mode exchanges are NCCL all-reduces of the small MTTKRP / Gram partials.
+A "step" is one CP-ALS sweep (all modes updated + reconstruction error) of the workload.
+The headline workload is the same at EVERY N so that the driver can compute scaling from
+the per-N values:
 
-One JSON line is printed by rank 0 (see DESIGN.md §Measurement for every key).
-`--impl reference` times the reference's own CPU implementation (unmodified TensorLy on
-its numpy backend when importable from baseline/_ref, else the oracle port) on a bounded
-sample of the same workload.
+  c5 (default): parafac rank 64 on random 2048^3 fp32  (BASELINE configs[4], the config the
+                north star's 8-GPU target is quoted on; 34.4 GB, fits one B200).  At N > 1 the
+                SAME tensor (generated block by block from fixed seeds) is sharded along mode 0
+                over the N ranks: strong scaling.
+  c2 block    : parafac rank 32 on random 1024^3 fp32  (BASELINE configs[1]) runs in the same
+                process as a secondary block `c2` with its own value, roofline and — at N = 1 —
+                its own CPU baseline measured on the REAL 1024^3 shape.
+
+One JSON line is printed by rank 0 (DESIGN.md "Measurement" explains every key).
+
+`--impl reference` times the UNMODIFIED reference (TensorLy from baseline/_ref, numpy backend,
+`core` tenalg; the oracle port only if TensorLy is not importable) on the host cores, with every
+host thread, on the same config: real sweeps of the real shape, each sweep time-stamped through the
+reference's own `verbose` prints.  K and W are honoured as far as a wall-clock budget allows
+(`--ref-budget-s`, default 150 s): the line's `steps` / `warmup` are the sweeps that were actually
+timed, so ms_per_step x steps is real time.  Only when the host cannot hold the reference's
+temporaries (C5 needs ~3.2x the 34 GB tensor) a mode-0 slab is timed instead and labelled
+`extrapolated`.
 """
 from __future__ import annotations
 
@@ -41,6 +53,37 @@ WORKLOADS = {
 }
 METRIC = "CP-ALS sweeps/s (MTTKRP HBM GB/s in roofline)"
 UNIT = "sweeps/s"
+PARITY_SHAPE, PARITY_RANK, PARITY_SWEEPS = (384, 320, 256), 32, 6
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def host_mem_available_bytes() -> int:
+    """MemAvailable, capped by the cgroup limit when there is one."""
+    avail = None
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    avail = int(line.split()[1]) * 1024
+                    break
+    except Exception:
+        pass
+    for p, q in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                 ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            lim = open(p).read().strip()
+            if lim != "max" and int(lim) < (1 << 60):
+                room = int(lim) - int(open(q).read().strip())
+                avail = room if avail is None else min(avail, room)
+        except Exception:
+            pass
+    return avail if avail is not None else 0
 
 
 def measured_peak_hbm():
@@ -78,17 +121,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+    def mark(self):
+        return len(self.rows)
+
+    def summary(self, start=0, end=None):
         sm, smax, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[start:end]:
             parts = [p.strip() for p in r.split(",")]
             if len(parts) < 7:
                 continue
@@ -99,144 +138,260 @@ class ClockSampler:
             for n, v in zip(names, parts[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        # "under load": samples in the upper half of the observed power range
         if sm:
+            # "under load": samples in the upper half of the observed power range
             thr = (max(power) + min(power)) / 2 if power else 0
             loaded = [s for s, p in zip(sm, power) if p >= thr] or sm
             return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
                     "samples": len(sm), "power_w_max": max(power) if power else None}
         return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "samples": 0}
 
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        return self.summary()
 
-# ----------------------------------------------------------------------------------------
-def cpu_reference_sweeps(shape, rank, dtype, steps, warmup):
-    """Time the reference's CPU implementation (numpy backend, `core` tenalg) for
-    `steps` sweeps after `warmup`, fixed init, tol=0, errors evaluated.  Returns
-    (seconds_per_sweep, kind, threads)."""
-    import numpy as np
-    from oracle import oracle as O
-    x = O.random_tensor(shape, 0, np.dtype(dtype))
-    w, fs = O.random_cp_factors(shape, rank, 1, np.dtype(dtype))
+
+# ---------------------------------------------------------------------------------------- CPU reference
+def _full_threads():
+    """Context manager forcing BLAS/OpenMP pools to every host thread (torchrun exports OMP_NUM_THREADS=1)."""
+    n = host_threads()
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=n), n
+    except Exception:
+        import contextlib
+        return contextlib.nullcontext(), n
+
+
+def _blas_threads(default):
     try:
         from threadpoolctl import threadpool_info
-        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [os.cpu_count() or 1])
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [default])
     except Exception:
-        threads = os.cpu_count() or 1
-    kind = "port"
-    run = None
+        return default
+
+
+def host_tensor(shape, dtype, seed=0):
+    """uniform[0,1) like tl.random.random_tensor; generated with torch's CPU generator in mode-0 blocks (numpy's
+    RandomState would need an fp64 copy of the whole tensor: 69 GB at C5)."""
+    import numpy as np
+    import torch
+    tdt = torch.float32 if dtype == "float32" else torch.float64
+    x = torch.empty(shape, dtype=tdt)
+    g = torch.Generator().manual_seed(seed)
+    step = max(1, (1 << 28) // max(1, int(np.prod(shape[1:]))))
+    for lo in range(0, shape[0], step):
+        x[lo:lo + step].uniform_(0, 1, generator=g)
+    return x.numpy()
+
+
+class _StampingStdout:
+    """Time-stamps the reference's own `verbose` prints ("Starting iteration k", _cp.py:404-405): per-sweep wall
+    times of the unmodified driver without its `callback` hook (which would add a full cp_to_tensor
+    reconstruction — two more tensor-sized temporaries — at start-up, _cp.py:383-393)."""
+
+    def __init__(self):
+        self.stamps = []
+
+    def write(self, text):
+        if text.startswith("Starting iteration"):
+            self.stamps.append(time.perf_counter())
+        return len(text)
+
+    def flush(self):
+        pass
+
+
+def _reference_parafac_timed(x, rank, w, fs, n_iter):
+    """One call of the unmodified reference parafac for n_iter sweeps; returns the start time of every sweep plus
+    the end time, and which implementation ran."""
+    import contextlib
     try:
         from tensorly_b200.backend import import_tensorly
         tl = import_tensorly()
+    except ImportError:
+        tl = None
+    if tl is not None:
         tl.set_backend("numpy")
         tl.tenalg.set_backend("core")
         from tensorly.cp_tensor import CPTensor
         from tensorly.decomposition import parafac
+        init = CPTensor((w.copy(), [f.copy() for f in fs]))
+        out = _StampingStdout()
+        with contextlib.redirect_stdout(out):
+            parafac(x, rank, n_iter_max=n_iter, init=init, tol=0, return_errors=True, verbose=2)
+        return out.stamps + [time.perf_counter()], "reference"
+    # TensorLy not importable: the oracle port, one sweep per call from the running factors
+    from oracle import oracle as O
+    cur = (w.copy(), [f.copy() for f in fs])
+    stamps = []
+    for _ in range(n_iter):
+        stamps.append(time.perf_counter())
+        (wn, fn), _ = O.parafac(x, cur, n_iter_max=1)
+        cur = (wn, fn)
+    return stamps + [time.perf_counter()], "port"
 
-        def run(n):
-            init = CPTensor((w.copy(), [f.copy() for f in fs]))
-            t0 = time.perf_counter()
-            parafac(x, rank, n_iter_max=n, init=init, tol=0, return_errors=True)
-            return time.perf_counter() - t0
-        kind = "reference"
-    except Exception:
-        def run(n):
-            t0 = time.perf_counter()
-            O.parafac(x, (w, fs), n_iter_max=n)
-            return time.perf_counter() - t0
-    # sweeps/s = delta(iters)/delta(time) between two runs removes init + tl.norm (SURVEY §8d)
-    t_a = run(warmup)
-    t_b = run(warmup + steps)
-    per = max((t_b - t_a) / steps, 1e-9)
-    return per, kind, threads
+
+def cpu_reference_sweeps(shape, rank, dtype, steps, warmup, budget_s, min_steps=2):
+    """Sweeps of the reference's CPU CP-ALS (unmodified parafac, numpy backend, `core` tenalg, fixed init, tol=0,
+    errors evaluated) at `shape`, every host thread.  `warmup` untimed + `steps` timed sweeps when that fits the
+    wall-clock budget; otherwise fewer (at least 1 + `min_steps`), decided up front from a calibration sweep on a
+    thin mode-0 slab.  Returns (seconds_per_sweep, steps_timed, warmup_done, kind, threads)."""
+    import numpy as np
+    from oracle import oracle as O
+    ctx, nthreads = _full_threads()
+    with ctx:
+        t_begin = time.perf_counter()
+        x = host_tensor(shape, dtype, 0)
+        w, fs = O.random_cp_factors(shape, rank, 1, np.dtype(dtype))
+        threads = _blas_threads(nthreads)
+        inner = 1
+        for s in shape[1:]:
+            inner *= s
+        rows = max(1, min(shape[0], (1 << 27) // max(inner, 1)))
+        if rows < shape[0]:
+            st, _ = _reference_parafac_timed(np.ascontiguousarray(x[:rows]), rank, w, [fs[0][:rows]] + list(fs[1:]), 2)
+            est = (st[-1] - st[1]) * shape[0] / rows          # second sweep (the first one warms the BLAS pools)
+        else:
+            est = 0.0
+        left = budget_s - (time.perf_counter() - t_begin)
+        warm, timed = warmup, steps
+        if est * (warm + timed) > left:
+            total = max(1 + min_steps, int(left / max(est, 1e-9)))
+            warm, timed = 1, max(min_steps, min(steps, total - 1))
+        stamps, kind = _reference_parafac_timed(x, rank, w, fs, warm + timed)
+    per = (stamps[-1] - stamps[warm]) / timed
+    return per, timed, warm, kind, threads
+
+
+def reference_plan(shape, rank, dtype):
+    """The shape the CPU arm can really run: the workload's own shape when the reference's temporaries fit in
+    host memory (tensor + permuted unfolding copy + the |x|, x^2 temporaries of tl.norm ~ 3.2x the tensor), else
+    the largest mode-0 slab that does."""
+    esize = 4 if dtype == "float32" else 8
+    elems = 1
+    for s in shape:
+        elems *= s
+    need = 3.2 * esize * elems + (2 << 30)
+    avail = host_mem_available_bytes()
+    if avail <= 0 or need <= avail:
+        return tuple(shape), 1.0, avail
+    rows = shape[0]
+    while rows > 1 and 3.2 * esize * elems * rows / shape[0] + (2 << 30) > avail:
+        rows //= 2
+    return (rows,) + tuple(shape[1:]), rows / shape[0], avail
 
 
 def run_reference(args):
-    rank_env = int(os.environ.get("RANK", "0"))
-    if rank_env != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return 0
     wl = WORKLOADS[args.workload]
     shape, rank, dtype = wl["shape"], wl["rank"], wl["dtype"]
-    # bounded sample: the same problem at a sub-shape that a CPU sweeps in ~a second
-    sample = tuple(min(s, 512 if args.workload in ("c2", "c5") else s) for s in shape)
-    frac = 1.0
-    for a, b in zip(sample, shape):
-        frac *= a / b
-    steps = max(1, min(args.steps, 8))
-    warm = max(1, min(args.warmup, 2))
-    per, kind, threads = cpu_reference_sweeps(sample, rank, dtype, steps, warm)
-    value = frac / per     # MTTKRP cost is linear in the element count
+    sample, frac, avail = reference_plan(shape, rank, dtype)
+    per, steps, warm, kind, threads = cpu_reference_sweeps(sample, rank, dtype, args.steps, args.warmup, args.ref_budget_s)
+    extrapolated = frac != 1.0
+    value = frac / per          # slab sample: MTTKRP cost is linear in the slab's rows
+    what = (f"{steps} timed sweeps (after {warm} warm-up) of unmodified tensorly.decomposition.parafac "
+            f"(numpy backend, core tenalg) at shape {tuple(sample)} rank {rank} {dtype}, {threads} threads, "
+            f"per-sweep times from the time-stamped `verbose` prints of the driver")
+    if extrapolated:
+        what += (f"; EXTRAPOLATED: host memory ({avail / 2**30:.0f} GiB available) cannot hold the reference's "
+                 f"temporaries for {tuple(shape)}, so a mode-0 slab was timed and scaled by {frac:.4g}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": per / frac * 1e3, "higher_is_better": True, "scaling": "strong",
+        "warmup": warm, "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": per * 1e3 / frac, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32" if dtype == "float32" else "f64", "data": "synthetic",
-        "config": {"workload": wl["name"], "rank": rank, "shape": list(shape)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
-                         "sample": f"{steps} sweeps of the same CP-ALS at sub-shape {sample} (rank {rank}, {dtype}), "
-                                   f"scaled by the element ratio {frac:.6g}"},
+        "config": {"workload": wl["name"], "shape": list(shape), "rank": rank},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": what,
+                         "extrapolated": extrapolated, "measured_ms_per_sweep_at_sample": per * 1e3,
+                         "sample_shape": list(sample)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
     return 0
 
 
-# ----------------------------------------------------------------------------------------
-def run_ours(args):
+# ---------------------------------------------------------------------------------------- synthetic data
+def device_slab(shape, lo, hi, dtype, device, seed=0, block=64):
+    """Rows lo:hi (mode 0) of THE synthetic tensor: uniform[0,1) like tl.random.random_tensor, produced in mode-0
+    blocks of `block` rows, each from its own seeded device generator — the same tensor whatever the number of
+    ranks and wherever the slab boundaries fall."""
     import torch
-    import torch.distributed as dist
-    import tensorly_b200 as tb
-    from tensorly_b200.cp_als import CPALS, _Comm
+    x = torch.empty((hi - lo,) + tuple(shape[1:]), dtype=dtype, device=device)
+    g = torch.Generator(device=device)
+    for b in range(lo // block, (hi + block - 1) // block):
+        b0, b1 = b * block, min((b + 1) * block, shape[0])
+        g.manual_seed(seed * 1000003 + b)
+        blk = torch.rand((b1 - b0,) + tuple(shape[1:]), generator=g, dtype=dtype, device=device)
+        s0, s1 = max(b0, lo), min(b1, hi)
+        x[s0 - lo:s1 - lo] = blk[s0 - b0:s1 - b0]
+        del blk
+    return x
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank_id = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # the sharded sweep (MTTKRP + NCCL all-reduce + solve, 3 modes) is replayed from one CUDA graph;
-        # the graph is destroyed before the process group at the end (the reverse order hangs in teardown)
-        os.environ.setdefault("TLB200_DIST_GRAPH", "1")
-        dist.init_process_group("nccl", device_id=device)
-    wl = WORKLOADS[args.workload]
+
+def initial_factors(shape, rank, dtype, device, seed=1):
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    return [torch.rand((s, rank), generator=g, dtype=dtype, device=device) for s in shape]
+
+
+# ---------------------------------------------------------------------------------------- our arm
+class Env:
+    pass
+
+
+def timed_sweeps(env, state, steps, warmup):
+    """`steps` sweeps between barrier+synchronize brackets, CUDA events on the launching stream, max over ranks."""
+    import torch
+    for _ in range(warmup):
+        state.sweep(True)
+    env.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        state.sweep(True)
+    e1.record()
+    env.barrier()
+    return env.max_over_ranks(e0.elapsed_time(e1))
+
+
+def bench_workload(env, key, args, headline):
+    """All device-resident measurements of one workload: MTTKRP roofline leg, K timed sweeps, the N-pass variant,
+    the TTM pass that feeds the dimension tree, launches per sweep."""
+    import torch
+    import tensorly_b200 as tb
+    from tensorly_b200.cp_als import CPALS
+    wl = WORKLOADS[key]
     shape, R = wl["shape"], wl["rank"]
     dtype = torch.float32 if wl["dtype"] == "float32" else torch.float64
     esize = 4 if dtype == torch.float32 else 8
-    lo, hi = tb.shard_bounds(shape[0], world, rank_id)
+    lo, hi = tb.shard_bounds(shape[0], env.world, env.rank)
     local_shape = (hi - lo,) + tuple(shape[1:])
-
-    # synthetic data: uniform[0,1) like tl.random.random_tensor, generated on device
-    gen = torch.Generator(device=device).manual_seed(1234 + rank_id)
-    x = torch.rand(local_shape, generator=gen, dtype=dtype, device=device)
-    fgen = torch.Generator(device=device).manual_seed(1)
-    factors = [torch.rand((s, R), generator=fgen, dtype=dtype, device=device) for s in shape]
+    x = device_slab(shape, lo, hi, dtype, env.device, seed=0)
+    factors = initial_factors(shape, R, dtype, env.device)
     factors[0] = factors[0][lo:hi].contiguous()
-    weights = torch.ones(R, dtype=dtype, device=device)
-    comm = _Comm(None)
-    state = CPALS(x, weights, factors, comm=comm, shard_mode=0)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local)
-    if rank_id == 0:
-        sampler.start()
+    weights = torch.ones(R, dtype=dtype, device=env.device)
+    state = CPALS(x, weights, factors, comm=env.comm, shard_mode=0)
+    out = {"x": x, "weights": weights, "factors": factors, "state": state, "local_shape": local_shape, "esize": esize}
 
     # ---- roofline leg: the MTTKRP call per mode, timed with CUDA events on its stream -----
     elems_local = 1
     for s in local_shape:
         elems_local *= s
     alg_bytes = esize * (elems_local + R * sum(local_shape))
-    mttkrp_ms = []
-    path_used = None
+    mttkrp_ms, path_used = [], None
+    reps = max(3, min(20, args.steps))
     for mode in range(len(shape)):
         for _ in range(3):
             tb.unfolding_dot_khatri_rao(x, (weights, state.factors), mode)
         path_used = tb.last_kernel_path()
-        reps = max(3, min(20, args.steps))
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
         torch.cuda.synchronize()
         ev[0].record()
@@ -248,51 +403,53 @@ def run_ours(args):
     avg_ms = statistics.mean(mttkrp_ms)
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak_hbm()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if env.world == 1 and os.path.exists(tp):      # the ncu capture is of the 1-GPU launch of this workload
+        try:
+            traffic = json.load(open(tp)).get(key, {}).get(path_used)
+        except Exception:
+            traffic = None
+    out["roofline"] = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "peak_source": peak_src, "kernel": f"MTTKRP ({path_used}), mean over the {len(shape)} modes, per call incl. "
+                                           "its prep and split-K reduce launches",
+        "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": avg_ms,
+        "per_mode_gbs": [alg_bytes / (m * 1e-3) / 1e9 for m in mttkrp_ms], "frac_of_nominal_8TBs": achieved / 8000.0,
+        "note": ("frac > 1: `peak` is the measured COPY bandwidth (read + write); a read-only stream like this one "
+                 "can exceed it — see frac_of_nominal_8TBs") if achieved > peak else None}
+    out["path"] = path_used
 
     # ---- launches per sweep (host-side count of one eager sweep) -------------------------
     c0 = tb.launch_count()
     state.sweep_eager(True)
-    launches_per_sweep = tb.launch_count() - c0
+    out["launches_per_sweep"] = int(tb.launch_count() - c0)
 
     # ---- timed region: K sweeps, inputs resident in HBM ----------------------------------
-    for _ in range(max(3, args.warmup)):
-        state.sweep(True)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        state.sweep(True)
-    e1.record()
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms.item())
-    value = args.steps / (total_ms * 1e-3)
-    rel_err = float(state.err[0].item())
+    mark0 = env.sampler.mark() if env.sampler else 0
+    total_ms = timed_sweeps(env, state, args.steps, max(3, args.warmup))
+    out["ms_per_step"] = total_ms / args.steps
+    out["value"] = args.steps / (total_ms * 1e-3)
+    out["rel_err"] = float(state.err[0].item())
+
+    # ---- sustained: the same sweeps for >= ~2 s (clocks settle under the power cap) --------
+    if not args.no_sustained:
+        n_long = int(min(2000, max(args.steps, 2000.0 / max(out["ms_per_step"], 1e-3))))
+        ms_long = timed_sweeps(env, state, n_long, 0)
+        out["sustained"] = {"value": n_long / (ms_long * 1e-3), "unit": UNIT, "steps": n_long,
+                            "ms_per_step": ms_long / n_long,
+                            "what": "same sweeps timed over a >= 2 s window (SM clocks settled under the power cap)"}
+    out["clock_marks"] = (mark0, env.sampler.mark() if env.sampler else 0)
 
     # ---- the same sweeps with one full MTTKRP per mode (N tensor passes, the reference's call pattern) ----
-    three_pass = None
-    ttm_pass = None
-    if state.dimtree:
-        st3 = CPALS(x, weights, factors, comm=comm, shard_mode=0, dimtree=False)
+    if state.dimtree and headline:
+        st3 = CPALS(x, weights, factors, comm=env.comm, shard_mode=0, dimtree=False)
         n3 = max(3, min(args.steps, 30))
-        for _ in range(3):
-            st3.sweep(True)
-        barrier()
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b0.record()
-        for _ in range(n3):
-            st3.sweep(True)
-        b1.record()
-        barrier()
-        ms3 = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
-        three_pass = {"value": n3 / (float(ms3.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(ms3.item()) / n3,
-                      "steps": n3, "final_rel_error": float(st3.err[0].item()),
-                      "what": "same sweeps with a full MTTKRP per mode (no dimension-tree reuse): the call pattern "
-                              "SURVEY 8(d)'s 12.89 GB/sweep model describes"}
+        ms3 = timed_sweeps(env, st3, n3, 3)
+        out["three_pass"] = {"value": n3 / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3 / n3, "steps": n3,
+                             "final_rel_error": float(st3.err[0].item()),
+                             "what": "same sweeps with a full MTTKRP per mode (no dimension-tree reuse): the call "
+                                     "pattern SURVEY 8(d)'s bytes/sweep model describes"}
         st3._graph = None
         del st3
         # the TTM pass that feeds the dimension tree (same tcgen05 engine): bytes = tensor read + T written
@@ -308,146 +465,343 @@ def run_ours(args):
         torch.cuda.synchronize()
         t_ms = c0_.elapsed_time(c1_) / 5
         t_bytes = esize * (elems_local + elems_local // local_shape[last] * R + R * local_shape[last])
-        ttm_pass = {"ms_per_launch": t_ms, "algorithmic_bytes_per_launch": t_bytes, "achieved": t_bytes / (t_ms * 1e-3) / 1e9,
-                    "unit": "GB/s", "kernel": f"mode_dot(X, F_last^T, last) ({tb.last_kernel_path()})"}
+        out["ttm_pass"] = {"ms_per_launch": t_ms, "algorithmic_bytes_per_launch": t_bytes,
+                           "achieved": t_bytes / (t_ms * 1e-3) / 1e9, "unit": "GB/s",
+                           "kernel": f"mode_dot(X, F_last^T, last) ({tb.last_kernel_path()})"}
+    return out
 
-    # ---- e2e: same sweep through the public API with HOST buffers ------------------------
-    e2e = None
-    if not args.no_e2e:
-        x_host = torch.empty(local_shape, dtype=dtype, pin_memory=True)
-        x_host.copy_(x)
-        f_host = [torch.empty(f.shape, dtype=dtype, pin_memory=True).copy_(f) for f in state.factors]
-        out_host = [torch.empty(f.shape, dtype=dtype, pin_memory=True) for f in state.factors]
-        err_host = torch.empty(3, dtype=dtype, pin_memory=True)
-        x_dev = torch.empty_like(x)
-        e2e_steps = max(2, min(args.steps, 6))
 
-        def e2e_step():
-            x_dev.copy_(x_host, non_blocking=True)                        # H2D: the tensor
-            fs = [h.to(device, non_blocking=True) for h in f_host]        # H2D: current factors
-            st = CPALS(x_dev, weights, fs, comm=comm, shard_mode=0)       # ||X||^2 + Grams
-            st.sweep_eager(True)
-            for o, f in zip(out_host, st.factors):
-                o.copy_(f, non_blocking=True)                             # D2H: updated factors
-            err_host.copy_(st.err, non_blocking=True)                     # D2H: the error
-            torch.cuda.current_stream().synchronize()
+def e2e_leg(env, res, args):
+    """The same sweep through the public API with HOST buffers: per step the pinned-host slab and factors go to the
+    device, ||X||^2 + Grams + one full sweep run through tensorly_b200.CPALS, factors and error come back."""
+    import torch
+    from tensorly_b200.cp_als import CPALS
+    x, state = res["x"], res["state"]
+    dtype, esize = x.dtype, res["esize"]
+    try:
+        x_host = torch.empty(x.shape, dtype=dtype, pin_memory=True)
+    except Exception as exc:
+        return {"unavailable": f"cannot pin {x.numel() * esize / 2**30:.1f} GiB of host memory: {str(exc)[:120]}"}
+    x_host.copy_(x)
+    f_host = [torch.empty(f.shape, dtype=dtype, pin_memory=True).copy_(f) for f in state.factors]
+    out_host = [torch.empty(f.shape, dtype=dtype, pin_memory=True) for f in state.factors]
+    err_host = torch.empty(3, dtype=dtype, pin_memory=True)
+    # the device copy of the step's input is the resident tensor's own buffer: every H2D copy overwrites it
+    x_dev = x
+    steps = max(2, min(args.steps, 6))
 
+    def step():
+        x_dev.copy_(x_host, non_blocking=True)                                 # H2D: the tensor slab
+        fs = [h.to(env.device, non_blocking=True) for h in f_host]             # H2D: current factors
+        st = CPALS(x_dev, res["weights"], fs, comm=env.comm, shard_mode=0)     # ||X||^2 + Grams
+        st.sweep_eager(True)
+        for o, f in zip(out_host, st.factors):
+            o.copy_(f, non_blocking=True)                                      # D2H: updated factors
+        err_host.copy_(st.err, non_blocking=True)                              # D2H: the error
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        step()
+    env.barrier()
+    t0 = time.perf_counter()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(steps):
+        step()
+    a1.record()
+    env.barrier()
+    secs = env.max_over_ranks(max(a0.elapsed_time(a1) * 1e-3, time.perf_counter() - t0))
+    R = state.rank
+    fbytes = esize * R * sum(res["local_shape"])
+    h2d = env.sum_over_ranks(esize * x.numel() + fbytes)
+    d2h = env.sum_over_ranks(fbytes + 3 * esize)
+    del x_host
+    return {"value": steps / secs, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "steps": steps, "final_rel_error": float(err_host[0]),
+            "note": "per step: pinned-host tensor slab + factors -> device, ||X||^2 + Grams + one full ALS sweep "
+                    "through tensorly_b200.CPALS, factors + error -> host (PCIe-bound by construction)"}
+
+
+def parity_leg(env):
+    """Driver-visible correctness of the path that was just timed, on a shape small enough to run twice:
+    the sharded trajectory (real kernels, real collectives) against the single-GPU one from the same tensor and
+    the same initial factors, and the dimension-tree sweep against the N-pass sweep.  Gate: 1e-4 relative on the
+    reconstruction errors (north star)."""
+    import torch
+    import tensorly_b200 as tb
+    from tensorly_b200.cp_als import CPALS, _Comm
+    shape, R, n = PARITY_SHAPE, PARITY_RANK, PARITY_SWEEPS
+    x = device_slab(shape, 0, shape[0], torch.float32, env.device, seed=7, block=32)
+    fs = initial_factors(shape, R, torch.float32, env.device, seed=8)
+    w = torch.ones(R, device=env.device)
+    solo = _Comm(None, sharded=False)
+
+    def trajectory(st):
+        errs = []
+        for _ in range(n):
+            st.sweep(True)
+            errs.append(st.err[0].clone())
+        return torch.stack(errs), st
+
+    e_tree, st_tree = trajectory(CPALS(x, w, fs, comm=solo))
+    e_npass, _ = trajectory(CPALS(x, w, fs, comm=solo, dimtree=False))
+    dev_tree = float(torch.max(torch.abs(e_tree - e_npass) / e_npass))
+    out = {"shape": list(shape), "rank": R, "sweeps": n, "gate": 1e-4,
+           "dimension_tree_vs_n_pass_max_rel_err_dev": dev_tree}
+    ok = dev_tree <= 1e-4
+    if env.world > 1:
+        lo, hi = tb.shard_bounds(shape[0], env.world, env.rank)
+        fl = [f.clone() for f in fs]
+        fl[0] = fl[0][lo:hi].contiguous()
+        e_sh, st_sh = trajectory(CPALS(x[lo:hi].contiguous(), w, fl, comm=env.comm, shard_mode=0))
+        dev_sh = float(torch.max(torch.abs(e_sh - e_tree) / e_tree))
+        fdev = 0.0
+        for k, (a, b) in enumerate(zip(st_sh.factors, st_tree.factors)):
+            b = b[lo:hi] if k == 0 else b
+            fdev = max(fdev, float(torch.linalg.norm(a - b) / torch.linalg.norm(b)))
+        dev_sh = env.max_over_ranks(dev_sh)
+        fdev = env.max_over_ranks(fdev)
+        out["sharded_vs_single_gpu_max_rel_err_dev"] = dev_sh
+        out["sharded_vs_single_gpu_max_factor_dev"] = fdev
+        out["collective"] = env.comm_kind
+        ok = ok and dev_sh <= 1e-4 and fdev <= 1e-2
+        st_sh._graph = None
+    out["ok"] = bool(ok)
+    out["final_rel_error"] = float(e_tree[-1])
+    return out
+
+
+def fp64_leg(env):
+    """fp64 MTTKRP / TTM on the SIMT DFMA path (B200's FP64 tensor and vector peaks are the same ~37 TFLOP/s, so
+    DFMA is the fp64 roofline): 512^3, rank 32; intensity 2R flop / 8 B = 8 flop/B => compute-bound."""
+    import torch
+    import tensorly_b200 as tb
+    shape, R = (512, 512, 512), 32
+    g = torch.Generator(device=env.device).manual_seed(5)
+    x = torch.rand(shape, generator=g, dtype=torch.float64, device=env.device)
+    fs = [torch.rand((s, R), generator=g, dtype=torch.float64, device=env.device) for s in shape]
+    res = {"shape": list(shape), "rank": R}
+    flops = 2.0 * R * x.numel()
+    nbytes = 8.0 * (x.numel() + R * sum(shape))
+
+    def timeit(fn, reps=5):
         for _ in range(2):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(e2e_steps):
-            e2e_step()
-        a1.record()
-        barrier()
-        t = torch.tensor([max(a0.elapsed_time(a1) * 1e-3, time.perf_counter() - t0)], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        fbytes = esize * R * sum(local_shape)
-        e2e = {"value": e2e_steps / float(t.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(esize * elems_local + fbytes) * world,
-               "d2h_bytes_per_step": int(fbytes + 3 * esize) * world, "steps": e2e_steps,
-               "note": "per step: pinned-host tensor slab + factors -> device, ||X||^2 + Grams + one full ALS sweep "
-                       "through tensorly_b200.CPALS, factors + error -> host"}
-        del x_host, x_dev
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+    ms = [timeit(lambda m=m: tb.unfolding_dot_khatri_rao(x, (None, fs), m)) for m in range(3)]
+    # DFMA peak of this GPU: 148 SMs x 64 DFMA/clk x 2 x SM clock
+    peak_tf = 148 * 64 * 2 * 1.965e9 / 1e12
+    res["mttkrp_ms_per_mode"] = ms
+    res["mttkrp_tflops"] = [flops / (m * 1e-3) / 1e12 for m in ms]
+    res["mttkrp_gbs"] = [nbytes / (m * 1e-3) / 1e9 for m in ms]
+    res["fp64_peak_tflops"] = peak_tf
+    res["mttkrp_frac_of_fp64_peak"] = statistics.mean(res["mttkrp_tflops"]) / peak_tf
+    m_t = timeit(lambda: tb.mode_dot(x, fs[2], 2, transpose=True))
+    res["ttm_ms"] = m_t
+    res["ttm_tflops"] = flops / (m_t * 1e-3) / 1e12
+    res["ttm_frac_of_fp64_peak"] = res["ttm_tflops"] / peak_tf
+    res["kernel_path"] = tb.last_kernel_path()
+    res["peak_source"] = "148 SMs x 64 DFMA/clk/SM x 2 flop x 1.965 GHz (nominal; FP64 tensor peak is the same on B200)"
+    return res
 
-    clocks = sampler.stop() if rank_id == 0 else None
 
-    # ---- optional: the UNMODIFIED reference driver on the b200 tenalg backend -------------
-    ref_driver = None
-    if rank_id == 0 and world == 1 and not args.no_refdriver:
+def reference_driver_leg(env, key, res):
+    """The UNMODIFIED tensorly.decomposition.parafac on the b200 tenalg backend (delta-iterations timing)."""
+    import torch
+    import tensorly_b200 as tb
+    x, weights, factors = res["x"], res["weights"], res["factors"]
+    R = WORKLOADS[key]["rank"]
+    try:
+        tl = tb.import_tensorly()
+        tl.set_backend("pytorch")
+        tb.use()
+        from tensorly.cp_tensor import CPTensor
+        from tensorly.decomposition import parafac
+
+        def timed(n):
+            init = CPTensor((weights.clone(), [f.clone() for f in factors]))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            parafac(x, R, n_iter_max=n, init=init, tol=0, return_errors=True)
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0
+        timed(2)
+        ta, tb_ = timed(2), timed(12)
+        out = {"value": 10.0 / max(tb_ - ta, 1e-9), "unit": UNIT,
+               "what": "tensorly.decomposition.parafac (unmodified) on tl.tenalg backend 'b200'"}
+        tb.set_dimension_tree(True)
         try:
-            tl = tb.import_tensorly()
-            tl.set_backend("pytorch")
-            tb.use()
-            from tensorly.cp_tensor import CPTensor
-            from tensorly.decomposition import parafac
-
-            def timed(n):
-                init = CPTensor((weights.clone(), [f.clone() for f in factors]))
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                parafac(x, R, n_iter_max=n, init=init, tol=0, return_errors=True)
-                torch.cuda.synchronize()
-                return time.perf_counter() - t0
             timed(2)
             ta, tb_ = timed(2), timed(12)
-            ref_driver = {"value": 10.0 / max(tb_ - ta, 1e-9), "unit": UNIT,
-                          "what": "tensorly.decomposition.parafac (unmodified) on tl.tenalg backend 'b200'"}
-            tb.set_dimension_tree(True)
+            out["value_dimension_tree"] = 10.0 / max(tb_ - ta, 1e-9)
+            out["what_dimension_tree"] = "same, with tensorly_b200.use(dimension_tree=True)"
+        finally:
+            tb.set_dimension_tree(False)
+        if hasattr(tb, "use_fast_solve"):
+            tb.use_fast_solve()
             try:
+                tb.set_dimension_tree(True)
                 timed(2)
                 ta, tb_ = timed(2), timed(12)
-                ref_driver["value_dimension_tree"] = 10.0 / max(tb_ - ta, 1e-9)
-                ref_driver["what_dimension_tree"] = "same, with tensorly_b200.use(dimension_tree=True)"
+                out["value_fast_solve"] = 10.0 / max(tb_ - ta, 1e-9)
+                out["what_fast_solve"] = "same, with the dimension-tree cache and the sync-free small-system `solve` hook"
             finally:
                 tb.set_dimension_tree(False)
-        except Exception as exc:  # tensorly not importable on this box
-            ref_driver = {"unavailable": str(exc)[:200]}
+                tb.use_default_solve()
+        return out
+    except Exception as exc:  # tensorly not importable on this box
+        return {"unavailable": str(exc)[:200]}
 
-    # ---- CPU baseline on the host cores (rank 0, N=1 only), bounded sample ---------------
+
+def cpu_baseline_leg(key, budget_s, steps=2, warmup=1):
+    """cpu_baseline of the `ours` line: the unmodified reference on the host cores, real shape when memory and
+    the time budget allow (C2: yes), else a mode-0 slab, labelled."""
+    wl = WORKLOADS[key]
+    sample, frac, avail = reference_plan(wl["shape"], wl["rank"], wl["dtype"])
+    if key == "c5" and sample[0] > 256:
+        # ~30 s per real C5 sweep on 16 threads: keep the default bench run short, the full-shape timing is the
+        # job of `--impl reference`.  One GPU's share at N = 8 (256 rows) is the bounded sample.
+        sample, frac = (256,) + tuple(wl["shape"][1:]), 256 / wl["shape"][0]
+    per, n, warm, kind, threads = cpu_reference_sweeps(sample, wl["rank"], wl["dtype"], steps, warmup, budget_s)
+    what = (f"{n} timed sweeps (after {warm} warm-up) of unmodified tensorly parafac, numpy backend + core tenalg, "
+            f"shape {tuple(sample)} rank {wl['rank']} {wl['dtype']}, {threads} threads")
+    if frac != 1.0:
+        what += f"; EXTRAPOLATED to {tuple(wl['shape'])} by the mode-0 row ratio {frac:.4g}"
+    return {"value": frac / per, "unit": UNIT, "cores": threads, "kind": kind, "sample": what,
+            "extrapolated": frac != 1.0, "measured_ms_per_sweep_at_sample": per * 1e3, "sample_shape": list(sample)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import tensorly_b200 as tb  # noqa: F401
+    from tensorly_b200.cp_als import _Comm
+
+    env = Env()
+    env.world = int(os.environ.get("WORLD_SIZE", "1"))
+    env.rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    env.device = torch.device("cuda", local)
+    if env.world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=env.device)
+    env.comm = _Comm(None, sharded=env.world > 1)
+    env.comm_kind = getattr(env.comm, "kind", "nccl all_reduce") if env.world > 1 else None
+
+    def barrier():
+        if env.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=env.device)
+        if env.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=env.device)
+        if env.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+    env.barrier, env.max_over_ranks, env.sum_over_ranks = barrier, max_over_ranks, sum_over_ranks
+    env.sampler = ClockSampler(local) if env.rank == 0 else None
+    if env.sampler:
+        env.sampler.start()
+
+    key = args.workload
+    res = bench_workload(env, key, args, headline=True)
+    state = res["state"]
+    clocks_timed = env.sampler.summary(*res["clock_marks"]) if env.sampler else None
+    parity = parity_leg(env)
+    ref_driver = None
+    if env.rank == 0 and env.world == 1 and not args.no_refdriver:
+        ref_driver = reference_driver_leg(env, key, res)
+    e2e = None if args.no_e2e else e2e_leg(env, res, args)
+    shape, R = WORKLOADS[key]["shape"], WORKLOADS[key]["rank"]
+    dimtree = state.dimtree
+    # free the headline tensor before the secondary block
+    state._graph = None
+    res.pop("state"), res.pop("x"), res.pop("factors")
+    del state
+    torch.cuda.empty_cache()
+
+    c2 = None
+    if key != "c2" and not args.no_c2:
+        r2 = bench_workload(env, "c2", args, headline=False)
+        c2 = {"workload": WORKLOADS["c2"]["name"], "value": r2["value"], "unit": UNIT, "ms_per_step": r2["ms_per_step"],
+              "steps": args.steps, "sustained": r2.get("sustained"), "roofline": r2["roofline"],
+              "final_rel_error": r2["rel_err"], "launches_per_sweep": r2["launches_per_sweep"],
+              "clocks": env.sampler.summary(*r2["clock_marks"]) if env.sampler else None}
+        if env.rank == 0 and env.world == 1 and not args.no_refdriver:
+            c2["reference_driver_on_b200"] = reference_driver_leg(env, "c2", r2)
+        r2["state"]._graph = None
+        del r2
+        torch.cuda.empty_cache()
+    fp64 = fp64_leg(env) if (env.rank == 0 and env.world == 1 and not args.no_fp64) else None
+    clocks = env.sampler.stop() if env.sampler else None
+
+    # ---- CPU baselines on the host cores (rank 0, N=1 only), bounded samples ---------------
     cpu = None
-    if rank_id == 0 and world == 1 and not args.no_cpu:
-        sample = tuple(min(s, 512 if args.workload in ("c2", "c5") else s) for s in shape)
-        frac = 1.0
-        for a, b in zip(sample, shape):
-            frac *= a / b
-        per, kind, threads = cpu_reference_sweeps(sample, R, wl["dtype"], 3, 1)
-        cpu = {"value": frac / per, "unit": UNIT, "cores": threads, "kind": kind,
-               "sample": f"3 sweeps of the same CP-ALS at sub-shape {sample} (rank {R}, {wl['dtype']}), numpy backend + "
-                         f"core tenalg, scaled by the element ratio {frac:.6g}"}
+    if env.rank == 0 and env.world == 1 and not args.no_cpu:
+        cpu = cpu_baseline_leg(key, args.cpu_budget_s)
+        if c2 is not None:
+            c2["cpu_baseline"] = cpu_baseline_leg("c2", args.cpu_budget_s)
 
-    if rank_id == 0:
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if world == 1 and os.path.exists(tp):      # the ncu capture is of the 1-GPU launch of this workload
-            try:
-                traffic = json.load(open(tp)).get(args.workload, {}).get(path_used)
-            except Exception:
-                traffic = None
+    if env.rank == 0:
+        wl = WORKLOADS[key]
+        if clocks_timed is not None and clocks is not None:
+            clocks_timed["whole_run"] = clocks
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32" if dtype == torch.float32 else "f64", "data": "synthetic",
-            "config": {"workload": wl["name"], "shape": list(shape), "rank": R, "sharding": f"mode-0 slabs over {world} GPU(s)",
-                       "l2": "inputs larger than L2 (tensor slab %.2f GB per GPU >> 126 MB)" % (esize * elems_local / 1e9),
-                       "kernel_path": path_used,
-                       "sweep": ("dimension-tree ALS sweep: T = X x_last F_last^T (one tensor pass) -> MTTKRP of every earlier "
-                                 "mode from T, full MTTKRP for the last mode (second tensor pass); identical factor updates, "
-                                 "parity-tested against the N-pass sweep" if state.dimtree else
-                                 "one full MTTKRP per mode") +
-                                (" + Gram-Hadamard LU solve + Gram per mode + error, one CUDA graph" if world == 1 else
-                                 " + all_reduce + solve + Gram per mode + error, one CUDA graph")},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": f"MTTKRP ({path_used})",
-                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": avg_ms,
-                         "per_mode_gbs": [alg_bytes / (m * 1e-3) / 1e9 for m in mttkrp_ms],
-                         "frac_of_nominal_8TBs": achieved / 8000.0,
-                         "note": ("frac > 1: `peak` is the measured COPY bandwidth (read + write); a read-only stream like "
-                                  "this one can exceed it — see frac_of_nominal_8TBs") if achieved > peak else None},
-            "three_pass": three_pass,
-            "ttm_pass": ttm_pass,
+            "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": env.world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32" if wl["dtype"] == "float32" else "f64",
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "shape": list(shape), "rank": R,
+                       "sharding": f"mode-0 slabs over {env.world} GPU(s), the same seeded tensor at every N",
+                       "l2": "inputs larger than L2 (tensor slab %.2f GB per GPU >> 126 MB)"
+                             % (res["esize"] * (shape[0] // env.world) * shape[1] * shape[2] / 1e9),
+                       "kernel_path": res["path"],
+                       "collective": env.comm_kind,
+                       "sweep": ("dimension-tree ALS sweep: T = X x_last F_last^T (one tensor pass) -> MTTKRP of every "
+                                 "earlier mode from T, full MTTKRP for the last mode (second tensor pass); identical "
+                                 "factor updates, parity-tested against the N-pass sweep" if dimtree else
+                                 "one full MTTKRP per mode") + " + Gram-Hadamard LU solve + Gram per mode + error"},
+            "roofline": res["roofline"],
+            "sustained": res.get("sustained"),
+            "three_pass": res.get("three_pass"),
+            "ttm_pass": res.get("ttm_pass"),
             "cpu_baseline": cpu,
             "e2e": e2e,
-            "gpu_launches": int(launches_per_sweep * args.steps),
-            "launches_per_sweep": int(launches_per_sweep),
-            "clocks": clocks,
-            "final_rel_error": rel_err,
+            "parity": parity,
+            "gpu_launches": int(res["launches_per_sweep"] * args.steps),
+            "launches_per_sweep": res["launches_per_sweep"],
+            "clocks": clocks_timed,
+            "final_rel_error": res["rel_err"],
             "reference_driver_on_b200": ref_driver,
+            "c2": c2,
+            "fp64": fp64,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        # teardown must never turn a finished measurement into a hang: drop the CUDA graphs (they hold NCCL
-        # kernels) before the communicator, and bail out hard if the collective teardown stalls anyway
+    if env.world > 1:
+        # teardown must never turn a finished measurement into a hang: drop the CUDA graphs before the
+        # communicator, and bail out hard if the collective teardown stalls anyway
         import gc
+
         def _bail():
             time.sleep(30)
             os._exit(0)
         threading.Thread(target=_bail, daemon=True).start()
-        state._graph = None
-        del state
         gc.collect()
         torch.cuda.synchronize()
         dist.barrier()
@@ -458,15 +812,24 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-c2", action="store_true")
+    ap.add_argument("--no-fp64", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true")
     ap.add_argument("--no-refdriver", action="store_true")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0)
+    ap.add_argument("--cpu-budget-s", type=float, default=30.0)
     args = ap.parse_args()
     if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1: undo it before numpy/OpenBLAS load, the CPU arm gets every host thread
+        n = str(host_threads())
+        for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[var] = n
         return run_reference(args)
     return run_ours(args)
 

@@ -52,6 +52,9 @@ const char* tlb200_last_path(void);
 /* Number of kernel launches this library has issued so far in this process (host-side
  * count; graph replays re-launch the captured kernels without passing through here). */
 int64_t     tlb200_launch_count(void);
+/* Stamp of the sources this binary was compiled from (sha256 prefix over csrc + this header, written by
+ * tensorly_b200/build.py); the Python loader refuses a library whose stamp differs from the tree beside it. */
+const char* tlb200_source_hash(void);
 
 /* ---------------------------------------------------------------------------
  * unfold — replaces tensorly.base.unfold (tensorly/base.py:39-53):

@@ -11,7 +11,7 @@ g = torch.Generator(device="cuda").manual_seed(0)
 x = torch.rand(shape, generator=g, device="cuda")
 fs = [torch.rand(s, R, generator=g, device="cuda") for s in shape]
 lo, hi = tb.shard_bounds(shape[0], world, rank)
-cp, errs = tb.parafac(x[lo:hi].contiguous(), R, n_iter_max=6, init=(None, fs), tol=0, return_errors=True, shard_mode=0)
+cp, errs = tb.parafac(x[lo:hi].contiguous(), R, n_iter_max=6, init=(None, fs), tol=0, return_errors=True, sharded=True, shard_mode=0)
 if rank == 0:
     dist_errs = errs
 torch.cuda.synchronize()

@@ -48,6 +48,7 @@ SIGNATURES = {
     "tlb200_status_string": (c_char_p, [c_int]),
     "tlb200_last_path": (c_char_p, []),
     "tlb200_launch_count": (c_int64, []),
+    "tlb200_source_hash": (c_char_p, []),
     "tlb200_unfold": (c_int, [c_void_p, _I64P, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tlb200_fold": (c_int, [c_void_p, _I64P, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tlb200_khatri_rao": (c_int, [_VPP, _I64P, _I64P, _I64P, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p,
@@ -83,6 +84,21 @@ SIGNATURES = {
 _lib = None
 
 
+def source_hash() -> str:
+    """sha256 over the CUDA sources and headers the library is built from (file names + contents, sorted).
+    build.py bakes it into the .so (tlb200_source_hash); load() refuses a library built from other sources."""
+    import hashlib
+    csrc = os.path.join(_HERE, "csrc")
+    files = sorted(os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".h")))
+    files.append(os.path.join(os.path.dirname(_HERE), "include", "tlb200.h"))
+    h = hashlib.sha256()
+    for path in files:
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:32]
+
+
 def load() -> ctypes.CDLL:
     """Load libtlb200.so (once). Raises RuntimeError if it is missing — never falls back."""
     global _lib
@@ -98,6 +114,11 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so is stale
         fn.restype = res
         fn.argtypes = args
+    built_from = lib.tlb200_source_hash().decode()
+    if os.environ.get("TLB200_SKIP_HASH_CHECK", "0") != "1" and built_from != source_hash():
+        raise RuntimeError(
+            f"tensorly_b200: {LIB_PATH} was built from other sources (stamp {built_from}, tree {source_hash()}); "
+            "rebuild it with `python -m tensorly_b200.build`.")
     _lib = lib
     return lib
 

@@ -54,7 +54,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every .cu under csrc/ for sm_100a and link libtlb200.so. Returns its path."""
     nvcc = _nvcc()
     os.makedirs(OBJ_DIR, exist_ok=True)
-    hdrs = _headers()
+    # stamp of the sources this library is built from (checked by _lib.load()); rewritten only when it changes,
+    # so that api.o is recompiled exactly then
+    from ._lib import source_hash
+    stamp = os.path.join(OBJ_DIR, "source_hash.inc")
+    text = f'#define TLB200_SOURCE_HASH "{source_hash()}"\n'
+    if not os.path.exists(stamp) or open(stamp).read() != text:
+        with open(stamp, "w") as f:
+            f.write(text)
+    hdrs = _headers() + [stamp]
     jobs = []
     objs = []
     for src in sources():

@@ -80,13 +80,28 @@ class CudaOps:
 
 
 class _Comm:
-    def __init__(self, group=None):
+    """The exchange side of the sharded driver.  Sharding is an explicit opt-in (`sharded=True` or a process
+    group): a plain `parafac(x, r)` inside a multi-rank job treats `x` as a whole tensor, never as a slab."""
+
+    def __init__(self, group=None, sharded=None):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
-        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        if sharded is None:
+            sharded = group is not None
+        ready = dist.is_available() and dist.is_initialized()
+        if sharded and not ready:
+            raise RuntimeError("sharded=True needs an initialised torch.distributed process group")
+        self.active = bool(sharded) and ready and dist.get_world_size(group) > 1
         self.world = dist.get_world_size(group) if self.active else 1
         self.rank = dist.get_rank(group) if self.active else 0
+
+    def broadcast(self, t, src_rank=0):
+        """Make rank `src_rank`'s copy of `t` everyone's (replicated state must be bit-identical)."""
+        if self.active:
+            src = self.dist.get_global_rank(self.group, src_rank) if self.group is not None else src_rank
+            self.dist.broadcast(t, src=src, group=self.group)
+        return t
 
     def all_reduce(self, t):
         if self.active:
@@ -279,19 +294,46 @@ def _random_init(shape, rank, random_state, dtype, device, non_negative=False):
     return weights, factors
 
 
-def _svd_init(tensor, rank, random_state):
-    """init='svd' of the reference (_cp.py:72-100): leading left singular vectors of each
-    unfolding (torch.linalg.svd on our unfold), mode-0 vectors scaled by the singular
-    values, random padding when I_n < rank."""
+def _nndsvda(matrix, U, S, V):
+    """make_svd_non_negative(..., nntype='nndsvda') of the reference (tenalg/svd.py:68-135), left factor only:
+    the leading triplet as is, every other column replaced by the dominant of its positive / negative parts
+    scaled by sqrt(S_j * |x_+-| * |y_+-|), entries below eps filled with the mean of the matrix.  All columns
+    at once, no host round trips (the reference loops over the columns and reads the norms back)."""
+    k = min(U.shape[1], V.shape[0])
+    x, y = U[:, :k], V[:k, :]
+    xp, yp = torch.clamp(x, min=0.0), torch.clamp(y, min=0.0)
+    xn, yn = torch.abs(torch.clamp(x, max=0.0)), torch.abs(torch.clamp(y, max=0.0))
+    xpn, ypn = torch.linalg.norm(xp, dim=0), torch.linalg.norm(yp, dim=1)
+    xnn, ynn = torch.linalg.norm(xn, dim=0), torch.linalg.norm(yn, dim=1)
+    m_p, m_n = xpn * ypn, xnn * ynn
+    pos = m_p > m_n
+    u = torch.where(pos, xp / xpn, xn / xnn)
+    lbd = torch.sqrt(S[:k] * torch.where(pos, m_p, m_n))
+    W = torch.zeros_like(U)
+    W[:, :k] = u * lbd
+    W[:, 0] = torch.sqrt(S[0]) * torch.abs(U[:, 0])
+    eps = torch.finfo(matrix.dtype).eps
+    return torch.where(W < eps, matrix.mean().expand_as(W), W)
+
+
+def _svd_init(tensor, rank, random_state, non_negative=False):
+    """init='svd' of the reference (_cp.py:72-100 through svd_interface, tenalg/svd.py:366-447): leading left
+    singular vectors of each unfolding (torch.linalg.svd on our unfold), sign-fixed by svd_flip, made
+    non-negative by NNDSVDA when asked, mode-0 vectors scaled by the singular values, random padding when
+    I_n < rank."""
     rng = np.random.RandomState(random_state) if not isinstance(random_state, np.random.RandomState) else random_state
     factors = []
     for mode in range(tensor.dim()):
-        U, S, _ = torch.linalg.svd(_ops.unfold(tensor, mode), full_matrices=False)
+        unf = _ops.unfold(tensor, mode)
+        U, S, V = torch.linalg.svd(unf, full_matrices=False)
         # svd_flip (tenalg/svd.py:13-40): largest-|.| entry of each column positive
         idx = torch.argmax(torch.abs(U), dim=0)
         signs = torch.sign(U[idx, torch.arange(U.shape[1], device=U.device)])
         U = U * signs
-        U = U[:, :rank].clone()
+        U, S = U[:, :rank], S[:rank]              # truncated_svd(n_eigenvecs=rank), tenalg/svd.py:232-235
+        if non_negative:
+            U = _nndsvda(unf, U, S, (V[:U.shape[1]] * signs[:U.shape[1], None])[:rank])
+        U = U.clone()
         if mode == 0:
             k = min(rank, S.shape[0])
             U[:, :k] = U[:, :k] * S[:k]
@@ -327,10 +369,10 @@ def _delegate(name, tensor, rank, kwargs):
 
 
 def _run(tensor, rank, n_iter_max, init, svd, tol, random_state, verbose, return_errors, l2_reg, cvg_criterion,
-         fixed_modes, callback, update, group, shard_mode, ops, use_graph):
+         fixed_modes, callback, update, group, shard_mode, ops, use_graph, sharded=None):
     if not isinstance(tensor, torch.Tensor):
         raise TypeError("tensor must be a torch.Tensor")
-    comm = _Comm(group)
+    comm = _Comm(group, sharded)
     ndim = tensor.dim()
     rank = int(rank)
     # global shape: the local slab's extent along shard_mode is summed over ranks
@@ -347,10 +389,13 @@ def _run(tensor, rank, n_iter_max, init, svd, tol, random_state, verbose, return
     if isinstance(init, str):
         if init == "random":
             weights, factors = _random_init(shape, rank, random_state, tensor.dtype, tensor.device)
+            if comm.active and not isinstance(random_state, int):
+                for f in factors:                 # unseeded / stateful generators differ per rank
+                    comm.broadcast(f)
         elif init == "svd":
             if comm.active:
                 raise NotImplementedError("init='svd' is not available for a sharded tensor; pass init='random' or factors")
-            weights, factors = _svd_init(tensor, rank, random_state)
+            weights, factors = _svd_init(tensor, rank, random_state, non_negative=non_negative)
             if non_negative:
                 factors = [torch.abs(f) for f in factors]
         else:
@@ -410,15 +455,16 @@ def _run(tensor, rank, n_iter_max, init, svd, tol, random_state, verbose, return
 def parafac(tensor, rank, n_iter_max=100, init="svd", svd="truncated_svd", normalize_factors=False,
             orthogonalise=False, tol=1e-8, random_state=None, verbose=0, return_errors=False, sparsity=None,
             l2_reg=0, mask=None, cvg_criterion="abs_rec_error", fixed_modes=None, svd_mask_repeats=5,
-            linesearch=False, callback=None, *, group=None, shard_mode=0, ops=CudaOps, use_graph=True):
+            linesearch=False, callback=None, *, sharded=None, group=None, shard_mode=0, ops=CudaOps, use_graph=True):
     """CANDECOMP/PARAFAC by ALS — same signature and semantics as
     tensorly.decomposition.parafac (tensorly/decomposition/_cp.py:230).
 
-    Keyword-only extras: `group`/`shard_mode` run the sharded multi-GPU algorithm (pass the
-    LOCAL slab of the tensor along `shard_mode`); `use_graph=False` disables CUDA graphs.
+    Keyword-only extras: `sharded=True` (or a process `group`) runs the sharded multi-GPU algorithm — pass the
+    LOCAL slab of the tensor along `shard_mode`; without either the tensor is decomposed on this GPU alone, also
+    inside a multi-rank job.  `use_graph=False` disables CUDA graphs.
     """
     if normalize_factors or orthogonalise or sparsity or mask is not None or linesearch or svd != "truncated_svd":
-        if group is not None:
+        if _Comm(group, sharded).active:
             raise NotImplementedError("normalize_factors/orthogonalise/sparsity/mask/linesearch are not available sharded")
         return _delegate("parafac", tensor, rank, dict(
             n_iter_max=n_iter_max, init=init, svd=svd, normalize_factors=normalize_factors, orthogonalise=orthogonalise,
@@ -426,21 +472,21 @@ def parafac(tensor, rank, n_iter_max=100, init="svd", svd="truncated_svd", norma
             l2_reg=l2_reg, mask=mask, cvg_criterion=cvg_criterion, fixed_modes=fixed_modes,
             svd_mask_repeats=svd_mask_repeats, linesearch=linesearch, callback=callback))
     return _run(tensor, rank, n_iter_max, init, svd, tol, random_state, verbose, return_errors, l2_reg, cvg_criterion,
-                fixed_modes, callback, "ls", group, shard_mode, ops, use_graph)
+                fixed_modes, callback, "ls", group, shard_mode, ops, use_graph, sharded)
 
 
 def non_negative_parafac(tensor, rank, n_iter_max=100, init="svd", svd="truncated_svd", tol=10e-7, random_state=None,
                          verbose=0, normalize_factors=False, return_errors=False, mask=None,
-                         cvg_criterion="abs_rec_error", fixed_modes=None, *, group=None, shard_mode=0, ops=CudaOps,
-                         use_graph=True):
+                         cvg_criterion="abs_rec_error", fixed_modes=None, *, sharded=None, group=None, shard_mode=0,
+                         ops=CudaOps, use_graph=True):
     """Non-negative CP by multiplicative updates — same signature and semantics as
     tensorly.decomposition.non_negative_parafac (tensorly/decomposition/_nn_cp.py:26)."""
     if normalize_factors or mask is not None or svd != "truncated_svd":
-        if group is not None:
+        if _Comm(group, sharded).active:
             raise NotImplementedError("normalize_factors/mask are not available sharded")
         return _delegate("non_negative_parafac", tensor, rank, dict(
             n_iter_max=n_iter_max, init=init, svd=svd, tol=tol, random_state=random_state, verbose=verbose,
             normalize_factors=normalize_factors, return_errors=return_errors, mask=mask, cvg_criterion=cvg_criterion,
             fixed_modes=fixed_modes))
     return _run(tensor, rank, n_iter_max, init, svd, tol, random_state, verbose, return_errors, 0.0, cvg_criterion,
-                fixed_modes, None, "mu", group, shard_mode, ops, use_graph)
+                fixed_modes, None, "mu", group, shard_mode, ops, use_graph, sharded)

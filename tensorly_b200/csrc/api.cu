@@ -1,6 +1,7 @@
 // Library introspection entry points.
 #include "common.cuh"
 #include <atomic>
+#include "build/source_hash.inc"     // written by tensorly_b200/build.py: sha256 of the sources of this build
 
 namespace tlb200 {
 int64_t launches();
@@ -13,6 +14,7 @@ int64_t launches() { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int tlb200_version(void) { return 100; }  // 0.1.0
 extern "C" const char* tlb200_build_arch(void) { return "sm_100a"; }
+extern "C" const char* tlb200_source_hash(void) { return TLB200_SOURCE_HASH; }
 extern "C" int64_t tlb200_launch_count(void) { return tlb200::launches(); }
 extern "C" const char* tlb200_last_path(void) { return tlb200::g_last_path; }
 extern "C" const char* tlb200_status_string(int status) {

@@ -1,6 +1,7 @@
 // Shared helpers for the tlb200 kernels (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stddef.h>
 #include "../../include/tlb200.h"
@@ -27,6 +28,20 @@ void count_launch();
         cudaError_t e__ = cudaGetLastError();               \
         if (e__ != cudaSuccess) return TLB200_ECUDA;        \
     } while (0)
+
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute belongs to the (kernel, device)
+// pair, so it is tracked per device — one bit per ordinal in a per-kernel atomic mask (a process may drive several
+// GPUs from several threads); ordinals >= 64 simply set it on every launch.
+template <typename K>
+inline int ensure_dynamic_smem(K kernel, int bytes, std::atomic<uint64_t>& done) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return TLB200_ECUDA;
+    const uint64_t bit = dev >= 0 && dev < 64 ? (1ull << dev) : 0;
+    if (bit && (done.load(std::memory_order_acquire) & bit)) return TLB200_OK;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return TLB200_ECUDA;
+    if (bit) done.fetch_or(bit, std::memory_order_release);
+    return TLB200_OK;
+}
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -686,13 +686,8 @@ int cp_update_launch(const void* const* grams, int nmodes, int mode, int64_t R, 
     size_t smem = sizeof(T) * ((size_t)R * ld + (size_t)kSolveRows * ld) + sizeof(int) * (R + 1);
     if (R <= 32) smem = SolveSmem<T, 32>::bytes((int)R);
     else if (sizeof(T) == 4 && R <= 64) smem = SolveSmem<T, 64>::bytes((int)R);
-    static bool attr_set[2] = {false, false};
-    const int ti = sizeof(T) == 8;
-    if (!attr_set[ti]) {
-        if (cudaFuncSetAttribute(cp_update_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
-            return TLB200_ECUDA;
-        attr_set[ti] = true;
-    }
+    static std::atomic<uint64_t> attr_done{0};        // one per instantiation (T), one bit per device
+    if (ensure_dynamic_smem(cp_update_kernel<T>, 200 * 1024, attr_done)) return TLB200_ECUDA;
     if (smem > 200 * 1024) return TLB200_EUNSUPPORTED;
     const int nblk = (int)ceil_div(rows, kSolveRows);
     if (nblk == 0) return TLB200_OK;
@@ -715,13 +710,8 @@ int nncp_update_launch(const void* const* grams, int nmodes, int mode, int64_t R
     if (st) return st;
     const int ld = (int)R + 1;
     const size_t smem = sizeof(T) * ((size_t)R * ld + 32 * (size_t)ld);
-    static bool attr_set[2] = {false, false};
-    const int ti = sizeof(T) == 8;
-    if (!attr_set[ti]) {
-        if (cudaFuncSetAttribute(nncp_update_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
-            return TLB200_ECUDA;
-        attr_set[ti] = true;
-    }
+    static std::atomic<uint64_t> attr_done{0};
+    if (ensure_dynamic_smem(nncp_update_kernel<T>, 200 * 1024, attr_done)) return TLB200_ECUDA;
     const int nblk = (int)ceil_div(rows, 32);
     if (nblk == 0) return TLB200_OK;
     nncp_update_kernel<T><<<nblk, 256, smem, stream>>>(gl, mode, (int)R, w, m, m_ld, f, f_ld, rows, (T)eps);

@@ -81,11 +81,14 @@ from_ttm_inner_kernel(const T* __restrict__ t, int64_t A, int64_t J, int64_t B, 
 }
 
 // B == 1: T viewed as [A][J][R].  Grid (j blocks, a-splits).  Threads: rv = vector column, jl = lane over j.
-//   partial[split][j][:] = sum_{a in split} P[a, :] * T[a, j, :]
+//   partial[split][j][:] = Q[0, :] * sum_{a in split} P[a, :] * T[a, j, :]
+// B == 1 also happens when every lead mode after `mode` is a singleton: Q is then a single row (it may carry the
+// weights), and P is absent when `mode` is the first mode — both are optional here.
 template <typename T, int VW>
 __global__ void __launch_bounds__(kThreads)
-from_ttm_outer_kernel(const T* __restrict__ t, int64_t A, int64_t J, int R, const T* __restrict__ P, int64_t a_per_split,
-                      T* __restrict__ out, int64_t out_ld, int64_t out_split) {
+from_ttm_outer_kernel(const T* __restrict__ t, int64_t A, int64_t J, int R, const T* __restrict__ P,
+                      const T* __restrict__ Qrow, int64_t a_per_split, T* __restrict__ out, int64_t out_ld,
+                      int64_t out_split) {
     using V = Vec<T, VW>;
     const int RV = R / VW;
     const int njl = kThreads / RV;
@@ -97,12 +100,25 @@ from_ttm_outer_kernel(const T* __restrict__ t, int64_t A, int64_t J, int R, cons
     V acc;
 #pragma unroll
     for (int c = 0; c < VW; ++c) acc.v[c] = T(0);
+    if (P != nullptr) {
 #pragma unroll 8
-    for (int64_t a = a0; a < a1; ++a) {
-        const V x = reinterpret_cast<const V*>(t + (a * J + j) * R)[rv];
-        const V p = reinterpret_cast<const V*>(P + a * R)[rv];
+        for (int64_t a = a0; a < a1; ++a) {
+            const V x = reinterpret_cast<const V*>(t + (a * J + j) * R)[rv];
+            const V p = reinterpret_cast<const V*>(P + a * R)[rv];
 #pragma unroll
-        for (int c = 0; c < VW; ++c) acc.v[c] += x.v[c] * p.v[c];
+            for (int c = 0; c < VW; ++c) acc.v[c] += x.v[c] * p.v[c];
+        }
+    } else {
+        for (int64_t a = a0; a < a1; ++a) {
+            const V x = reinterpret_cast<const V*>(t + (a * J + j) * R)[rv];
+#pragma unroll
+            for (int c = 0; c < VW; ++c) acc.v[c] += x.v[c];
+        }
+    }
+    if (Qrow != nullptr) {
+        const V q = reinterpret_cast<const V*>(Qrow)[rv];
+#pragma unroll
+        for (int c = 0; c < VW; ++c) acc.v[c] *= q.v[c];
     }
     T* dst = out + (int64_t)blockIdx.y * out_split + j * out_ld + rv * VW;
 #pragma unroll
@@ -173,7 +189,7 @@ int launch(const T* t, const Geometry& g, int R, const T* P, const T* Q, T* dst,
     } else {
         const int njl = kThreads / RV;
         dim3 grid((unsigned)ceil_div(g.J, njl), (unsigned)g.splits);
-        from_ttm_outer_kernel<T, VW><<<grid, kThreads, 0, stream>>>(t, g.A, g.J, R, P, g.a_per_split, dst, dst_ld, dst_split);
+        from_ttm_outer_kernel<T, VW><<<grid, kThreads, 0, stream>>>(t, g.A, g.J, R, P, Q, g.a_per_split, dst, dst_ld, dst_split);
     }
     TLB_CHECK_LAUNCH();
     return TLB200_OK;

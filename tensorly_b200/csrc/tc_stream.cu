@@ -727,12 +727,8 @@ template <int RP, int XL, int BM>
 int launch_cfg(const TcStreamLaunch& l, cudaStream_t stream) {
     using C = Cfg<RP, XL>;
     const int smem = C::SMEM + 1024;
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(tc_stream_kernel<RP, XL, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-            return TLB200_ECUDA;
-        attr = true;
-    }
+    static std::atomic<uint64_t> attr_done{0};        // per instantiation, one bit per device
+    if (ensure_dynamic_smem(tc_stream_kernel<RP, XL, BM>, smem, attr_done)) return TLB200_ECUDA;
     int64_t n_items = (int64_t)l.p.m_tiles * l.p.n_bblocks * l.p.k_ranges;
     if (n_items <= 0) return TLB200_OK;
     static int grid_cap = -1;

@@ -52,7 +52,7 @@ def _worker(rank, world, port, shape, cp_rank, shard_mode, update, iters, ret):
         x_local = torch.from_numpy(np.ascontiguousarray(x[tuple(sl)]))
         init = (None, [torch.from_numpy(f.copy()) for f in fs])
         fn = tb.parafac if update == "ls" else tb.non_negative_parafac
-        kw = dict(n_iter_max=iters, init=init, return_errors=True, shard_mode=shard_mode, ops=OracleOps, use_graph=False)
+        kw = dict(n_iter_max=iters, init=init, return_errors=True, sharded=True, shard_mode=shard_mode, ops=OracleOps, use_graph=False)
         kw["tol"] = 0 if update == "ls" else 1e-30
         cp, errs = fn(x_local, cp_rank, **kw)
         if update == "ls":

@@ -154,6 +154,8 @@ MTTKRP_CASES = [
     ((128, 96, 160), 130),       # three column blocks on the tensor-core path
     ((16, 16, 4096), 32),
     ((4096, 16, 16), 32),
+    ((48, 1, 40), 8),
+    ((24, 20, 1, 36), 12),
 ]
 
 
@@ -178,7 +180,9 @@ def test_mttkrp_vs_oracle(shape, rank, dtype, path):
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("shape,rank", [((64, 48, 80), 32), ((130, 70, 45), 10), ((256, 64, 96), 64), ((33, 257, 19), 7),
                                         ((40, 24, 20, 12), 16), ((12, 10, 9, 8, 6), 5), ((96, 160, 64), 100),
-                                        ((512, 256, 128), 32)])
+                                        ((512, 256, 128), 32),
+                                        # singleton lead modes: the inner range collapses to one row
+                                        ((48, 1, 40), 8), ((24, 20, 1, 36), 12), ((1, 30, 28), 6), ((20, 1, 1, 16), 4)])
 def test_mttkrp_from_ttm_vs_oracle(shape, rank, dtype):
     """Dimension-tree reuse: the MTTKRP of every mode before the last, from T = X x_{N-1} F_{N-1}^T, meets the
     same gate against the oracle's full MTTKRP."""
@@ -583,7 +587,7 @@ def test_parafac_driver_vs_reference(golden, tag, use_graph):
             assert rel_fro(host(a), b) <= 1e-6
 
 
-@pytest.mark.parametrize("shape,rank", [((96, 80, 112), 16), ((40, 24, 20, 12), 8)])
+@pytest.mark.parametrize("shape,rank", [((96, 80, 112), 16), ((40, 24, 20, 12), 8), ((48, 1, 40), 8), ((24, 20, 1, 36), 6)])
 def test_parafac_dimtree_same_trajectory(shape, rank):
     """Two tensor passes per sweep (dimension tree) vs N passes: same ALS trajectory."""
     g = torch.Generator(device="cuda").manual_seed(3)
