@@ -22,7 +22,7 @@ One JSON line is printed by rank 0 (DESIGN.md "Measurement" explains every key).
 `core` tenalg; the oracle port only if TensorLy is not importable) on the host cores, with every
 host thread, on the same config: real sweeps of the real shape, each sweep time-stamped through the
 reference's own `verbose` prints.  K and W are honoured as far as a wall-clock budget allows
-(`--ref-budget-s`, default 150 s): the line's `steps` / `warmup` are the sweeps that were actually
+(`--ref-budget-s`, default 180 s): the line's `steps` / `warmup` are the sweeps that were actually
 timed, so ms_per_step x steps is real time.  Only when the host cannot hold the reference's
 temporaries (C5 needs ~3.2x the 34 GB tensor) a mode-0 slab is timed instead and labelled
 `extrapolated`.
@@ -612,6 +612,89 @@ def fp64_leg(env):
     return res
 
 
+def tucker_leg(env, steps):
+    """C3 (BASELINE configs[2]): tucker HOOI rank [64,64,64] on random 512^3 fp32 — the TTM tensor-core path.
+    Own driver (TTM chains + Gram + subspace iteration on the hand-written kernels) and, beside it, the unmodified
+    reference driver on the b200 tenalg backend with torch's SVD and with the Gram+eigh plug-in.  Roofline of the
+    dominant kernel = the first TTM of a chain (the only pass over the 537 MB tensor): HBM-bound at this intensity."""
+    import torch
+    import tensorly_b200 as tb
+    shape, ranks = (512, 512, 512), [64, 64, 64]
+    x = device_slab(shape, 0, shape[0], torch.float32, env.device, seed=3)
+    out = {"workload": "C3: tucker HOOI rank [64,64,64] on random 512x512x512 fp32", "unit": UNIT}
+    # own driver: sweeps timed with CUDA events after init + warm-up sweeps
+    factors = tb.tucker_hooi._svd_init(tb.tucker_hooi.CudaOps, x, ranks, [0, 1, 2])
+    st = tb.HOOI(x, ranks, [0, 1, 2], factors)
+    for _ in range(3):
+        st.sweep()
+    n = max(5, min(steps, 20))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0 = tb.launch_count()
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(n):
+        st.sweep()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / n
+    out.update({"value": 1e3 / ms, "ms_per_step": ms, "steps": n, "final_rel_error": float(st.err[0]),
+                "launches_per_sweep": int((tb.launch_count() - c0) / n), "svd_iters": st.svd_iters,
+                "what": "tensorly_b200.tucker sweep: 3 x (TTM chain skip=k, Gram of the unfolding, warm-started subspace "
+                        "iteration) + core + error; no SVD/eigh, no host sync in the loop"})
+    # the first TTM of a chain: X x_1 U1^T (the tensor pass), tcgen05 engine
+    u = st.factors
+    def ttm():
+        return tb.mode_dot(x, u[1], 1, transpose=True)
+    for _ in range(3):
+        ttm()
+    a.record()
+    for _ in range(10):
+        ttm()
+    b.record()
+    torch.cuda.synchronize()
+    t_ms = a.elapsed_time(b) / 10
+    nbytes = 4.0 * (x.numel() + x.numel() // 512 * 64 + 64 * 512)
+    peak, peak_src = measured_peak_hbm()
+    out["roofline"] = {"bound": "hbm", "kernel": f"mode_dot(X, U^T, mode 1) ({tb.last_kernel_path()}), first TTM of a HOOI chain",
+                       "ms_per_launch": t_ms, "algorithmic_bytes_per_launch": nbytes, "achieved": nbytes / (t_ms * 1e-3) / 1e9,
+                       "peak": peak, "unit": "GB/s", "frac": nbytes / (t_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                       "tflops_useful": 2.0 * 64 * x.numel() / (t_ms * 1e-3) / 1e12,
+                       "note": "28 flop/B: 3xTF32 on tcgen05 keeps the pass HBM-bound; tensor-pipe utilisation in profiles/"}
+    # unmodified reference driver on the backend
+    try:
+        tl = tb.import_tensorly()
+        tl.set_backend("pytorch")
+        tb.use()
+        from tensorly.decomposition import tucker as ref_tucker
+
+        def timed(k):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            _, errs = ref_tucker(x, ranks, n_iter_max=k, init="random", random_state=1, tol=0, return_errors=True)
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0, float(errs[-1])
+        timed(1)
+        ta, _ = timed(1)
+        tb_, e_ref = timed(4)
+        out["reference_driver_on_b200"] = {"value": 3.0 / max(tb_ - ta, 1e-9), "unit": UNIT, "final_rel_error_4_sweeps": e_ref,
+                                           "what": "tensorly.decomposition.tucker (unmodified, torch.linalg.svd) on tenalg 'b200'"}
+        tb.use_gram_svd()
+        try:
+            timed(1)
+            ta, _ = timed(1)
+            tb_, _ = timed(4)
+            out["reference_driver_on_b200"]["value_gram_svd"] = 3.0 / max(tb_ - ta, 1e-9)
+        finally:
+            tb.use_default_svd()
+        # same init, same number of sweeps through the own driver: the errors must agree (1e-4 gate)
+        _, errs = tb.tucker(x, ranks, n_iter_max=4, init="random", random_state=1, tol=0, return_errors=True)
+        out["parity_vs_reference_driver"] = {"own": errs[-1], "reference": e_ref, "rel_dev": abs(errs[-1] - e_ref) / e_ref,
+                                             "gate": 1e-4, "ok": abs(errs[-1] - e_ref) / e_ref <= 1e-4}
+    except Exception as exc:
+        out["reference_driver_on_b200"] = {"unavailable": str(exc)[:200]}
+    return out
+
+
 def reference_driver_leg(env, key, res):
     """The UNMODIFIED tensorly.decomposition.parafac on the b200 tenalg backend (delta-iterations timing)."""
     import torch
@@ -749,6 +832,7 @@ def run_ours(args):
         del r2
         torch.cuda.empty_cache()
     fp64 = fp64_leg(env) if (env.rank == 0 and env.world == 1 and not args.no_fp64) else None
+    c3 = tucker_leg(env, args.steps) if (env.rank == 0 and env.world == 1 and not args.no_c3) else None
     clocks = env.sampler.stop() if env.sampler else None
 
     # ---- CPU baselines on the host cores (rank 0, N=1 only), bounded samples ---------------
@@ -790,6 +874,7 @@ def run_ours(args):
             "final_rel_error": res["rel_err"],
             "reference_driver_on_b200": ref_driver,
             "c2": c2,
+            "c3": c3,
             "fp64": fp64,
         }
         print(json.dumps(line), flush=True)
@@ -820,9 +905,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-c2", action="store_true")
     ap.add_argument("--no-fp64", action="store_true")
+    ap.add_argument("--no-c3", action="store_true")
     ap.add_argument("--no-sustained", action="store_true")
     ap.add_argument("--no-refdriver", action="store_true")
-    ap.add_argument("--ref-budget-s", type=float, default=150.0)
+    ap.add_argument("--ref-budget-s", type=float, default=180.0)
     ap.add_argument("--cpu-budget-s", type=float, default=30.0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -245,6 +245,55 @@ int tlb200_nncp_update(const void* const* grams, int nmodes, int mode, int64_t r
                        const void* weights, const void* m, int64_t m_ld, void* f,
                        int64_t f_ld, int64_t rows, double eps, int dtype, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * CP reconstruction — replaces tensorly.cp_tensor.cp_to_tensor (tensorly/cp_tensor.py:433-485):
+ *   out[i_0..i_{N-1}] = sum_r w_r * prod_n F_n[i_n, r]      (times mask[i_0..i_{N-1}] when mask != NULL)
+ * factors[n] is (shape[n], rank) with element strides; weights (rank,) and mask (C-contiguous, `shape`) may be
+ * NULL.  out: C-contiguous `shape`, written exactly once; the Khatri-Rao matrix of the reference is never formed.
+ * 2 <= ndim <= TLB200_MAX_NDIM (a vector is the caller's 2-way case with a 1 x rank factor of ones).
+ * ------------------------------------------------------------------------- */
+int tlb200_cp_to_tensor(const void* const* factors, const int64_t* shape,
+                        const int64_t* f_row_stride, const int64_t* f_col_stride, int ndim,
+                        int64_t rank, const void* weights, const void* mask, int dtype,
+                        void* out, void* stream);
+
+/* Masked-ALS imputation and error in ONE pass over the tensor — replaces the mask branch of error_calc
+ * (tensorly/decomposition/_cp.py:195-207: cp_to_tensor, tensor*mask + rec*(1-mask), tl.norm twice):
+ *   out   = x * mask + rec * (1 - mask)             (out may alias x; mask: 1 = observed, 0 = missing)
+ *   stats = [ ||out - rec|| / ||out||,  ||out||^2,  ||out - rec||^2 ]      (3 device scalars of `dtype`,
+ *           accumulated in double, fixed summation order)
+ * rec is formed in registers and never stored. */
+size_t tlb200_cp_impute_workspace_bytes(const int64_t* shape, int ndim);
+
+int tlb200_cp_impute(const void* x, const void* mask, const void* const* factors,
+                     const int64_t* shape, const int64_t* f_row_stride,
+                     const int64_t* f_col_stride, int ndim, int64_t rank, const void* weights,
+                     int dtype, void* out, void* stats, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Orthonormal basis of the span of a tall block — the truncated "SVD" step of the own HOOI driver, replacing
+ * svd_interface(unfold(core_approximation, mode), n_eigenvecs=rank) inside the loop of
+ * tensorly/decomposition/_tucker.py:197-201 (-> tensorly/tenalg/svd.py:211-235) together with warm-started
+ * subspace iteration on the Gram matrix of the unfolding (tensorly_b200/tucker_hooi.py):
+ *   out = Z R^{-1},  R^T R = Z^T Z   (Cholesky-QR; Gram, Cholesky factor and inverse in fp64)
+ * z: (rows, rank) with element strides, rank <= 64 <= ... <= rows; out: (rows, rank), row stride out_ld.
+ * The first 8 bytes of `workspace` are a ticket counter and a status word: the counter must be zero before the
+ * first call and is left zero; status (second int) is 1 when the block was numerically rank deficient.
+ * ------------------------------------------------------------------------- */
+size_t tlb200_orthonormalize_workspace_bytes(int64_t rows, int64_t rank);
+
+int tlb200_orthonormalize(const void* z, int64_t rows, int64_t rank, int64_t row_stride,
+                          int64_t col_stride, int dtype, void* out, int64_t out_ld,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Eigendecomposition of a small symmetric matrix (n <= 64): cyclic Jacobi with parallel ordering in fp64, one CTA.
+ * evals (n) in DESCENDING order, evecs (n x n, row stride ldv) with the eigenvectors as columns.  The Rayleigh-Ritz
+ * step of the HOOI subspace iteration (it replaces the ordering that the SVD of tensorly/tenalg/svd.py:211-235
+ * provides); a is read as (a + a^T) / 2. */
+int tlb200_symeig(const void* a, int64_t n, int64_t lda, int dtype, void* evals, void* evecs,
+                  int64_t ldv, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

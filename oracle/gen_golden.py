@@ -236,7 +236,99 @@ def gen_als():
     save("als", **d)
 
 
+def gen_round2():
+    """Round-2 fixtures (SURVEY 8(f) n4 + the NNDSVD initialisation): reconstruction, masked ALS, HALS."""
+    from tensorly.decomposition import non_negative_parafac_hals
+    from tensorly.decomposition._cp import initialize_cp
+    from tensorly.solvers.nnls import hals_nnls
+    d = {}
+    rng = np.random.RandomState(31)
+    # cp_to_tensor (tensorly/cp_tensor.py:433-485)
+    for tag, shape, rank, dt, wts in (("rec_a", (9, 8, 7), 4, np.float64, True), ("rec_b", (40, 33, 21), 16, np.float32, False),
+                                      ("rec_c", (12, 10, 9, 8), 5, np.float32, True), ("rec_d", (130, 70), 9, np.float64, True),
+                                      ("rec_e", (7,), 3, np.float64, True), ("rec_f", (33, 5, 3, 4, 6), 40, np.float32, True)):
+        fs = [(rng.random_sample((s, rank)) - 0.3).astype(dt) for s in shape]
+        w = (rng.random_sample(rank) + 0.5).astype(dt) if wts else None
+        for i, f in enumerate(fs):
+            d[f"{tag}/f{i}"] = f
+        if w is not None:
+            d[f"{tag}/w"] = w
+        d[f"{tag}/out"] = np.ascontiguousarray(tl.cp_to_tensor((w, fs)))
+    # masked parafac (decomposition/_cp.py:195-207, :442-445): 20 % of the entries missing
+    for tag, shape, rank, dt, iters in (("mask64", (18, 15, 12), 3, np.float64, 8), ("mask32", (30, 25, 20), 4, np.float32, 6),
+                                        ("mask4way", (10, 9, 8, 7), 3, np.float64, 5)):
+        gt = tlrandom.random_cp(shape, rank, random_state=5, normalise_factors=False)
+        x = (tl.cp_to_tensor(gt) + 0.01 * rng.standard_normal(shape)).astype(dt)
+        mask = (rng.random_sample(shape) > 0.2).astype(dt)
+        x = x * mask                      # missing entries start at zero
+        init = tlrandom.random_cp(shape, rank, random_state=1, normalise_factors=False)
+        init = CPTensor((init.weights.astype(dt), [f.astype(dt) for f in init.factors]))
+        cp, errs = parafac(x, rank, n_iter_max=iters, init=init.cp_copy(), tol=0, return_errors=True, mask=mask)
+        d[f"{tag}/x"] = x
+        d[f"{tag}/mask"] = mask
+        d[f"{tag}/rank"] = np.array(rank)
+        d[f"{tag}/iters"] = np.array(iters)
+        for i, f in enumerate(init.factors):
+            d[f"{tag}/init{i}"] = f
+        for i, f in enumerate(cp.factors):
+            d[f"{tag}/f{i}"] = f
+        d[f"{tag}/errors"] = np.array([float(e) for e in errs])
+    # hals_nnls (solvers/nnls.py:5-175) on its own
+    for tag, r, n, dt in (("hals_a", 6, 40, np.float64), ("hals_b", 32, 300, np.float32), ("hals_c", 64, 129, np.float32)):
+        U = rng.random_sample((80, r)).astype(dt)
+        M = rng.random_sample((80, n)).astype(dt)
+        V0 = rng.random_sample((r, n)).astype(dt)
+        UtM, UtU = U.T @ M, U.T @ U
+        d[f"{tag}/UtM"], d[f"{tag}/UtU"], d[f"{tag}/V0"] = UtM, UtU, V0
+        d[f"{tag}/V"] = hals_nnls(UtM.copy(), UtU.copy(), V0.copy(), n_iter_max=100)
+        d[f"{tag}/V_sparse"] = hals_nnls(UtM.copy(), UtU.copy(), V0.copy(), n_iter_max=20, sparsity_coefficient=0.05,
+                                         ridge_coefficient=0.1, epsilon=1e-6)
+    # non_negative_parafac_hals (decomposition/_nn_cp.py:186-379)
+    for tag, shape, rank, dt, iters in (("nnhals64", (14, 12, 10), 4, np.float64, 6), ("nnhals32", (24, 20, 16), 5, np.float32, 5)):
+        x = tlrandom.random_tensor(shape, random_state=0).astype(dt)
+        init = tlrandom.random_cp(shape, rank, random_state=1, normalise_factors=False)
+        init = CPTensor((init.weights.astype(dt), [f.astype(dt) for f in init.factors]))
+        cp, errs = non_negative_parafac_hals(x, rank, n_iter_max=iters, init=init.cp_copy(), tol=1e-30, return_errors=True)
+        d[f"{tag}/x"] = x
+        d[f"{tag}/rank"] = np.array(rank)
+        d[f"{tag}/iters"] = np.array(iters)
+        for i, f in enumerate(init.factors):
+            d[f"{tag}/init{i}"] = f
+        for i, f in enumerate(cp.factors):
+            d[f"{tag}/f{i}"] = f
+        d[f"{tag}/errors"] = np.array([float(e) for e in errs])
+    # non_negative_parafac with the default init='svd' (NNDSVDA through svd_interface, tenalg/svd.py:68-135)
+    shape, rank = (16, 14, 12), 4
+    x = tlrandom.random_tensor(shape, random_state=3).astype(np.float64)
+    kt = initialize_cp(x, rank, init="svd", non_negative=True)
+    cp, errs = non_negative_parafac(x, rank, n_iter_max=8, init="svd", tol=1e-30, return_errors=True)
+    d["nnsvd/x"] = x
+    d["nnsvd/rank"] = np.array(rank)
+    for i, f in enumerate(kt.factors):
+        d[f"nnsvd/init{i}"] = np.array(f)
+    d["nnsvd/errors"] = np.array([float(e) for e in errs])
+    # tucker with init='svd' (the default) for the own HOOI driver; tucker_to_tensor of the result
+    shape, ranks = (24, 20, 22), [5, 4, 6]
+    gtc = rng.standard_normal(ranks)
+    gtf = [np.linalg.qr(rng.standard_normal((s, r)))[0] for s, r in zip(shape, ranks)]
+    x = (multi_mode_dot(gtc, gtf) + 0.05 * rng.standard_normal(shape)).astype(np.float64)
+    (core, factors), errs = tucker(x, ranks, n_iter_max=6, init="svd", tol=0, return_errors=True)
+    d["tucker_svd/x"] = x
+    d["tucker_svd/ranks"] = np.array(ranks)
+    d["tucker_svd/errors"] = np.array([float(e) for e in errs])
+    d["tucker_svd/rec"] = np.ascontiguousarray(tl.tucker_to_tensor((core, factors)))
+    x2 = tlrandom.random_tensor((26, 24, 28), random_state=0).astype(np.float32)
+    (core, factors), errs = tucker(x2, [6, 5, 7], n_iter_max=8, init="svd", tol=0, return_errors=True)
+    d["tucker_svd32/x"] = x2
+    d["tucker_svd32/ranks"] = np.array([6, 5, 7])
+    d["tucker_svd32/errors"] = np.array([float(e) for e in errs])
+    save("round2", **d)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":      # the round-1 fixtures stay byte-identical
+        gen_round2()
+        sys.exit(0)
     gen_unfold()
     gen_khatri_rao()
     gen_mttkrp()

@@ -219,6 +219,94 @@ def parafac(tensor, init, n_iter_max=10, l2_reg=0.0, return_errors=True):
     return (weights, factors), rec_errors
 
 
+def cp_impute(tensor, mask, cp_tensor):
+    """The mask branch of error_calc, tensorly/decomposition/_cp.py:195-207: returns the imputed tensor,
+    its norm and the unnormalised error ||tensor_new - rec||."""
+    low_rank = cp_to_tensor(cp_tensor)
+    tensor = tensor * mask + low_rank * (1 - mask)
+    return tensor, tensor_norm(tensor), tensor_norm(tensor - low_rank)
+
+
+def parafac_masked(tensor, mask, init, n_iter_max=10):
+    """tensorly/decomposition/_cp.py:394-478 with a mask (1 = observed), init=(weights, factors), tol=0,
+    return_errors=True: the factor updates run on the current (imputed) tensor, then error_calc re-imputes the
+    missing entries from the new factors, recomputes the tensor norm and reports ||tensor - rec|| / ||tensor||."""
+    weights, factors = init
+    factors = [np.array(f, copy=True) for f in factors]
+    rank = factors[0].shape[1]
+    dtype = tensor.dtype
+    weights = np.ones(rank, dtype=dtype) if weights is None else np.array(weights, dtype=dtype)
+    tensor = np.array(tensor, copy=True)
+    rec_errors = []
+    for _ in range(n_iter_max):
+        for mode in range(tensor.ndim):
+            pinv = np.ones((rank, rank), dtype=dtype)
+            for i, f in enumerate(factors):
+                if i != mode:
+                    pinv = pinv * np.dot(np.conj(np.transpose(f)), f)
+            pinv = np.reshape(weights, (-1, 1)) * pinv * np.reshape(weights, (1, -1))
+            mttkrp = unfolding_dot_khatri_rao(tensor, (weights, factors), mode)
+            factors[mode] = np.transpose(np.linalg.solve(np.conj(np.transpose(pinv)), np.transpose(mttkrp)))
+        tensor, norm_tensor, unnorm = cp_impute(tensor, mask, (weights, factors))
+        rec_errors.append(unnorm / norm_tensor)
+    return (weights, factors), rec_errors, tensor
+
+
+def hals_nnls(UtM, UtU, V, n_iter_max=500, tol=1e-8, sparsity_coefficient=None, ridge_coefficient=None, epsilon=0.0):
+    """tensorly/solvers/nnls.py:139-173 for a given V (nonzero_rows=False, exact=False, no callback).  Note the
+    reference's stopping statistic: `tl.norm(V - newV) ** 2` subtracts the new ROW from the whole matrix
+    (broadcast), i.e. sum_{l, j} (V[l, j] - newV[j])^2 — restated as is."""
+    V = np.array(V, copy=True)
+    rank = UtM.shape[0]
+    rec_error0 = None
+    for iteration in range(n_iter_max):
+        rec_error = 0
+        for k in range(rank):
+            if UtU[k, k]:
+                num = UtM[k, :] - np.dot(UtU[k, :], V) + UtU[k, k] * V[k, :]
+                den = UtU[k, k]
+                if sparsity_coefficient is not None:
+                    num = num - sparsity_coefficient
+                if ridge_coefficient is not None:
+                    den = den + 2 * ridge_coefficient
+                newV = np.clip(num / den, epsilon, None)
+                rec_error += np.sqrt(np.sum(np.abs(V - newV) ** 2)) ** 2
+                V[k, :] = newV
+        if iteration == 0:
+            rec_error0 = rec_error
+        if rec_error < tol * rec_error0:
+            break
+    return V
+
+
+def non_negative_parafac_hals(tensor, init, n_iter_max=10, return_errors=True):
+    """tensorly/decomposition/_nn_cp.py:307-379 (nn_modes='all', no sparsity, exact=False, fixed_modes=[],
+    normalize_factors=False, tol truthy) for init=(weights, factors)."""
+    weights, factors = init
+    factors = [np.array(f, copy=True) for f in factors]
+    rank = factors[0].shape[1]
+    dtype = tensor.dtype
+    weights = np.ones(rank, dtype=dtype) if weights is None else np.array(weights, dtype=dtype)
+    norm_tensor = tensor_norm(tensor)
+    rec_errors = []
+    for _ in range(n_iter_max):
+        mttkrp = None
+        for mode in range(tensor.ndim):
+            pinv = np.ones((rank, rank), dtype=dtype)
+            for i, f in enumerate(factors):
+                if i != mode:
+                    pinv = pinv * np.dot(np.transpose(f), f)
+            pinv = np.reshape(weights, (-1, 1)) * pinv * np.reshape(weights, (1, -1))
+            mttkrp = unfolding_dot_khatri_rao(tensor, (weights, factors), mode)
+            nn = hals_nnls(np.transpose(mttkrp), pinv, np.transpose(factors[mode]), n_iter_max=100)
+            factors[mode] = np.transpose(nn)
+        if return_errors:
+            factors_norm = cp_norm((weights, factors))
+            iprod = np.sum(np.sum(mttkrp * factors[-1], axis=0))
+            rec_errors.append(np.sqrt(np.abs(norm_tensor ** 2 + factors_norm ** 2 - 2 * iprod)) / norm_tensor)
+    return (weights, factors), rec_errors
+
+
 def non_negative_parafac(tensor, init, n_iter_max=10, return_errors=True):
     """tensorly/decomposition/_nn_cp.py:107-152 (multiplicative updates, no mask,
     fixed_modes=[], normalize_factors=False) for init=(weights, factors)."""

@@ -612,3 +612,146 @@ def cp_error(grams, weights, mttkrp_last: torch.Tensor, factor_last: torch.Tenso
                                  out.data_ptr(), _stream(mttkrp_last))
     _lib.check(st, "cp_error")
     return out
+
+
+# --------------------------------------------------------------------------- reconstruction
+def _check_cp(cp_tensor, what: str):
+    """(weights | None, factors) -> (w tensor | None, factors, shape, rank) with the reference's validation
+    (tensorly/cp_tensor.py:163-214): matrices with one common column count, weights of that length."""
+    weights, factors = cp_tensor
+    factors = list(factors)
+    if len(factors) < 1:
+        raise ValueError(f"{what}: a CP tensor needs at least one factor")
+    first = _check_tensor(factors[0], "factors[0]")
+    for i, f in enumerate(factors):
+        _check_tensor(f, f"factors[{i}]", first)
+        if f.dim() != 2:
+            raise ValueError("A CP tensor should be composed of a list of matrices,"
+                             f"but factor {i} has {f.dim()} dimensions.")
+        if f.shape[1] != first.shape[1]:
+            raise ValueError("All the factors of a CP tensor should have the same number of column."
+                             f"However, factors[0].shape[1]={first.shape[1]} but factors[{i}].shape[1]={f.shape[1]}.")
+    rank = first.shape[1]
+    w = None
+    if weights is not None:
+        w = torch.as_tensor(weights, dtype=first.dtype, device=first.device).reshape(-1).contiguous()
+        if w.numel() != rank:
+            raise ValueError(f"Given factors for a rank-{rank} CP tensor but len(weights)={w.numel()}.")
+    return w, factors, tuple(f.shape[0] for f in factors), rank
+
+
+def cp_to_tensor(cp_tensor, mask=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Full tensor of a CP decomposition (tensorly/cp_tensor.py:433-485): sum_r w_r a_r o b_r o c_r ..., written
+    once, without the reference's Khatri-Rao matrix.  `mask` (an array with as many entries as the tensor)
+    multiplies the result element-wise — the evident intent of the reference's `mask` branch, whose
+    `khatri_rao(..., mask=mask)` only accepts a column of prod(shape) entries."""
+    w, factors, shape, rank = _check_cp(cp_tensor, "cp_to_tensor")
+    first = factors[0]
+    vector = len(shape) == 1
+    if vector:                 # reference: sum(weights * factors[0], axis=1); here the 2-way case with a row of ones
+        factors = factors + [torch.ones((1, rank), dtype=first.dtype, device=first.device)]
+        shape = shape + (1,)
+    if len(shape) > _lib.MAX_NDIM:
+        raise ValueError(f"cp_to_tensor supports at most {_lib.MAX_NDIM} modes")
+    mk = None
+    if mask is not None:
+        mk = torch.as_tensor(mask, device=first.device).to(first.dtype).contiguous()
+        if mk.numel() != _prod(shape):
+            raise ValueError(f"mask has {mk.numel()} entries but the tensor has {_prod(shape)}")
+    if out is None:
+        out = torch.empty(shape, dtype=first.dtype, device=first.device)
+    else:
+        _check_tensor(out, "out", first)
+        if tuple(out.shape) != shape or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous tensor of shape {shape}")
+    if out.numel() > 0:
+        lib = _lib.load()
+        with _Device(first):
+            st = lib.tlb200_cp_to_tensor(_lib.ptr_array(f.data_ptr() for f in factors), _lib.i64_array(shape),
+                                         _lib.i64_array(f.stride(0) for f in factors),
+                                         _lib.i64_array(f.stride(1) for f in factors), len(shape), rank,
+                                         w.data_ptr() if w is not None else None,
+                                         mk.data_ptr() if mk is not None else None, _DTYPES[first.dtype],
+                                         out.data_ptr(), _stream(first))
+        _lib.check(st, "cp_to_tensor")
+    return out.reshape(shape[0]) if vector else out
+
+
+def cp_impute(tensor: torch.Tensor, mask: torch.Tensor, cp_tensor, out: torch.Tensor | None = None,
+              stats: torch.Tensor | None = None):
+    """Masked-ALS imputation step (tensorly/decomposition/_cp.py:195-207) in one pass:
+    out = tensor * mask + cp_to_tensor(cp_tensor) * (1 - mask) (`out` may be `tensor` itself), and
+    stats = [||out - rec|| / ||out||, ||out||^2, ||out - rec||^2] as device scalars.  Returns (out, stats)."""
+    _check_tensor(tensor, "tensor")
+    w, factors, shape, rank = _check_cp(cp_tensor, "cp_impute")
+    _check_tensor(factors[0], "factors[0]", tensor)
+    if tuple(tensor.shape) != shape:
+        raise ValueError(f"tensor has shape {tuple(tensor.shape)} but the factors describe {shape}")
+    if tensor.dim() < 2 or tensor.dim() > _lib.MAX_NDIM:
+        raise ValueError(f"cp_impute supports 2..{_lib.MAX_NDIM}-way tensors")
+    _check_tensor(mask, "mask", tensor)
+    if tuple(mask.shape) != shape:
+        raise ValueError(f"mask has shape {tuple(mask.shape)} but the tensor has shape {shape}")
+    if not tensor.is_contiguous() or not mask.is_contiguous():
+        raise ValueError("cp_impute needs C-contiguous tensor and mask")
+    if out is None:
+        out = torch.empty_like(tensor)
+    elif tuple(out.shape) != shape or not out.is_contiguous() or out.dtype != tensor.dtype:
+        raise ValueError("out must be a contiguous tensor like `tensor`")
+    if stats is None:
+        stats = torch.empty(3, dtype=tensor.dtype, device=tensor.device)
+    lib = _lib.load()
+    cshape = _lib.i64_array(shape)
+    ws = _workspace(lib.tlb200_cp_impute_workspace_bytes(cshape, len(shape)), tensor)
+    with _Device(tensor):
+        st = lib.tlb200_cp_impute(tensor.data_ptr(), mask.data_ptr(), _lib.ptr_array(f.data_ptr() for f in factors), cshape,
+                                  _lib.i64_array(f.stride(0) for f in factors),
+                                  _lib.i64_array(f.stride(1) for f in factors), len(shape), rank,
+                                  w.data_ptr() if w is not None else None, _DTYPES[tensor.dtype], out.data_ptr(),
+                                  stats.data_ptr(), ws.data_ptr(), ws.numel(), _stream(tensor))
+    _lib.check(st, "cp_impute")
+    return out, stats
+
+
+# --------------------------------------------------------------------------- HOOI pieces (SURVEY 8(f) n1)
+def orthonormalize(z: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Orthonormal basis of the column span of a tall (rows, rank <= 64) block: Cholesky-QR with the small Gram
+    matrix, its factor and inverse in fp64 (tlb200_orthonormalize)."""
+    _check_tensor(z, "z")
+    if z.dim() != 2:
+        raise ValueError("orthonormalize expects a matrix")
+    rows, rank = z.shape
+    if rows < rank:
+        raise ValueError(f"orthonormalize needs rows >= columns, got {tuple(z.shape)}")
+    if out is None:
+        out = torch.empty((rows, rank), dtype=z.dtype, device=z.device)
+    lib = _lib.load()
+    nbytes = lib.tlb200_orthonormalize_workspace_bytes(rows, rank)
+    if nbytes == 0:
+        raise ValueError(f"orthonormalize: unsupported block {tuple(z.shape)} (at most 64 columns)")
+    ws = _zero_workspace(nbytes, z)
+    with _Device(z):
+        st = lib.tlb200_orthonormalize(z.data_ptr(), rows, rank, z.stride(0), z.stride(1), _DTYPES[z.dtype], out.data_ptr(),
+                                       out.stride(0), ws.data_ptr(), ws.numel(), _stream(z))
+    _lib.check(st, "orthonormalize")
+    return out
+
+
+def symeig(a: torch.Tensor):
+    """(eigenvalues descending, eigenvectors as columns) of a small symmetric matrix (order <= 64): Jacobi in fp64 in one
+    CTA (tlb200_symeig)."""
+    _check_tensor(a, "a")
+    if a.dim() != 2 or a.shape[0] != a.shape[1]:
+        raise ValueError("symeig expects a square matrix")
+    n = a.shape[0]
+    if n > 64:
+        raise ValueError("symeig supports matrices of order <= 64")
+    ac = a if a.is_contiguous() else a.contiguous()
+    evals = torch.empty(n, dtype=a.dtype, device=a.device)
+    evecs = torch.empty((n, n), dtype=a.dtype, device=a.device)
+    lib = _lib.load()
+    with _Device(a):
+        st = lib.tlb200_symeig(ac.data_ptr(), n, ac.stride(0), _DTYPES[a.dtype], evals.data_ptr(), evecs.data_ptr(), n,
+                               _stream(a))
+    _lib.check(st, "symeig")
+    return evals, evecs

@@ -13,8 +13,8 @@ Unlike the unmodified reference loop (≈26 array-library calls and one host syn
 mode) a mode update here is 5 kernel launches with no host synchronisation, and the whole
 sweep is captured in a CUDA graph.  The unmodified reference drivers also run on the same
 kernels through the tenalg backend (tensorly_b200.use()); options that this driver does
-not implement (mask, sparsity, linesearch, orthogonalise, normalize_factors) are delegated
-to them.
+not implement (sparsity, linesearch, orthogonalise, normalize_factors) are delegated
+to them.  Missing values (`mask`) are handled here: one fused imputation + error pass per sweep.
 
 Multi-GPU (one process per GPU, torch.distributed): the tensor is sharded along
 `shard_mode` (each rank holds a contiguous slab and that mode's factor rows); every
@@ -75,6 +75,7 @@ class CudaOps:
     fused_gram = True        # cp_update(..., gram_out=) also writes the Gram of the updated factor
     nncp_update = staticmethod(_ops.nncp_update)
     cp_error = staticmethod(_ops.cp_error)
+    cp_impute = staticmethod(_ops.cp_impute)     # masked ALS: imputation + both norms in one tensor pass
     sumsq = staticmethod(_ops.sumsq)
     supports_graphs = True
 
@@ -136,7 +137,18 @@ class CPALS:
 
     def __init__(self, tensor_local: torch.Tensor, weights: torch.Tensor, factors: Sequence[torch.Tensor],
                  l2_reg: float = 0.0, update: str = "ls", fixed_modes: Sequence[int] = (), comm: Optional[_Comm] = None,
-                 shard_mode: int = 0, ops=CudaOps, eps: Optional[float] = None, dimtree: Optional[bool] = None):
+                 shard_mode: int = 0, ops=CudaOps, eps: Optional[float] = None, dimtree: Optional[bool] = None,
+                 mask: Optional[torch.Tensor] = None):
+        # Missing values (mask: 1 = observed, 0 = missing; tensorly/decomposition/_cp.py:195-207, :442-445): the
+        # driver owns a copy of the tensor whose missing entries are re-imputed from the current factors after
+        # every sweep (before every mode update for the multiplicative rule, _nn_cp.py:124-127).
+        self.mask = None
+        if mask is not None:
+            if tuple(mask.shape) != tuple(tensor_local.shape):
+                raise ValueError(f"mask has shape {tuple(mask.shape)} but the tensor has shape {tuple(tensor_local.shape)}")
+            self.mask = torch.as_tensor(mask, device=tensor_local.device).to(tensor_local.dtype).contiguous()
+            tensor_local = tensor_local.clone(memory_format=torch.contiguous_format)
+            self.stats = torch.zeros(3, dtype=tensor_local.dtype, device=tensor_local.device)
         self.x = tensor_local
         self.ops = ops
         self.comm = comm or _Comm()
@@ -169,7 +181,7 @@ class CPALS:
         can = hasattr(self.ops, "mttkrp_from_ttm") and self.ndim >= 3 and len(served) >= 2
         if dimtree is None:
             dimtree = os.environ.get("TLB200_DIMTREE", "1") != "0"
-        self.dimtree = bool(dimtree) and can
+        self.dimtree = bool(dimtree) and can and not (self.mask is not None and update == "mu")
         self._contracted: Optional[torch.Tensor] = None
         # Sharded runs: the Gram of the sharded mode's new rows (R x R partial) and the MTTKRP partial of the NEXT
         # updated mode are both all-reduced before that mode's solve, so they travel in ONE collective: the Gram
@@ -197,7 +209,18 @@ class CPALS:
         if self.shard_mode == n and not defer:
             self.comm.all_reduce(self.grams[n])
 
+    def _impute(self) -> None:
+        """tensor <- tensor * mask + rec * (1 - mask); err <- ||tensor - rec|| / ||tensor||; ||tensor||^2 refreshed."""
+        self.ops.cp_impute(self.x, self.mask, (self.weights, self.factors), out=self.x, stats=self.stats)
+        if self.shard_mode is not None:
+            self.comm.all_reduce(self.stats[1:3])          # both sums are over this rank's slab
+            self.stats[0] = torch.sqrt(self.stats[2] / self.stats[1])
+        self.err[0].copy_(self.stats[0])
+        self.norm_x2.copy_(self.stats[1:2])
+
     def _update_mode(self, mode: int) -> None:
+        if self.mask is not None and self.update == "mu":
+            self._impute()
         packed = self._pack is not None and mode == self._pack_mode
         out = self._pack_m if packed else None
         if self._contracted is not None and mode < self.ndim - 1:
@@ -239,6 +262,9 @@ class CPALS:
                 self._contracted = None       # the last factor changes now: T is stale (and its memory is free again)
             self._update_mode(mode)
         self._contracted = None
+        if self.mask is not None:
+            self._impute()           # also yields the error (no shortcut through the last MTTKRP with a mask)
+            return
         if with_error:
             if self.modes[-1] != self.ndim - 1:
                 # the fast error needs the last mode's MTTKRP with the current factors
@@ -358,6 +384,19 @@ def _init_from(init, tensor, rank):
     return torch.ones(rank, dtype=tensor.dtype, device=tensor.device), factors
 
 
+def _reference_init(tensor, rank, svd, non_negative, random_state, mask, svd_mask_repeats):
+    """initialize_cp of the reference (tensorly/decomposition/_cp.py:26-152) on the pytorch backend."""
+    from .backend import import_tensorly, use
+    tl = import_tensorly()
+    if tl.get_backend() != "pytorch":
+        tl.set_backend("pytorch")
+    use()
+    from tensorly.decomposition._cp import initialize_cp
+    kt = initialize_cp(tensor, rank, init="svd", svd=svd, non_negative=non_negative, random_state=random_state,
+                       mask=torch.as_tensor(mask, device=tensor.device).to(tensor.dtype), svd_mask_repeats=svd_mask_repeats)
+    return torch.ones(rank, dtype=tensor.dtype, device=tensor.device), [f.contiguous() for f in kt.factors]
+
+
 def _delegate(name, tensor, rank, kwargs):
     from .backend import import_tensorly, use
     tl = import_tensorly()
@@ -369,7 +408,8 @@ def _delegate(name, tensor, rank, kwargs):
 
 
 def _run(tensor, rank, n_iter_max, init, svd, tol, random_state, verbose, return_errors, l2_reg, cvg_criterion,
-         fixed_modes, callback, update, group, shard_mode, ops, use_graph, sharded=None):
+         fixed_modes, callback, update, group, shard_mode, ops, use_graph, sharded=None, mask=None,
+         svd_mask_repeats=5):
     if not isinstance(tensor, torch.Tensor):
         raise TypeError("tensor must be a torch.Tensor")
     comm = _Comm(group, sharded)
@@ -395,7 +435,12 @@ def _run(tensor, rank, n_iter_max, init, svd, tol, random_state, verbose, return
         elif init == "svd":
             if comm.active:
                 raise NotImplementedError("init='svd' is not available for a sharded tensor; pass init='random' or factors")
-            weights, factors = _svd_init(tensor, rank, random_state, non_negative=non_negative)
+            if mask is not None:
+                # SVD of an incomplete tensor: the reference imputes inside svd_interface (tenalg/svd.py:431-439);
+                # initialisation is not on the hot path, so it is the reference's own routine that runs
+                weights, factors = _reference_init(tensor, rank, svd, non_negative, random_state, mask, svd_mask_repeats)
+            else:
+                weights, factors = _svd_init(tensor, rank, random_state, non_negative=non_negative)
             if non_negative:
                 factors = [torch.abs(f) for f in factors]
         else:
@@ -413,7 +458,7 @@ def _run(tensor, rank, n_iter_max, init, svd, tol, random_state, verbose, return
                       "Consider using tl.moveaxis()")
         fixed_modes.remove(ndim - 1)
     state = CPALS(tensor, weights, factors, l2_reg=l2_reg, update=update, fixed_modes=fixed_modes, comm=comm,
-                  shard_mode=shard_mode, ops=ops)
+                  shard_mode=shard_mode, ops=ops, mask=mask)
     want_err = bool(tol) or return_errors
     err_hist = torch.zeros(max(n_iter_max, 1), dtype=tensor.dtype, device=tensor.device)
     rec_errors: List[float] = []
@@ -463,16 +508,16 @@ def parafac(tensor, rank, n_iter_max=100, init="svd", svd="truncated_svd", norma
     LOCAL slab of the tensor along `shard_mode`; without either the tensor is decomposed on this GPU alone, also
     inside a multi-rank job.  `use_graph=False` disables CUDA graphs.
     """
-    if normalize_factors or orthogonalise or sparsity or mask is not None or linesearch or svd != "truncated_svd":
+    if normalize_factors or orthogonalise or sparsity or linesearch or svd != "truncated_svd":
         if _Comm(group, sharded).active:
-            raise NotImplementedError("normalize_factors/orthogonalise/sparsity/mask/linesearch are not available sharded")
+            raise NotImplementedError("normalize_factors/orthogonalise/sparsity/linesearch are not available sharded")
         return _delegate("parafac", tensor, rank, dict(
             n_iter_max=n_iter_max, init=init, svd=svd, normalize_factors=normalize_factors, orthogonalise=orthogonalise,
             tol=tol, random_state=random_state, verbose=verbose, return_errors=return_errors, sparsity=sparsity,
             l2_reg=l2_reg, mask=mask, cvg_criterion=cvg_criterion, fixed_modes=fixed_modes,
             svd_mask_repeats=svd_mask_repeats, linesearch=linesearch, callback=callback))
     return _run(tensor, rank, n_iter_max, init, svd, tol, random_state, verbose, return_errors, l2_reg, cvg_criterion,
-                fixed_modes, callback, "ls", group, shard_mode, ops, use_graph, sharded)
+                fixed_modes, callback, "ls", group, shard_mode, ops, use_graph, sharded, mask, svd_mask_repeats)
 
 
 def non_negative_parafac(tensor, rank, n_iter_max=100, init="svd", svd="truncated_svd", tol=10e-7, random_state=None,
@@ -481,12 +526,12 @@ def non_negative_parafac(tensor, rank, n_iter_max=100, init="svd", svd="truncate
                          ops=CudaOps, use_graph=True):
     """Non-negative CP by multiplicative updates — same signature and semantics as
     tensorly.decomposition.non_negative_parafac (tensorly/decomposition/_nn_cp.py:26)."""
-    if normalize_factors or mask is not None or svd != "truncated_svd":
+    if normalize_factors or svd != "truncated_svd":
         if _Comm(group, sharded).active:
-            raise NotImplementedError("normalize_factors/mask are not available sharded")
+            raise NotImplementedError("normalize_factors is not available sharded")
         return _delegate("non_negative_parafac", tensor, rank, dict(
             n_iter_max=n_iter_max, init=init, svd=svd, tol=tol, random_state=random_state, verbose=verbose,
             normalize_factors=normalize_factors, return_errors=return_errors, mask=mask, cvg_criterion=cvg_criterion,
             fixed_modes=fixed_modes))
     return _run(tensor, rank, n_iter_max, init, svd, tol, random_state, verbose, return_errors, 0.0, cvg_criterion,
-                fixed_modes, None, "mu", group, shard_mode, ops, use_graph, sharded)
+                fixed_modes, None, "mu", group, shard_mode, ops, use_graph, sharded, mask)

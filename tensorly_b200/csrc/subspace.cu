@@ -1,0 +1,301 @@
+// Orthonormalisation of a tall block of vectors — the "SVD" of the own HOOI driver.
+//
+// The reference's HOOI takes the leading left singular vectors of every mode unfolding of the projected tensor
+// with a full LAPACK/cuSOLVER SVD (tensorly/decomposition/_tucker.py:197-201 -> tenalg/svd.py:211-235).  HOOI
+// only needs an orthonormal basis of the dominant subspace, so the own driver runs warm-started subspace
+// iteration  U <- orth(G U)  on the small Gram matrix G = Y_(k) Y_(k)^T (both products on the existing TTM
+// kernels) and this file supplies `orth`: Cholesky-QR with the R x R Gram, its Cholesky factor and the
+// triangular inverse in fp64 — exact enough for blocks whose condition number squared exceeds 1/eps(fp32),
+// which G U reaches after a single power step on tensors with a dominant mean component.
+//
+//   kernel 1  partial Grams of 64-row blocks (fp64 accumulation); the last CTA to arrive sums them in block
+//             order, factors S = R^T R in shared memory and writes R^{-1} (upper triangular, fp64).
+//   kernel 2  Q = Z R^{-1}: one thread per row, the row in registers, R^{-1} broadcast from shared memory.
+// Latency-bound R x R work (R <= 64); deterministic.
+#include "common.cuh"
+
+namespace tlb200 {
+namespace {
+
+constexpr int OR_MAX = 64;        // widest block
+constexpr int OR_ROWS = 64;       // rows per CTA in kernel 1
+constexpr int OR_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(OR_THREADS)
+orth_gram_chol_kernel(const T* __restrict__ z, int64_t rows, int R, int64_t rs, int64_t cs, double* __restrict__ partial,
+                      unsigned* __restrict__ counter, double* __restrict__ rinv, int* __restrict__ status) {
+    // dynamic shared memory: [Zs | S]; R^{-1} later reuses the Zs block (the row tile is dead by then)
+    extern __shared__ __align__(16) unsigned char orth_smem[];
+    typedef double Row[OR_MAX + 1];
+    Row* Zs = reinterpret_cast<Row*>(orth_smem);
+    Row* S = Zs + OR_ROWS;
+    Row* Ri = Zs;
+    static_assert(OR_ROWS >= OR_MAX, "R^{-1} aliases the row tile");
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * OR_ROWS;
+    for (int e = tid; e < OR_ROWS * R; e += OR_THREADS) {
+        int rr, c;
+        if (cs <= rs) { rr = e / R; c = e - rr * R; } else { c = e / OR_ROWS; rr = e - c * OR_ROWS; }
+        const int64_t gr = row0 + rr;
+        Zs[rr][c] = gr < rows ? (double)z[gr * rs + c * cs] : 0.0;
+    }
+    __syncthreads();
+    double* mine = partial + (size_t)blockIdx.x * R * R;
+    for (int e = tid; e < R * R; e += OR_THREADS) {
+        const int a = e / R, b = e - a * R;
+        double acc = 0.0;
+#pragma unroll 8
+        for (int i = 0; i < OR_ROWS; ++i) acc = fma(Zs[i][a], Zs[i][b], acc);
+        mine[e] = acc;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int e = tid; e < R * R; e += OR_THREADS) {
+        double acc = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) acc += __ldcg(partial + (size_t)b * R * R + e);
+        S[e / R][e % R] = acc;
+    }
+    __syncthreads();
+    // Cholesky S = R^T R (upper R, stored in the upper triangle of S), right-looking; thread t owns column t
+    int bad = 0;
+    for (int k = 0; k < R; ++k) {
+        if (tid == 0) {
+            double d = S[k][k];
+            if (!(d > 0.0)) { d = 1e-300; bad = 1; }      // rank-deficient block: keep going, report it
+            S[k][k] = sqrt(d);
+        }
+        __syncthreads();
+        const double dk = S[k][k];
+        if (tid > k && tid < R) S[k][tid] /= dk;
+        __syncthreads();
+        // trailing update: S[i][j] -= R[k][i] * R[k][j], k < i <= j
+        for (int e = tid; e < R * R; e += OR_THREADS) {
+            const int i = e / R, j = e - i * R;
+            if (i > k && j >= i) S[i][j] -= S[k][i] * S[k][j];
+        }
+        __syncthreads();
+    }
+    // R^{-1}: column c of the inverse by back substitution, one thread per column
+    if (tid < R) {
+        const int c = tid;
+        for (int i = R - 1; i >= 0; --i) {
+            double v = i == c ? 1.0 : 0.0;
+            if (i <= c) {
+                for (int j = i + 1; j <= c; ++j) v -= S[i][j] * Ri[j][c];
+                v /= S[i][i];
+            } else {
+                v = 0.0;
+            }
+            Ri[i][c] = v;
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < R * R; e += OR_THREADS) rinv[e] = Ri[e / R][e % R];
+    if (tid == 0) { *status = bad; *counter = 0u; }
+}
+
+template <typename T, int RM>
+__global__ void __launch_bounds__(128)
+orth_apply_kernel(const T* __restrict__ z, int64_t rows, int R, int64_t rs, int64_t cs, const double* __restrict__ rinv,
+                  T* __restrict__ out, int64_t out_ld) {
+    __shared__ double Ri[RM * RM];
+    for (int e = threadIdx.x; e < RM * RM; e += 128) {
+        const int i = e / RM, j = e - i * RM;
+        Ri[e] = (i < R && j < R) ? rinv[i * R + j] : 0.0;
+    }
+    __syncthreads();
+    const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (row >= rows) return;
+    double zr[RM];
+#pragma unroll
+    for (int i = 0; i < RM; ++i) zr[i] = i < R ? (double)z[row * rs + i * cs] : 0.0;
+#pragma unroll 4
+    for (int j = 0; j < RM; ++j) {
+        if (j >= R) break;
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < RM; ++i) acc = fma(zr[i], Ri[i * RM + j], acc);     // R^{-1} is upper triangular: zeros below
+        out[row * out_ld + j] = (T)acc;
+    }
+}
+
+// ---- symmetric eigendecomposition of a small matrix (n <= 64): cyclic Jacobi, parallel ordering --------------
+// One CTA.  A round rotates n/2 disjoint index pairs (round-robin "circle" schedule, n - 1 rounds per sweep):
+// angles from the current A, rows of all pairs, then columns of A and of the eigenvector matrix V.  Sweeps repeat
+// until off(A)^2 <= 1e-30 ||A||^2 (fp64) or 30 sweeps.  Output: eigenvalues in DESCENDING order, eigenvectors as
+// columns, in the caller's dtype.  Used for the Rayleigh-Ritz step of the HOOI subspace iteration.
+constexpr int EIG_MAX = 64;
+constexpr int EIG_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(EIG_THREADS)
+symeig_jacobi_kernel(const T* __restrict__ a, int n, int64_t lda, T* __restrict__ evals, T* __restrict__ evecs,
+                     int64_t ldv) {
+    extern __shared__ __align__(16) unsigned char eig_smem[];       // A | V, (EIG_MAX x (EIG_MAX + 1)) doubles each
+    typedef double ERow[EIG_MAX + 1];
+    ERow* A = reinterpret_cast<ERow*>(eig_smem);
+    ERow* V = A + EIG_MAX;
+    __shared__ double cs_c[EIG_MAX / 2], cs_s[EIG_MAX / 2];
+    __shared__ int pr_p[EIG_MAX / 2], pr_q[EIG_MAX / 2];
+    __shared__ double red[EIG_THREADS / 32];
+    __shared__ double s_off, s_tot;
+    __shared__ int order[EIG_MAX];
+    const int tid = threadIdx.x;
+    const int m = (n + 1) & ~1;                  // even working size; the padding index never rotates (zero couplings)
+    for (int e = tid; e < m * m; e += EIG_THREADS) {
+        const int i = e / m, j = e - i * m;
+        // symmetrise the input: the caller's matrix is U^T G U up to rounding
+        A[i][j] = (i < n && j < n) ? 0.5 * ((double)a[i * lda + j] + (double)a[j * lda + i]) : 0.0;
+        V[i][j] = i == j ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const int half = m / 2;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        // convergence test
+        double off = 0.0, tot = 0.0;
+        for (int e = tid; e < m * m; e += EIG_THREADS) {
+            const int i = e / m, j = e - i * m;
+            const double v = A[i][j] * A[i][j];
+            tot += v;
+            if (i != j) off += v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { off += __shfl_xor_sync(0xffffffffu, off, o); tot += __shfl_xor_sync(0xffffffffu, tot, o); }
+        if ((tid & 31) == 0) red[tid >> 5] = off;
+        __syncthreads();
+        if (tid == 0) { double t = 0.0; for (int i = 0; i < EIG_THREADS / 32; ++i) t += red[i]; s_off = t; }
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = tot;
+        __syncthreads();
+        if (tid == 0) { double t = 0.0; for (int i = 0; i < EIG_THREADS / 32; ++i) t += red[i]; s_tot = t; }
+        __syncthreads();
+        if (s_off <= 1e-30 * s_tot) break;
+        for (int r = 0; r < m - 1; ++r) {
+            if (tid < half) {
+                int p, q;
+                if (tid == 0) { p = m - 1; q = r; }
+                else { p = (r + tid) % (m - 1); q = (r - tid + (m - 1)) % (m - 1); }
+                if (p > q) { const int t = p; p = q; q = t; }
+                double c = 1.0, sn = 0.0;
+                const double apq = A[p][q];
+                if (fabs(apq) > 1e-300) {
+                    const double tau = (A[q][q] - A[p][p]) / (2.0 * apq);
+                    const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                    c = 1.0 / sqrt(1.0 + t * t);
+                    sn = t * c;
+                }
+                pr_p[tid] = p; pr_q[tid] = q; cs_c[tid] = c; cs_s[tid] = sn;
+            }
+            __syncthreads();
+            // rows: A <- J^T A
+            for (int e = tid; e < half * m; e += EIG_THREADS) {
+                const int pi = e / m, k = e - pi * m;
+                const int p = pr_p[pi], q = pr_q[pi];
+                const double c = cs_c[pi], sn = cs_s[pi];
+                const double ap = A[p][k], aq = A[q][k];
+                A[p][k] = c * ap - sn * aq;
+                A[q][k] = sn * ap + c * aq;
+            }
+            __syncthreads();
+            // columns: A <- A J, V <- V J
+            for (int e = tid; e < half * m; e += EIG_THREADS) {
+                const int pi = e / m, k = e - pi * m;
+                const int p = pr_p[pi], q = pr_q[pi];
+                const double c = cs_c[pi], sn = cs_s[pi];
+                const double ap = A[k][p], aq = A[k][q];
+                A[k][p] = c * ap - sn * aq;
+                A[k][q] = sn * ap + c * aq;
+                const double vp = V[k][p], vq = V[k][q];
+                V[k][p] = c * vp - sn * vq;
+                V[k][q] = sn * vp + c * vq;
+            }
+            __syncthreads();
+        }
+    }
+    // descending order (ties: lower index first), then write
+    if (tid < n) {
+        const double mine = A[tid][tid];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const double o = A[j][j];
+            if (o > mine || (o == mine && j < tid)) ++rank;
+        }
+        order[rank] = tid;
+    }
+    __syncthreads();
+    for (int e = tid; e < n * n; e += EIG_THREADS) {
+        const int i = e / n, j = e - i * n;
+        evecs[i * ldv + j] = (T)V[i][order[j]];
+    }
+    if (tid < n) evals[tid] = (T)A[order[tid]][order[tid]];
+}
+
+template <typename T>
+int run(const T* z, int64_t rows, int64_t R, int64_t rs, int64_t cs, T* out, int64_t out_ld, void* workspace,
+        cudaStream_t stream) {
+    // workspace: [counter + status, 256 B][R^{-1}, fp64][partials, fp64]
+    unsigned* counter = static_cast<unsigned*>(workspace);
+    int* status = reinterpret_cast<int*>(counter + 1);
+    double* rinv = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
+    double* partial = rinv + align_up((size_t)R * R, 32);
+    const int nblk = (int)ceil_div(rows, OR_ROWS);
+    constexpr int smem = (OR_ROWS + OR_MAX) * (OR_MAX + 1) * (int)sizeof(double);
+    static std::atomic<uint64_t> attr_done{0};
+    if (ensure_dynamic_smem(orth_gram_chol_kernel<T>, smem, attr_done)) return TLB200_ECUDA;
+    orth_gram_chol_kernel<T><<<nblk, OR_THREADS, smem, stream>>>(z, rows, (int)R, rs, cs, partial, counter, rinv, status);
+    TLB_CHECK_LAUNCH();
+    const int nb2 = (int)ceil_div(rows, 128);
+    if (R <= 16) orth_apply_kernel<T, 16><<<nb2, 128, 0, stream>>>(z, rows, (int)R, rs, cs, rinv, out, out_ld);
+    else if (R <= 32) orth_apply_kernel<T, 32><<<nb2, 128, 0, stream>>>(z, rows, (int)R, rs, cs, rinv, out, out_ld);
+    else orth_apply_kernel<T, 64><<<nb2, 128, 0, stream>>>(z, rows, (int)R, rs, cs, rinv, out, out_ld);
+    TLB_CHECK_LAUNCH();
+    return TLB200_OK;
+}
+
+}  // namespace
+}  // namespace tlb200
+
+using namespace tlb200;
+
+extern "C" int tlb200_symeig(const void* a, int64_t n, int64_t lda, int dtype, void* evals, void* evecs, int64_t ldv,
+                             void* stream) {
+    if (!a || !evals || !evecs || n < 1 || lda < n || ldv < n || !dtype_valid(dtype)) return TLB200_EINVAL;
+    if (n > EIG_MAX) return TLB200_EUNSUPPORTED;
+    set_last_path("simt");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    constexpr int smem = 2 * EIG_MAX * (EIG_MAX + 1) * (int)sizeof(double);
+    static std::atomic<uint64_t> done_f{0}, done_d{0};
+    if (dtype == TLB200_F32) {
+        if (ensure_dynamic_smem(symeig_jacobi_kernel<float>, smem, done_f)) return TLB200_ECUDA;
+        symeig_jacobi_kernel<float><<<1, EIG_THREADS, smem, s>>>((const float*)a, (int)n, lda, (float*)evals, (float*)evecs, ldv);
+    } else {
+        if (ensure_dynamic_smem(symeig_jacobi_kernel<double>, smem, done_d)) return TLB200_ECUDA;
+        symeig_jacobi_kernel<double><<<1, EIG_THREADS, smem, s>>>((const double*)a, (int)n, lda, (double*)evals, (double*)evecs, ldv);
+    }
+    TLB_CHECK_LAUNCH();
+    return TLB200_OK;
+}
+
+extern "C" size_t tlb200_orthonormalize_workspace_bytes(int64_t rows, int64_t rank) {
+    if (rows < 1 || rank < 1 || rank > OR_MAX) return 0;
+    return 256 + sizeof(double) * (align_up((size_t)rank * rank, 32) + (size_t)ceil_div(rows, OR_ROWS) * rank * rank) + 256;
+}
+
+extern "C" int tlb200_orthonormalize(const void* z, int64_t rows, int64_t rank, int64_t row_stride, int64_t col_stride,
+                                     int dtype, void* out, int64_t out_ld, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+    if (!z || !out || !workspace || rows < 1 || rank < 1 || out_ld < rank || !dtype_valid(dtype)) return TLB200_EINVAL;
+    if (rank > OR_MAX || rows < rank) return TLB200_EUNSUPPORTED;
+    if (workspace_bytes < tlb200_orthonormalize_workspace_bytes(rows, rank)) return TLB200_EWORKSPACE;
+    set_last_path("simt");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == TLB200_F32)
+        return run<float>((const float*)z, rows, rank, row_stride, col_stride, (float*)out, out_ld, workspace, s);
+    return run<double>((const double*)z, rows, rank, row_stride, col_stride, (double*)out, out_ld, workspace, s);
+}

@@ -86,6 +86,39 @@ class OracleOps:
         return vals if out is None else out.copy_(vals)
 
     @staticmethod
+    def cp_impute(x, mask, cp, out=None, stats=None):
+        w, fs = cp
+        new, nrm, unnorm = O.cp_impute(_np(x), _np(mask), (_np(w), [_np(f) for f in fs]))
+        new = torch.from_numpy(np.ascontiguousarray(new.astype(_np(x).dtype)))
+        vals = torch.tensor([unnorm / nrm, nrm ** 2, unnorm ** 2], dtype=x.dtype)
+        out = new if out is None else out.copy_(new)
+        return out, (vals if stats is None else stats.copy_(vals))
+
+    @staticmethod
     def sumsq(x, out=None):
         v = torch.tensor([float(np.sum(_np(x).astype(np.float64) ** 2))], dtype=x.dtype)
         return v if out is None else out.copy_(v)
+
+
+    # ---- HOOI pieces (tensorly_b200.tucker_hooi.CudaOps stand-ins) ----
+    @staticmethod
+    def multi_mode_dot(x, mats, modes=None, skip=None, transpose=False):
+        return torch.from_numpy(np.ascontiguousarray(O.multi_mode_dot(_np(x), [_np(m) for m in mats], modes=modes, skip=skip,
+                                                                      transpose=transpose)))
+
+    @staticmethod
+    def unfold(x, mode, contiguous=False):
+        return torch.from_numpy(np.ascontiguousarray(O.unfold(_np(x), mode)))
+
+    @staticmethod
+    def orthonormalize(z, out=None):
+        """Cholesky-QR in fp64, like tlb200_orthonormalize."""
+        zz = _np(z).astype(np.float64)
+        r = np.linalg.cholesky(zz.T @ zz).T
+        q = torch.from_numpy(np.ascontiguousarray(zz @ np.linalg.inv(r)).astype(_np(z).dtype))
+        return q if out is None else out.copy_(q)
+
+    @staticmethod
+    def symeig(a):
+        w, v = np.linalg.eigh(0.5 * (_np(a) + _np(a).T))
+        return torch.from_numpy(w[::-1].copy()), torch.from_numpy(np.ascontiguousarray(v[:, ::-1]))

@@ -28,7 +28,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, shape, cp_rank, shard_mode, update, iters, ret):
+def _worker(rank, world, port, shape, cp_rank, shard_mode, update, iters, ret, masked=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -54,8 +54,15 @@ def _worker(rank, world, port, shape, cp_rank, shard_mode, update, iters, ret):
         fn = tb.parafac if update == "ls" else tb.non_negative_parafac
         kw = dict(n_iter_max=iters, init=init, return_errors=True, sharded=True, shard_mode=shard_mode, ops=OracleOps, use_graph=False)
         kw["tol"] = 0 if update == "ls" else 1e-30
+        if masked:
+            mask = (np.random.RandomState(5).random_sample(shape) > 0.25).astype(x.dtype)
+            x = x * mask
+            x_local = torch.from_numpy(np.ascontiguousarray(x[tuple(sl)]))
+            kw["mask"] = torch.from_numpy(np.ascontiguousarray(mask[tuple(sl)]))
         cp, errs = fn(x_local, cp_rank, **kw)
-        if update == "ls":
+        if masked:
+            (_, ref_f), ref_e, _ = O.parafac_masked(x, mask, (w, fs), n_iter_max=iters)
+        elif update == "ls":
             (_, ref_f), ref_e = O.parafac(x, (w, fs), n_iter_max=iters)
         else:
             (_, ref_f), ref_e = O.non_negative_parafac(x, (w, fs), n_iter_max=iters)
@@ -67,10 +74,11 @@ def _worker(rank, world, port, shape, cp_rank, shard_mode, update, iters, ret):
         dist.destroy_process_group()
 
 
-def _run(shape, cp_rank, shard_mode, update="ls", iters=4, world=2, all_reduces=None):
+def _run(shape, cp_rank, shard_mode, update="ls", iters=4, world=2, all_reduces=None, masked=False):
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), shape, cp_rank, shard_mode, update, iters, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), shape, cp_rank, shard_mode, update, iters, ret, masked), nprocs=world,
+             join=True)
     assert len(ret) == world
     for r in range(world):
         err_dev, fac_dev, shapes_ok, n, n_all_reduce = ret[r]
@@ -105,6 +113,42 @@ def test_sharded_parafac_last_mode_and_four_way():
 @pytest.mark.timeout(300)
 def test_sharded_non_negative_parafac():
     _run((8, 7, 6), 3, shard_mode=0, update="mu", iters=5)
+
+
+@pytest.mark.timeout(300)
+def test_sharded_masked_parafac():
+    """Missing values + sharding: every rank imputes its own slab, the two norms are all-reduced."""
+    _run((10, 8, 9), 3, shard_mode=0, masked=True)
+
+
+def test_masked_parafac_host_logic_vs_reference_golden():
+    """Own driver with `mask=` (oracle-backed ops, fp64) against the reference's masked parafac trajectories; the
+    caller's tensor is not modified; plain sharded=False inside a process without a process group stays local."""
+    import tensorly_b200 as tb
+    from oracle_ops import OracleOps
+    from conftest import Golden
+    g = Golden("round2")
+    for tag in ("mask64", "mask4way"):
+        x, mask = g[f"{tag}/x"], g[f"{tag}/mask"]
+        rank, iters = int(g[f"{tag}/rank"]), int(g[f"{tag}/iters"])
+        xt = torch.from_numpy(x.copy())
+        init = (None, [torch.from_numpy(f.copy()) for f in g.arrays(tag, "init")])
+        cp, errs = tb.parafac(xt, rank, n_iter_max=iters, init=init, tol=0, return_errors=True,
+                              mask=torch.from_numpy(mask.copy()), ops=OracleOps, use_graph=False)
+        ref = g[f"{tag}/errors"]
+        assert np.max(np.abs(np.array(errs) - ref) / ref) <= 1e-10
+        assert np.array_equal(xt.numpy(), x)
+        for a, b in zip(cp[1], g.arrays(tag, "f")):
+            assert np.linalg.norm(a.numpy() - b) / np.linalg.norm(b) <= 1e-7
+
+
+def test_sharded_requires_opt_in():
+    """sharding never switches on implicitly; sharded=True without a process group is an error."""
+    import tensorly_b200 as tb
+    from tensorly_b200.cp_als import _Comm
+    assert _Comm(None).active is False
+    with pytest.raises(RuntimeError):
+        _Comm(None, sharded=True)
 
 
 def test_dimension_tree_sweep_equals_n_pass_sweep_on_cpu_ops():

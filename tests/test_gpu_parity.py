@@ -752,6 +752,39 @@ def test_reference_tucker_with_gram_svd_plugin(tl_b200, golden):
     assert abs(float(torch.linalg.norm(core)) - float(g["tucker/core_norm"])) <= 1e-5 * float(g["tucker/core_norm"])
 
 
+def test_reference_parafac_with_fast_solve_plugin(tl_b200, golden):
+    """The sync-free `solve` hook (solve.py): unmodified parafac follows the reference trajectories, and the hook
+    agrees with torch.linalg.solve on the systems the loop hands it (transposed views) and declines the rest."""
+    from tensorly.cp_tensor import CPTensor
+    from tensorly.decomposition import parafac
+    g = golden("als")
+    tb.use_fast_solve()
+    try:
+        for tag in ("p32", "p64", "p4way"):
+            x = g[f"{tag}/x"]
+            rank, iters = int(g[f"{tag}/rank"]), int(g[f"{tag}/iters"])
+            init = CPTensor((torch.ones(rank, dtype=dev(x).dtype, device="cuda"), [dev(f) for f in g.arrays(tag, "init")]))
+            cp, errs = parafac(dev(x), rank, n_iter_max=iters, init=init, tol=0, return_errors=True)
+            ref = g[f"{tag}/errors"]
+            got = np.array([float(e) for e in errs])
+            assert np.max(np.abs(got - ref) / ref) <= 1e-4
+    finally:
+        tb.use_default_solve()
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    for n, cols, dt in ((32, 1000, torch.float32), (64, 300, torch.float32), (10, 77, torch.float64), (100, 50, torch.float64)):
+        f = torch.rand(500, n, generator=gen, device="cuda", dtype=dt)
+        v = f.T @ f + torch.eye(n, device="cuda", dtype=dt)
+        m = torch.rand(cols, n, generator=gen, device="cuda", dtype=dt)
+        got = tb.fast_solve(v.T, m.T)
+        ref = torch.linalg.solve(v.T.double(), m.T.double())
+        assert tuple(got.shape) == (n, cols)
+        assert float(torch.linalg.norm(got.double() - ref) / torch.linalg.norm(ref)) <= (1e-3 if dt == torch.float32 else 1e-10)
+    # not a small square CUDA system: handed to the previous solve untouched
+    a = torch.rand(200, 200, device="cuda", dtype=torch.float64) + 200 * torch.eye(200, device="cuda", dtype=torch.float64)
+    b = torch.rand(200, 3, device="cuda", dtype=torch.float64)
+    assert torch.allclose(tb.fast_solve(a, b), torch.linalg.solve(a, b))
+
+
 def test_reference_reconstruction_uses_backend(tl_b200):
     tl = tl_b200
     rng = np.random.RandomState(2)
@@ -763,3 +796,159 @@ def test_reference_reconstruction_uses_backend(tl_b200):
     assert tl.tenalg.get_backend() == "b200"
     with pytest.raises(ValueError):
         tl.tenalg.set_backend("no-such-backend")
+
+
+# --------------------------------------------------------------------------- reconstruction / masked ALS
+def test_cp_to_tensor_golden(golden):
+    """tlb200_cp_to_tensor against the reference's cp_to_tensor outputs (tests/golden/round2.npz)."""
+    g = golden("round2")
+    for tag in ("rec_a", "rec_b", "rec_c", "rec_d", "rec_e", "rec_f"):
+        fs = g.arrays(tag, "f")
+        w = g[f"{tag}/w"] if g.has(f"{tag}/w") else None
+        ref = g[f"{tag}/out"]
+        out = tb.cp_to_tensor((dev(w) if w is not None else None, [dev(f) for f in fs]))
+        assert tuple(out.shape) == ref.shape
+        assert rel_fro(host(out), ref) <= TOL[ref.dtype], tag
+        if len(fs) >= 2:
+            # column-major factors (strided views) and an element-wise mask
+            fT = [dev(np.ascontiguousarray(f.T)).T for f in fs]
+            assert rel_fro(host(tb.cp_to_tensor((dev(w) if w is not None else None, fT))), ref) <= TOL[ref.dtype]
+            mask = (np.random.RandomState(1).random_sample(ref.shape) > 0.4).astype(ref.dtype)
+            got = tb.cp_to_tensor((dev(w) if w is not None else None, [dev(f) for f in fs]), mask=dev(mask))
+            assert rel_fro(host(got), ref * mask) <= TOL[ref.dtype]
+    with pytest.raises(ValueError):
+        tb.cp_to_tensor((None, [dev(np.ones((4, 3))), dev(np.ones((5, 2)))]))
+    with pytest.raises(ValueError):
+        tb.cp_to_tensor((dev(np.ones(4)), [dev(np.ones((4, 3))), dev(np.ones((5, 3)))]))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape,rank", [((96, 80, 112), 16), ((130, 70, 45), 10), ((40, 24, 20, 12), 33), ((300, 200), 64),
+                                        ((257, 129), 100)])
+def test_cp_to_tensor_and_impute_vs_oracle(shape, rank, dtype):
+    rng = np.random.RandomState(17)
+    fs = [(rng.random_sample((s, rank)) - 0.4).astype(dtype) for s in shape]
+    w = (rng.random_sample(rank) + 0.5).astype(dtype)
+    ref = O.cp_to_tensor((w, fs))
+    out = tb.cp_to_tensor((dev(w), [dev(f) for f in fs]))
+    assert rel_fro(host(out), ref) <= TOL[np.dtype(dtype)]
+    x = rng.standard_normal(shape).astype(dtype)
+    mask = (rng.random_sample(shape) > 0.3).astype(dtype)
+    new_ref, nrm, unnorm = O.cp_impute(x, mask, (w, fs))
+    xd = dev(x)
+    new, stats = tb.cp_impute(xd, dev(mask), (dev(w), [dev(f) for f in fs]))
+    assert np.array_equal(host(xd), x)                            # out-of-place by default
+    assert rel_fro(host(new), new_ref) <= TOL[np.dtype(dtype)]
+    st = host(stats).astype(np.float64)
+    tol = 1e-5 if dtype == np.float32 else 1e-11
+    assert abs(st[1] - float(nrm) ** 2) <= tol * float(nrm) ** 2
+    assert abs(st[2] - float(unnorm) ** 2) <= tol * float(unnorm) ** 2
+    assert abs(st[0] - float(unnorm) / float(nrm)) <= tol * float(unnorm) / float(nrm)
+    # observed entries are kept bit for bit, in place too
+    tb.cp_impute(xd, dev(mask), (dev(w), [dev(f) for f in fs]), out=xd)
+    assert np.array_equal(host(xd)[mask == 1], x[mask == 1])
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+@pytest.mark.parametrize("tag", ["mask64", "mask32", "mask4way"])
+def test_masked_parafac_driver_vs_reference(golden, tag, use_graph):
+    """parafac(mask=...) of the own driver (fused imputation + error pass) against the reference's trajectories."""
+    g = golden("round2")
+    x, mask = g[f"{tag}/x"], g[f"{tag}/mask"]
+    rank, iters = int(g[f"{tag}/rank"]), int(g[f"{tag}/iters"])
+    xd = dev(x)
+    init = (None, [dev(f) for f in g.arrays(tag, "init")])
+    cp, errs = tb.parafac(xd, rank, n_iter_max=iters, init=init, tol=0, return_errors=True, mask=dev(mask), use_graph=use_graph)
+    ref = g[f"{tag}/errors"]
+    rel = np.max(np.abs(np.array(errs) - ref) / ref)
+    assert rel <= (1e-9 if x.dtype == np.float64 else 1e-4), rel
+    assert np.array_equal(host(xd), x)                            # the caller's tensor is not modified
+    for a, b in zip(cp[1], g.arrays(tag, "f")):
+        assert rel_fro(host(a), b) <= (1e-6 if x.dtype == np.float64 else 2e-2)
+
+
+def test_non_negative_parafac_svd_init_vs_reference(golden):
+    """init='svd' of non_negative_parafac is NNDSVDA (svd_interface(non_negative=True)), not |U|."""
+    from tensorly_b200.cp_als import _svd_init
+    g = golden("round2")
+    x = g["nnsvd/x"]
+    rank = int(g["nnsvd/rank"])
+    _, fs = _svd_init(dev(x), rank, None, non_negative=True)
+    for a, b in zip(fs, g.arrays("nnsvd", "init")):
+        assert rel_fro(np.abs(host(a)), b) <= 1e-8
+    _, errs = tb.non_negative_parafac(dev(x), rank, n_iter_max=8, init="svd", tol=1e-30, return_errors=True)
+    ref = g["nnsvd/errors"]
+    assert np.max(np.abs(np.array(errs) - ref) / ref) <= 1e-8
+
+
+# --------------------------------------------------------------------------- own HOOI driver (SURVEY 8(f) n1)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("rows,rank", [(512, 64), (300, 20), (64, 64), (1000, 7), (130, 33)])
+def test_orthonormalize_and_symeig(rows, rank, dtype):
+    rng = np.random.RandomState(5)
+    # an ill-conditioned block: one dominant direction (like G U on a tensor with a large mean), cond ~ 1e5
+    z = rng.standard_normal((rows, rank)) + 1e5 * np.outer(rng.random_sample(rows), np.ones(rank))
+    z = z.astype(dtype)
+    q = host(tb.orthonormalize(dev(z))).astype(np.float64)
+    tol = 5e-5 if dtype == np.float32 else 1e-9
+    assert np.linalg.norm(q.T @ q - np.eye(rank)) <= tol * rank
+    # same span: projecting z on q reproduces z
+    z64 = z.astype(np.float64)
+    assert np.linalg.norm(q @ (q.T @ z64) - z64) / np.linalg.norm(z64) <= tol
+    qs = host(tb.orthonormalize(dev(np.ascontiguousarray(z.T)).T)).astype(np.float64)      # column-major input
+    assert np.linalg.norm(qs - q) <= tol * rank
+    a = rng.standard_normal((rank, rank))
+    a = (a @ a.T + np.diag(rng.random_sample(rank))).astype(dtype)
+    w, v = tb.symeig(dev(a))
+    w, v = host(w).astype(np.float64), host(v).astype(np.float64)
+    ref = np.linalg.eigvalsh(a.astype(np.float64))[::-1]
+    etol = 1e-5 if dtype == np.float32 else 1e-12
+    assert np.max(np.abs(w - ref)) <= etol * np.abs(ref).max()
+    assert np.all(np.diff(w) <= 0)
+    assert np.linalg.norm(a.astype(np.float64) @ v - v * w) <= etol * 10 * np.abs(ref).max() * rank
+    assert np.linalg.norm(v.T @ v - np.eye(rank)) <= etol * rank
+
+
+def test_own_tucker_vs_reference(golden):
+    """tensorly_b200.tucker (TTM chains + Gram + warm-started subspace iteration, no SVD in the loop) against the
+    reference's HOOI trajectories: random init (small modes: the exact Rayleigh-Ritz path), SVD init on a
+    low-rank + noise tensor and on a uniform random tensor."""
+    g, g2 = golden("als"), golden("round2")
+    x = g["tucker/x"]
+    ranks = [int(r) for r in g["tucker/ranks"]]
+    tk, errs = tb.tucker(dev(x), ranks, n_iter_max=5, init="random", random_state=1, tol=0, return_errors=True)
+    core, factors = tk
+    ref = g["tucker/errors"]
+    assert np.max(np.abs(np.array(errs) - ref) / ref) <= 1e-8
+    assert abs(float(torch.linalg.norm(core)) - float(g["tucker/core_norm"])) <= 1e-8 * float(g["tucker/core_norm"])
+    for f in factors:
+        ff = host(f)
+        assert np.linalg.norm(ff.T @ ff - np.eye(ff.shape[1])) <= 1e-8
+    for tag, iters, tol in (("tucker_svd", 6, 1e-8), ("tucker_svd32", 8, 1e-4)):
+        x = g2[f"{tag}/x"]
+        ranks = [int(r) for r in g2[f"{tag}/ranks"]]
+        tk, errs = tb.tucker(dev(x), ranks, n_iter_max=iters, init="svd", tol=0, return_errors=True)
+        ref = g2[f"{tag}/errors"]
+        assert np.max(np.abs(np.array(errs) - ref) / ref) <= tol, tag
+        if tag == "tucker_svd":
+            rec = tb.tucker_to_tensor(tk)
+            assert rel_fro(host(rec), g2["tucker_svd/rec"]) <= 1e-8
+    # partial tucker: modes 0 and 2 only
+    (core, factors), errs = tb.partial_tucker(dev(g["tucker/x"]), [4, 6], modes=[0, 2], n_iter_max=4, init="svd", tol=0)
+    assert tuple(core.shape) == (4, 22, 6) and len(factors) == 2 and len(errs) == 4
+    assert errs[-1] <= errs[0] + 1e-12
+
+
+@pytest.mark.parametrize("shape,ranks", [((160, 150, 140), [32, 32, 32]), ((200, 64, 300), [40, 20, 64]), ((100, 90, 80, 70), [10, 12, 8, 9])])
+def test_own_tucker_large_modes_vs_oracle(shape, ranks):
+    """Modes wider than 64 (oversampled subspace iteration + Rayleigh-Ritz, or plain subspace iteration at rank 64)
+    on uniform random data — the flat-spectrum worst case — against the oracle's exact-SVD HOOI: 1e-4 on the errors."""
+    rng = np.random.RandomState(0)
+    x = rng.random_sample(shape).astype(np.float32)
+    rs = np.random.RandomState(1)
+    rs.random_sample(ranks)
+    init = [rs.random_sample((s, r)) for s, r in zip(shape, ranks)]
+    (_, _), ref = O.tucker_hooi(x, ranks, init, n_iter_max=5)
+    tk, errs = tb.tucker(dev(x), ranks, n_iter_max=5, init="random", random_state=1, tol=0, return_errors=True)
+    dev_ = np.max(np.abs(np.array(errs) - np.array(ref, dtype=np.float64)) / np.array(ref, dtype=np.float64))
+    assert dev_ <= 1e-4, (errs, ref)

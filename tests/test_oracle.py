@@ -217,3 +217,48 @@ def test_gram_svd_plugin_matches_lapack_svd():
         assert float(torch.linalg.norm(u.T @ u - torch.eye(k, dtype=a.dtype))) < 1e-8
     u, s, vh = gram_svd(torch.as_tensor(rng.standard_normal((6, 9))), full_matrices=True)
     assert u.shape == (6, 6) and vh.shape == (9, 9)
+
+
+# --------------------------------------------------------------------------- round-2 fixtures
+def test_cp_to_tensor_vs_reference(golden):
+    g = golden("round2")
+    for tag in ("rec_a", "rec_b", "rec_c", "rec_d", "rec_e", "rec_f"):
+        fs = g.arrays(tag, "f")
+        w = g[f"{tag}/w"] if g.has(f"{tag}/w") else None
+        out = O.cp_to_tensor((w, fs))
+        ref = g[f"{tag}/out"]
+        assert out.shape == ref.shape
+        assert np.array_equal(out, ref), tag          # same expression, same BLAS: bit for bit
+
+
+def test_masked_parafac_vs_reference(golden):
+    g = golden("round2")
+    for tag in ("mask64", "mask32", "mask4way"):
+        x, mask = g[f"{tag}/x"], g[f"{tag}/mask"]
+        rank, iters = int(g[f"{tag}/rank"]), int(g[f"{tag}/iters"])
+        init = (np.ones(rank, dtype=x.dtype), g.arrays(tag, "init"))
+        (_, factors), errs, _ = O.parafac_masked(x, mask, init, n_iter_max=iters)
+        ref = g[f"{tag}/errors"]
+        tol = 1e-9 if x.dtype == np.float64 else 1e-4
+        assert np.max(np.abs(np.array(errs, dtype=np.float64) - ref) / ref) <= tol, tag
+        for a, b in zip(factors, g.arrays(tag, "f")):
+            assert rel_fro(a, b) <= (1e-7 if x.dtype == np.float64 else 5e-3)
+
+
+def test_hals_vs_reference(golden):
+    g = golden("round2")
+    for tag in ("hals_a", "hals_b", "hals_c"):
+        UtM, UtU, V0 = g[f"{tag}/UtM"], g[f"{tag}/UtU"], g[f"{tag}/V0"]
+        tol = 1e-10 if UtM.dtype == np.float64 else 1e-4
+        assert rel_fro(O.hals_nnls(UtM, UtU, V0, n_iter_max=100), g[f"{tag}/V"]) <= tol
+        v = O.hals_nnls(UtM, UtU, V0, n_iter_max=20, sparsity_coefficient=0.05, ridge_coefficient=0.1, epsilon=1e-6)
+        assert rel_fro(v, g[f"{tag}/V_sparse"]) <= tol
+    for tag in ("nnhals64", "nnhals32"):
+        x = g[f"{tag}/x"]
+        rank, iters = int(g[f"{tag}/rank"]), int(g[f"{tag}/iters"])
+        init = (np.ones(rank, dtype=x.dtype), g.arrays(tag, "init"))
+        (_, factors), errs = O.non_negative_parafac_hals(x, init, n_iter_max=iters)
+        ref = g[f"{tag}/errors"]
+        assert np.max(np.abs(np.array(errs, dtype=np.float64) - ref) / ref) <= (1e-9 if x.dtype == np.float64 else 1e-4)
+        for a, b in zip(factors, g.arrays(tag, "f")):
+            assert rel_fro(a, b) <= (1e-7 if x.dtype == np.float64 else 5e-3)
