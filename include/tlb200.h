@@ -294,6 +294,28 @@ int tlb200_orthonormalize(const void* z, int64_t rows, int64_t rank, int64_t row
 int tlb200_symeig(const void* a, int64_t n, int64_t lda, int dtype, void* evals, void* evecs,
                   int64_t ldv, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * HALS non-negative least squares in one launch — replaces tensorly.solvers.nnls.hals_nnls
+ * (tensorly/solvers/nnls.py:5-175, rank loop :139-153) as called per mode by non_negative_parafac_hals
+ * (tensorly/decomposition/_nn_cp.py:326-336):
+ *   repeat <= n_iter_max times, for k = 0..rank-1:
+ *     V[k,:] = max((UtM[k,:] - UtU[k,:] V + UtU[k,k] V[k,:] - sparsity) / (UtU[k,k] + 2 ridge), epsilon)
+ *   until sum_k ||V - V_new[k,:]||^2 < tol * (its value in the first iteration)      (the reference's statistic)
+ * UtU = (w w^T) o prod_{i != mode} grams[i] as in tlb200_cp_update, or grams[0] itself when mode < 0.
+ * m = UtM^T and f = V^T (updated in place) are addressed as x[row * row_stride + k * col_stride], row < rows,
+ * i.e. the MTTKRP and the factor of the CP driver are passed as they are.  sparsity / ridge: NULL = absent.
+ * rank <= 64 (fp32) / 32 (fp64); rows <= a few 10^4 (one cooperative grid).  iters_out (device int, may be NULL)
+ * receives the number of inner iterations run.
+ * ------------------------------------------------------------------------- */
+size_t tlb200_hals_workspace_bytes(int64_t rows);
+
+int tlb200_hals_update(const void* const* grams, int nmodes, int mode, int64_t rank,
+                       const void* weights, const void* m, int64_t m_row_stride,
+                       int64_t m_col_stride, void* f, int64_t f_row_stride, int64_t f_col_stride,
+                       int64_t rows, int n_iter_max, double tol, const double* sparsity,
+                       const double* ridge, double epsilon, int dtype, void* iters_out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

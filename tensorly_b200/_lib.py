@@ -87,6 +87,10 @@ SIGNATURES = {
     "tlb200_orthonormalize": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p,
                                       c_size_t, c_void_p]),
     "tlb200_symeig": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
+    "tlb200_hals_workspace_bytes": (c_size_t, [c_int64]),
+    "tlb200_hals_update": (c_int, [_VPP, c_int, c_int, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64,
+                                   c_int64, c_int64, c_int, c_double, POINTER(c_double), POINTER(c_double), c_double, c_int,
+                                   c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 _lib = None

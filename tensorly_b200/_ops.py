@@ -755,3 +755,54 @@ def symeig(a: torch.Tensor):
                                _stream(a))
     _lib.check(st, "symeig")
     return evals, evecs
+
+
+# --------------------------------------------------------------------------- HALS
+def hals_update(grams, mode: int, weights, mttkrp: torch.Tensor, factor: torch.Tensor, n_iter_max: int = 100,
+                tol: float = 1e-8, sparsity_coefficient=None, ridge_coefficient=None, epsilon: float = 0.0,
+                iters_out: torch.Tensor | None = None) -> torch.Tensor:
+    """In-place HALS update of `factor` (rows x rank) from its MTTKRP: hals_nnls(M^T, V, F^T) with
+    V = (w w^T) o prod_{i != mode} G_i (tensorly/decomposition/_nn_cp.py:311-336, solvers/nnls.py:139-173),
+    the whole inner iteration in one kernel.  mode < 0: grams[0] is UtU itself."""
+    import ctypes
+    _check_tensor(mttkrp, "mttkrp")
+    _check_tensor(factor, "factor", mttkrp)
+    rows, rank = factor.shape
+    if tuple(mttkrp.shape) != (rows, rank):
+        raise ValueError(f"mttkrp {tuple(mttkrp.shape)} and factor {tuple(factor.shape)} must have the same shape")
+    lib = _lib.load()
+    ws = _workspace(lib.tlb200_hals_workspace_bytes(rows), factor)
+    sp = ctypes.byref(ctypes.c_double(float(sparsity_coefficient))) if sparsity_coefficient is not None else None
+    rg = ctypes.byref(ctypes.c_double(float(ridge_coefficient))) if ridge_coefficient is not None else None
+    with _Device(factor):
+        st = lib.tlb200_hals_update(_gram_ptrs(grams, mode), len(grams), mode, rank,
+                                    weights.data_ptr() if weights is not None else None, mttkrp.data_ptr(),
+                                    mttkrp.stride(0), mttkrp.stride(1), factor.data_ptr(), factor.stride(0), factor.stride(1),
+                                    rows, int(n_iter_max), float(tol), sp, rg, float(epsilon), _DTYPES[factor.dtype],
+                                    iters_out.data_ptr() if iters_out is not None else None, ws.data_ptr(), ws.numel(),
+                                    _stream(factor))
+    if st == _lib.TLB200_EUNSUPPORTED:
+        raise NotImplementedError(f"hals: rank {rank} / {rows} rows exceed the single-kernel solver "
+                                  "(rank <= 64 in fp32, 32 in fp64)")
+    _lib.check(st, "hals_update")
+    return factor
+
+
+def hals_nnls(UtM, UtU, V=None, n_iter_max=500, tol=1e-8, sparsity_coefficient=None, ridge_coefficient=None,
+              nonzero_rows=False, exact=False, epsilon=0.0, callback=None) -> torch.Tensor:
+    """tensorly.solvers.nnls.hals_nnls (tensorly/solvers/nnls.py:5-175) for a given V (rank x n): returns the new
+    V; the input is not modified.  `nonzero_rows`, `callback` and V=None are not part of the kernel."""
+    if V is None or nonzero_rows or callback is not None:
+        raise NotImplementedError("hals_nnls kernel: pass V, nonzero_rows=False, callback=None")
+    _check_tensor(UtM, "UtM")
+    _check_tensor(UtU, "UtU", UtM)
+    _check_tensor(V, "V", UtM)
+    rank, n = UtM.shape
+    if tuple(UtU.shape) != (rank, rank) or tuple(V.shape) != (rank, n):
+        raise ValueError(f"shapes: UtM {tuple(UtM.shape)}, UtU {tuple(UtU.shape)}, V {tuple(V.shape)}")
+    if exact:
+        n_iter_max, tol = 50000, 1e-16
+    out = V.clone()
+    hals_update([UtU.contiguous()], -1, None, UtM.transpose(0, 1), out.transpose(0, 1), n_iter_max, tol,
+                sparsity_coefficient, ridge_coefficient, epsilon)
+    return out

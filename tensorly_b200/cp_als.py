@@ -74,6 +74,7 @@ class CudaOps:
     cp_update = staticmethod(_ops.cp_update)
     fused_gram = True        # cp_update(..., gram_out=) also writes the Gram of the updated factor
     nncp_update = staticmethod(_ops.nncp_update)
+    hals_update = staticmethod(_ops.hals_update)   # the whole HALS inner iteration of one mode in one kernel
     cp_error = staticmethod(_ops.cp_error)
     cp_impute = staticmethod(_ops.cp_impute)     # masked ALS: imputation + both norms in one tensor pass
     sumsq = staticmethod(_ops.sumsq)
@@ -138,7 +139,12 @@ class CPALS:
     def __init__(self, tensor_local: torch.Tensor, weights: torch.Tensor, factors: Sequence[torch.Tensor],
                  l2_reg: float = 0.0, update: str = "ls", fixed_modes: Sequence[int] = (), comm: Optional[_Comm] = None,
                  shard_mode: int = 0, ops=CudaOps, eps: Optional[float] = None, dimtree: Optional[bool] = None,
-                 mask: Optional[torch.Tensor] = None):
+                 mask: Optional[torch.Tensor] = None, nn_modes=None, sparsity_coefficients=None, exact: bool = False):
+        # update == "hals" (non_negative_parafac_hals, tensorly/decomposition/_nn_cp.py:307-341): modes in `nn_modes`
+        # are updated by HALS non-negative least squares, the others by the unconstrained solve
+        self.nn_modes = set(range(tensor_local.dim())) if nn_modes in (None, "all") else set(nn_modes)
+        self.sparsity_coefficients = list(sparsity_coefficients) if sparsity_coefficients is not None else [None] * tensor_local.dim()
+        self.exact = bool(exact)
         # Missing values (mask: 1 = observed, 0 = missing; tensorly/decomposition/_cp.py:195-207, :442-445): the
         # driver owns a copy of the tensor whose missing entries are re-imputed from the current factors after
         # every sweep (before every mode update for the multiplicative rule, _nn_cp.py:124-127).
@@ -238,8 +244,13 @@ class CPALS:
             if self.shard_mode == mode and self._pack is None:
                 self.comm.all_reduce(self.grams[mode])     # (packed: reduced together with the next mode's MTTKRP)
         else:
-            if self.update == "ls":
+            if self.update == "ls" or (self.update == "hals" and mode not in self.nn_modes):
                 self.ops.cp_update(self.grams, mode, self.weights, m, self.l2_reg, out=self.factors[mode])
+            elif self.update == "hals":
+                # hals_nnls(M^T, V, F^T, n_iter_max=100, sparsity_coefficient=..., exact=...) (_nn_cp.py:328-335)
+                self.ops.hals_update(self.grams, mode, self.weights, m, self.factors[mode],
+                                     n_iter_max=50000 if self.exact else 100, tol=1e-16 if self.exact else 1e-8,
+                                     sparsity_coefficient=self.sparsity_coefficients[mode])
             else:
                 self.ops.nncp_update(self.grams, mode, self.weights, m, self.factors[mode], self.eps)
             self._refresh_gram(mode, defer=self._pack is not None)   # packed: reduced with the next mode's MTTKRP
@@ -280,6 +291,7 @@ class CPALS:
         # The sharded sweep stays eager by default: capturing the NCCL all-reduces works and is ~4 % faster at
         # 2 GPUs, but process-group teardown then hung in our runs (torch 2.11 / NCCL 2.28).  TLB200_DIST_GRAPH=1 opts in.
         graphable = (use_graph and getattr(self.ops, "supports_graphs", False) and self.x.is_cuda
+                     and self.update != "hals"          # its kernel is a cooperative launch: kept out of graph capture
                      and (not self.comm.active or os.environ.get("TLB200_DIST_GRAPH", "0") == "1")
                      and not (self.comm.active and self.shard_mode == self.ndim - 1))
         if not graphable:
@@ -409,7 +421,7 @@ def _delegate(name, tensor, rank, kwargs):
 
 def _run(tensor, rank, n_iter_max, init, svd, tol, random_state, verbose, return_errors, l2_reg, cvg_criterion,
          fixed_modes, callback, update, group, shard_mode, ops, use_graph, sharded=None, mask=None,
-         svd_mask_repeats=5):
+         svd_mask_repeats=5, hals=None):
     if not isinstance(tensor, torch.Tensor):
         raise TypeError("tensor must be a torch.Tensor")
     comm = _Comm(group, sharded)
@@ -425,7 +437,7 @@ def _run(tensor, rank, n_iter_max, init, svd, tol, random_state, verbose, return
         exts = [int(e.item()) for e in exts]
         shape[shard_mode] = sum(exts)
         lo = sum(exts[: comm.rank])
-    non_negative = update == "mu"
+    non_negative = update in ("mu", "hals")
     if isinstance(init, str):
         if init == "random":
             weights, factors = _random_init(shape, rank, random_state, tensor.dtype, tensor.device)
@@ -458,7 +470,7 @@ def _run(tensor, rank, n_iter_max, init, svd, tol, random_state, verbose, return
                       "Consider using tl.moveaxis()")
         fixed_modes.remove(ndim - 1)
     state = CPALS(tensor, weights, factors, l2_reg=l2_reg, update=update, fixed_modes=fixed_modes, comm=comm,
-                  shard_mode=shard_mode, ops=ops, mask=mask)
+                  shard_mode=shard_mode, ops=ops, mask=mask, **(hals or {}))
     want_err = bool(tol) or return_errors
     err_hist = torch.zeros(max(n_iter_max, 1), dtype=tensor.dtype, device=tensor.device)
     rec_errors: List[float] = []
@@ -535,3 +547,40 @@ def non_negative_parafac(tensor, rank, n_iter_max=100, init="svd", svd="truncate
             fixed_modes=fixed_modes))
     return _run(tensor, rank, n_iter_max, init, svd, tol, random_state, verbose, return_errors, 0.0, cvg_criterion,
                 fixed_modes, None, "mu", group, shard_mode, ops, use_graph, sharded, mask)
+
+
+def non_negative_parafac_hals(tensor, rank, n_iter_max=100, init="svd", svd="truncated_svd", tol=10e-8, random_state=None,
+                              sparsity_coefficients=None, fixed_modes=None, nn_modes="all", exact=False,
+                              normalize_factors=False, verbose=False, return_errors=False, cvg_criterion="abs_rec_error", *,
+                              sharded=None, group=None, shard_mode=0, ops=CudaOps):
+    """Non-negative CP by HALS — same signature and semantics as tensorly.decomposition.non_negative_parafac_hals
+    (tensorly/decomposition/_nn_cp.py:186-379).  Per mode: Gram-Hadamard, MTTKRP, then the whole hals_nnls inner
+    iteration (up to 100 Gauss-Seidel passes over the rank, tensorly/solvers/nnls.py:139-173) as ONE kernel
+    (tlb200_hals_update) instead of ~6 array-library calls per rank and pass."""
+    if normalize_factors or svd != "truncated_svd":
+        if _Comm(group, sharded).active:
+            raise NotImplementedError("normalize_factors is not available sharded")
+        return _delegate("non_negative_parafac_hals", tensor, rank, dict(
+            n_iter_max=n_iter_max, init=init, svd=svd, tol=tol, random_state=random_state,
+            sparsity_coefficients=sparsity_coefficients, fixed_modes=fixed_modes, nn_modes=nn_modes, exact=exact,
+            normalize_factors=normalize_factors, verbose=verbose, return_errors=return_errors, cvg_criterion=cvg_criterion))
+    n_modes = tensor.dim()
+    if sparsity_coefficients is None or isinstance(sparsity_coefficients, float):
+        sparsity_coefficients = [sparsity_coefficients] * n_modes
+    sparsity_coefficients = list(sparsity_coefficients)
+    fixed = list(fixed_modes or [])
+    for m in fixed:
+        sparsity_coefficients[m] = None
+    nn = set(range(n_modes)) if nn_modes == "all" else set(nn_modes or ())
+    for m in range(n_modes):
+        if sparsity_coefficients[m] is not None and m not in nn:
+            import warnings
+            warnings.warn("Sparsity coefficient is ignored in unconstrained modes.")
+    # the reference evaluates the error only when tol is truthy (_nn_cp.py:342) and never fixes... any mode may be fixed
+    out = _run(tensor, rank, n_iter_max, init, svd, tol, random_state, verbose, True, 0.0, cvg_criterion, fixed, None,
+               "hals", group, shard_mode, ops, False, sharded, None, 5,
+               dict(nn_modes=nn, sparsity_coefficients=sparsity_coefficients, exact=exact))
+    cp, errs = out
+    if not tol:
+        errs = []
+    return (cp, errs) if return_errors else cp

@@ -74,6 +74,15 @@ class OracleOps:
         return factor
 
     @staticmethod
+    def hals_update(grams, mode, weights, m, factor, n_iter_max=100, tol=1e-8, sparsity_coefficient=None,
+                    ridge_coefficient=None, epsilon=0.0, iters_out=None):
+        v = _form_v(grams, mode, weights, 0.0)
+        new = O.hals_nnls(_np(m).T, v, _np(factor).T, n_iter_max=n_iter_max, tol=tol,
+                          sparsity_coefficient=sparsity_coefficient, ridge_coefficient=ridge_coefficient, epsilon=epsilon)
+        factor.copy_(torch.from_numpy(np.ascontiguousarray(new.T)))
+        return factor
+
+    @staticmethod
     def cp_error(grams, weights, m_last, f_last, norm_x2, out=None):
         w = _np(weights)
         ncp = np.ones_like(_np(grams[0]))

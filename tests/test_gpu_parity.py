@@ -952,3 +952,54 @@ def test_own_tucker_large_modes_vs_oracle(shape, ranks):
     tk, errs = tb.tucker(dev(x), ranks, n_iter_max=5, init="random", random_state=1, tol=0, return_errors=True)
     dev_ = np.max(np.abs(np.array(errs) - np.array(ref, dtype=np.float64)) / np.array(ref, dtype=np.float64))
     assert dev_ <= 1e-4, (errs, ref)
+
+
+# --------------------------------------------------------------------------- HALS
+def test_hals_nnls_golden(golden):
+    """tlb200_hals_update against the reference's hals_nnls outputs (plain, and with sparsity / ridge / epsilon)."""
+    g = golden("round2")
+    for tag in ("hals_a", "hals_b", "hals_c"):
+        UtM, UtU, V0 = g[f"{tag}/UtM"], g[f"{tag}/UtU"], g[f"{tag}/V0"]
+        tol = 1e-9 if UtM.dtype == np.float64 else 2e-4
+        v0 = dev(V0)
+        out = tb.hals_nnls(dev(UtM), dev(UtU), v0, n_iter_max=100)
+        assert np.array_equal(host(v0), V0)                      # input untouched
+        assert rel_fro(host(out), g[f"{tag}/V"]) <= tol, tag
+        assert float(out.min()) >= 0.0
+        out = tb.hals_nnls(dev(UtM), dev(UtU), dev(V0), n_iter_max=20, sparsity_coefficient=0.05, ridge_coefficient=0.1,
+                           epsilon=1e-6)
+        assert rel_fro(host(out), g[f"{tag}/V_sparse"]) <= tol, tag
+        assert float(out.min()) >= 1e-6 * (1 - 1e-6)
+    with pytest.raises(NotImplementedError):
+        tb.hals_nnls(dev(np.ones((100, 5))), dev(np.eye(100)), dev(np.ones((100, 5))))      # rank 100 in fp64
+
+
+@pytest.mark.parametrize("tag", ["nnhals64", "nnhals32"])
+def test_non_negative_parafac_hals_driver_vs_reference(golden, tag):
+    g = golden("round2")
+    x = g[f"{tag}/x"]
+    rank, iters = int(g[f"{tag}/rank"]), int(g[f"{tag}/iters"])
+    init = (None, [dev(f) for f in g.arrays(tag, "init")])
+    cp, errs = tb.non_negative_parafac_hals(dev(x), rank, n_iter_max=iters, init=init, tol=1e-30, return_errors=True)
+    ref = g[f"{tag}/errors"]
+    assert len(errs) == iters
+    assert np.max(np.abs(np.array(errs) - ref) / ref) <= (1e-8 if x.dtype == np.float64 else 1e-4)
+    for a, b in zip(cp[1], g.arrays(tag, "f")):
+        assert rel_fro(host(a), b) <= (1e-6 if x.dtype == np.float64 else 1e-2)
+        assert float(a.min()) >= 0.0
+
+
+def test_hals_large_factor_many_ctas():
+    """A factor with thousands of rows: several CTAs, the grid-wide stopping statistic, iteration count reported."""
+    rng = np.random.RandomState(8)
+    R, n = 32, 5000
+    U = rng.random_sample((300, R)).astype(np.float32)
+    M = rng.random_sample((300, n)).astype(np.float32)
+    V0 = rng.random_sample((R, n)).astype(np.float32)
+    UtM, UtU = U.T @ M, U.T @ U
+    ref = O.hals_nnls(UtM, UtU, V0, n_iter_max=30)
+    iters = torch.zeros(1, dtype=torch.int32, device="cuda")
+    f = dev(np.ascontiguousarray(V0.T))
+    tb.hals_update([dev(UtU)], -1, None, dev(np.ascontiguousarray(UtM.T)), f, n_iter_max=30, iters_out=iters)
+    assert rel_fro(host(f).T, ref) <= 2e-4
+    assert 1 <= int(iters[0]) <= 30
