@@ -276,7 +276,8 @@ int tlb200_cp_impute(const void* x, const void* mask, const void* const* factors
  * svd_interface(unfold(core_approximation, mode), n_eigenvecs=rank) inside the loop of
  * tensorly/decomposition/_tucker.py:197-201 (-> tensorly/tenalg/svd.py:211-235) together with warm-started
  * subspace iteration on the Gram matrix of the unfolding (tensorly_b200/tucker_hooi.py):
- *   out = Z R^{-1},  R^T R = Z^T Z   (Cholesky-QR; Gram, Cholesky factor and inverse in fp64)
+ *   out = Z R^{-1},  R^T R = Z^T Z   (Cholesky-QR; Gram, Cholesky factor and inverse in fp64; passes = 2 repeats
+ *   it on the result, which makes `out` orthonormal to rounding whenever cond(Z)^2 < 1e16)
  * z: (rows, rank) with element strides, rank <= 64 <= ... <= rows; out: (rows, rank), row stride out_ld.
  * The first 8 bytes of `workspace` are a ticket counter and a status word: the counter must be zero before the
  * first call and is left zero; status (second int) is 1 when the block was numerically rank deficient.
@@ -284,7 +285,7 @@ int tlb200_cp_impute(const void* x, const void* mask, const void* const* factors
 size_t tlb200_orthonormalize_workspace_bytes(int64_t rows, int64_t rank);
 
 int tlb200_orthonormalize(const void* z, int64_t rows, int64_t rank, int64_t row_stride,
-                          int64_t col_stride, int dtype, void* out, int64_t out_ld,
+                          int64_t col_stride, int dtype, void* out, int64_t out_ld, int passes,
                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* Eigendecomposition of a small symmetric matrix (n <= 64): cyclic Jacobi with parallel ordering in fp64, one CTA.

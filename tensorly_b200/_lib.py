@@ -84,8 +84,8 @@ SIGNATURES = {
     "tlb200_cp_impute": (c_int, [c_void_p, c_void_p, _VPP, _I64P, _I64P, _I64P, c_int, c_int64, c_void_p, c_int, c_void_p,
                                  c_void_p, c_void_p, c_size_t, c_void_p]),
     "tlb200_orthonormalize_workspace_bytes": (c_size_t, [c_int64, c_int64]),
-    "tlb200_orthonormalize": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p,
-                                      c_size_t, c_void_p]),
+    "tlb200_orthonormalize": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_int64, c_int,
+                                      c_void_p, c_size_t, c_void_p]),
     "tlb200_symeig": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "tlb200_hals_workspace_bytes": (c_size_t, [c_int64]),
     "tlb200_hals_update": (c_int, [_VPP, c_int, c_int, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64,

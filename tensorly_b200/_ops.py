@@ -714,9 +714,10 @@ def cp_impute(tensor: torch.Tensor, mask: torch.Tensor, cp_tensor, out: torch.Te
 
 
 # --------------------------------------------------------------------------- HOOI pieces
-def orthonormalize(z: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+def orthonormalize(z: torch.Tensor, out: torch.Tensor | None = None, passes: int = 2) -> torch.Tensor:
     """Orthonormal basis of the column span of a tall (rows, rank <= 64) block: Cholesky-QR with the small Gram
-    matrix, its factor and inverse in fp64 (tlb200_orthonormalize)."""
+    matrix, its factor and inverse in fp64 (tlb200_orthonormalize); `passes=2` repeats it on the result (orthonormal
+    to rounding), `passes=1` leaves an orthogonality defect of about cond(z)^2 * 1e-16."""
     _check_tensor(z, "z")
     if z.dim() != 2:
         raise ValueError("orthonormalize expects a matrix")
@@ -732,7 +733,7 @@ def orthonormalize(z: torch.Tensor, out: torch.Tensor | None = None) -> torch.Te
     ws = _zero_workspace(nbytes, z)
     with _Device(z):
         st = lib.tlb200_orthonormalize(z.data_ptr(), rows, rank, z.stride(0), z.stride(1), _DTYPES[z.dtype], out.data_ptr(),
-                                       out.stride(0), ws.data_ptr(), ws.numel(), _stream(z))
+                                       out.stride(0), int(passes), ws.data_ptr(), ws.numel(), _stream(z))
     _lib.check(st, "orthonormalize")
     return out
 

@@ -163,6 +163,10 @@ class CPALS:
         self.update = update
         self.l2_reg = float(l2_reg or 0.0)
         self.weights = weights
+        # all-ones weights (what every driver here produces: the reference keeps the scale in the factors,
+        # _cp.py:102-121) are passed to the kernels as "no weights": multiplying by 1 is exact, and the kernels can
+        # then read an unweighted factor matrix in place instead of building a weighted Khatri-Rao table first
+        self._w = None if bool(torch.all(weights == 1)) else weights
         # own the factor buffers (row-major) — the caller's tensors are never mutated
         self.factors: List[torch.Tensor] = [f.clone().contiguous() for f in factors]
         self.rank = self.factors[0].shape[1]
@@ -230,9 +234,9 @@ class CPALS:
         packed = self._pack is not None and mode == self._pack_mode
         out = self._pack_m if packed else None
         if self._contracted is not None and mode < self.ndim - 1:
-            m = self.ops.mttkrp_from_ttm(self._contracted, (self.weights, self.factors), mode, out=out)
+            m = self.ops.mttkrp_from_ttm(self._contracted, (self._w, self.factors), mode, out=out)
         else:
-            m = self.ops.mttkrp(self.x, (self.weights, self.factors), mode, out=out)
+            m = self.ops.mttkrp(self.x, (self._w, self.factors), mode, out=out)
         if packed:
             self.comm.all_reduce(self._pack)     # this mode's MTTKRP partial + the sharded mode's Gram partial
         elif self.shard_mode is not None and mode != self.shard_mode:
@@ -279,7 +283,7 @@ class CPALS:
         if with_error:
             if self.modes[-1] != self.ndim - 1:
                 # the fast error needs the last mode's MTTKRP with the current factors
-                self.mttkrp_last = self.ops.mttkrp(self.x, (self.weights, self.factors), self.ndim - 1)
+                self.mttkrp_last = self.ops.mttkrp(self.x, (self._w, self.factors), self.ndim - 1)
                 if self.shard_mode is not None and self.shard_mode != self.ndim - 1:
                     self.comm.all_reduce(self.mttkrp_last)
             self._error()

@@ -63,6 +63,17 @@ struct Carver {
     size_t used() const { return align_up(off, 256); }
 };
 
+// A Khatri-Rao table that would be a plain copy of ONE unweighted factor matrix already in the table's layout
+// (row-major, row stride = padded rank, 16-byte aligned): use the factor in place and skip the prep launch.
+template <typename T>
+inline const T* table_is_factor(const T* const* factors, const int64_t* frs, const int64_t* fcs, int first, int count,
+                                const T* weights, int64_t rank, int64_t rank_padded) {
+    if (count != 1 || weights != nullptr || rank != rank_padded) return nullptr;
+    if (fcs[first] != 1 || frs[first] != rank_padded) return nullptr;
+    if (reinterpret_cast<uintptr_t>(factors[first]) % 16) return nullptr;
+    return factors[first];
+}
+
 // ---- internal launchers shared between translation units ------------------
 // Khatri-Rao of `nmats` matrices into out[(rows), ld]; columns [rank, pad_cols) are
 // written as zero.  Unlike the public entry point, weights are applied even for a

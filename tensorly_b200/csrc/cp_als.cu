@@ -100,7 +100,8 @@ gram_reduce_kernel(const T* __restrict__ partial, int nblk, int RR, T* __restric
 }
 
 // ---- CP update: V, LU with partial pivoting, solve for a block of rows ---------------
-constexpr int kSolveRows = 64;   // rows of M per CTA
+constexpr int kSolveRows = 64;   // rows of M per CTA (general path)
+constexpr int kFastRows = 32;    // rows of M per CTA on the register-LU path: two passes of 16 rows x 16 lanes
 constexpr int kSolveThreads = 256;
 
 // A = V^T in shared memory (ld = R + 1); perm[] row permutation.  All 256 threads of the CTA, arranged
@@ -219,8 +220,7 @@ __device__ __forceinline__ void gram_tail(const GramTail<T>& gt, const T* Y, int
 // of code) while every register index is static.  Step k: the unused row with the largest |a[0]| (one redux +
 // ballot in fp32) publishes its rotated row as Urot[k] through shared memory (vector stores); everyone else
 // eliminates against it and shifts left.  Multipliers go to Lraw[original row][k].
-// Substitution: one thread per right-hand side, the vector in registers and rotated the same way (axpy form,
-// like trsm): no shuffles, no barriers, no shared-memory round trip on the dependency chain.
+// Substitution: 16 lanes per right-hand side (axpy form, like trsm), see solve_fast.
 template <int RM>
 __device__ __forceinline__ void lu_barrier() {
     if constexpr (RM > 32) asm volatile("bar.sync 1, %0;" ::"n"(RM) : "memory");
@@ -261,13 +261,14 @@ struct SolveSmem {
     T* Y;       // [kSolveRows][ld] right-hand sides, then solutions
     T* Lraw;    // [R][ld]   multipliers by original row
     T* Urot;    // [R][RM]   Urot[k][j] = U[k][k+j]
-    T* Lcol;    // [R][RM]   Lcol[k][j] = L[k+j][k], j >= 1
-    T* Ucol;    // [R][RM]   Ucol[k][j] = U[k-j][k], j >= 1
+    T* Lcol;    // [R][RM]   Lcol[k][i] = L[i][k] for i > k, else 0   (column k of L, un-rotated)
+    T* Ucol;    // [R][RM]   Ucol[k][i] = U[i][k] for i < k, else 0   (column k of U)
+    T* inv;     // [RM]      1 / U[k][k]
     T* s_val;   // [4]
     int* perm;  // [R]
     int* s_idx; // [4]
     unsigned* s_key;  // [4]
-    __host__ __device__ static size_t elems(int R) { return (size_t)(2 * R + 64) * (R + 1) + 3 + (size_t)3 * R * RM + 4; }
+    __host__ __device__ static size_t elems(int R) { return (size_t)(2 * R + 64) * (R + 1) + 3 + (size_t)3 * R * RM + RM + 4; }
     __host__ __device__ static size_t bytes(int R) { return sizeof(T) * elems(R) + sizeof(int) * (R + 8); }
     __device__ SolveSmem(unsigned char* raw, int R) {
         const int ld = R + 1;
@@ -279,7 +280,8 @@ struct SolveSmem {
         Urot = A + off;
         Lcol = Urot + R * RM;
         Ucol = Lcol + R * RM;
-        s_val = Ucol + R * RM;
+        inv = Ucol + R * RM;
+        s_val = inv + RM;
         perm = reinterpret_cast<int*>(s_val + 4);
         s_idx = perm + R;
         s_key = reinterpret_cast<unsigned*>(s_idx + 4);
@@ -343,13 +345,13 @@ __device__ __forceinline__ void lu_factor_rot(int R, const SolveSmem<T, RM>& sm,
     }
 }
 
-// One CTA: factor V^T, then solve kSolveRows right-hand sides (rows of M).  `tmp` = this thread's share of the
+// One CTA: factor V^T, then solve kFastRows right-hand sides (rows of M).  `tmp` = this thread's share of the
 // right-hand sides, fetched by the caller before the factorisation so the loads are long done.
 template <typename T, int RM>
 __device__ __forceinline__ void solve_fast(unsigned char* raw, const GramList<T>& gl, int mode, int R, const T* __restrict__ w,
                                            T l2, const T* __restrict__ m, int64_t m_ld, int64_t rows, T* __restrict__ out,
                                            int64_t out_ld, const GramTail<T>& gtail) {
-    constexpr int kRows = 64;
+    constexpr int kRows = kFastRows;
     const SolveSmem<T, RM> sm(raw, R);
     const int ld = R + 1;
     const int tid = threadIdx.x;
@@ -391,33 +393,64 @@ __device__ __forceinline__ void solve_fast(unsigned char* raw, const GramList<T>
     }
     CP_TRACE(2);
     __syncthreads();
-    // substitution operands: columns of L below / of U above the diagonal, contiguous and zero padded
+    // substitution operands: whole columns of L (below the diagonal) and of U (above it), zero elsewhere, so the
+    // updates below need no bounds: Lcol[k][i] = L[i][k], Ucol[k][i] = U[i][k]; inv[k] = 1 / U[k][k]
     for (int e = tid; e < R * RM; e += 256) {
-        const int k = e / RM, j = e - k * RM;
-        sm.Lcol[e] = (j >= 1 && k + j < R) ? sm.Lraw[sm.perm[k + j] * ld + k] : T(0);
-        sm.Ucol[e] = (j >= 1 && j <= k) ? sm.Urot[(k - j) * RM + j] : T(0);
+        const int k = e / RM, i = e - k * RM;
+        sm.Lcol[e] = (i > k && i < R) ? sm.Lraw[sm.perm[i] * ld + k] : T(0);
+        sm.Ucol[e] = i < k ? sm.Urot[i * RM + (k - i)] : T(0);
     }
+    for (int k = tid; k < RM; k += 256) sm.inv[k] = k < R ? T(1) / sm.Urot[k * RM] : T(0);
     __syncthreads();
     CP_TRACE(3);
-    if (tid < kRows) {
-        T* y = sm.Y + tid * ld;
-        T b[RM];
+    // 16 lanes per right-hand side: lane l of a group owns the entries i = l, l + 16, ... of its vector.  Step k:
+    // the owner of entry k broadcasts it inside the group (one shuffle), everyone applies column k to its entries
+    // (axpy form, like trsm): RM / 16 FMAs per lane and step, the shuffle is the only thing on the dependency chain.
+    constexpr int NS = RM / 16;
+    const int grp = tid >> 4, l16 = tid & 15;
+#pragma unroll 1
+    for (int pass = 0; pass < kRows / 16; ++pass) {
+        T* y = sm.Y + (pass * 16 + grp) * ld;
+        T b[NS];
 #pragma unroll
-        for (int j = 0; j < RM; ++j) b[j] = j < R ? y[sm.perm[j]] : T(0);      // P * rhs
+        for (int t = 0; t < NS; ++t) {
+            const int i = t * 16 + l16;
+            b[t] = i < R ? y[sm.perm[i]] : T(0);                 // P * rhs
+        }
+        __syncwarp();
         // forward substitution, unit lower triangular
-        for (int k = 0; k < R; ++k) {
-            const T yk = b[0];
-            y[k] = yk;
-            axpy_rotate<T, RM>(b, sm.Lcol + k * RM, yk, false);
+#pragma unroll
+        for (int sl = 0; sl < NS; ++sl) {
+#pragma unroll 4
+            for (int kk = 0; kk < 16; ++kk) {
+                const int k = sl * 16 + kk;
+                if (k >= R) break;
+                const T yk = __shfl_sync(0xffffffffu, b[sl], kk, 16);
+                const T* c = sm.Lcol + k * RM + l16;
+#pragma unroll
+                for (int t = 0; t < NS; ++t) b[t] = fma(-c[t * 16], yk, b[t]);
+            }
         }
         CP_TRACE(4);
+        // back substitution: x_k = b_k / U_kk, then b_i -= U[i][k] x_k for i < k
 #pragma unroll
-        for (int j = 0; j < RM; ++j) b[j] = j < R ? y[R - 1 - j] : T(0);
-        // back substitution
-        for (int k = R - 1; k >= 0; --k) {
-            const T xk = b[0] / sm.Urot[k * RM];
-            y[k] = xk;
-            axpy_rotate<T, RM>(b, sm.Ucol + k * RM, xk, false);
+        for (int sl = NS - 1; sl >= 0; --sl) {
+#pragma unroll 4
+            for (int kk = 15; kk >= 0; --kk) {
+                const int k = sl * 16 + kk;
+                if (k >= R) continue;
+                const T xk = __shfl_sync(0xffffffffu, b[sl] * sm.inv[k], kk, 16);
+                if (l16 == kk) b[sl] = xk;
+                const T* c = sm.Ucol + k * RM + l16;
+#pragma unroll
+                for (int t = 0; t < NS; ++t) b[t] = fma(-c[t * 16], xk, b[t]);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < NS; ++t) {
+            const int i = t * 16 + l16;
+            if (i < R) y[i] = b[t];
         }
     }
     CP_TRACE(5);
@@ -689,7 +722,8 @@ int cp_update_launch(const void* const* grams, int nmodes, int mode, int64_t R, 
     static std::atomic<uint64_t> attr_done{0};        // one per instantiation (T), one bit per device
     if (ensure_dynamic_smem(cp_update_kernel<T>, 200 * 1024, attr_done)) return TLB200_ECUDA;
     if (smem > 200 * 1024) return TLB200_EUNSUPPORTED;
-    const int nblk = (int)ceil_div(rows, kSolveRows);
+    const bool fast = R <= 32 || (sizeof(T) == 4 && R <= 64);          // must match the dispatch in cp_update_kernel
+    const int nblk = (int)ceil_div(rows, fast ? kFastRows : kSolveRows);
     if (nblk == 0) return TLB200_OK;
     GramTail<T> gt;
     gt.partial = nullptr; gt.gram = gram_out; gt.counter = nullptr;
@@ -756,7 +790,7 @@ extern "C" int tlb200_cp_update(const void* const* grams, int nmodes, int mode, 
 
 extern "C" size_t tlb200_cp_update_gram_workspace_bytes(int64_t rows, int64_t rank, int dtype) {
     if (rows < 0 || rank < 1 || !dtype_valid(dtype)) return 0;
-    return 256 + align_up((size_t)ceil_div(rows > 0 ? rows : 1, kSolveRows) * rank * rank * dtype_size(dtype), 256);
+    return 256 + align_up((size_t)ceil_div(rows > 0 ? rows : 1, kFastRows) * rank * rank * dtype_size(dtype), 256);
 }
 
 extern "C" int tlb200_cp_update_gram(const void* const* grams, int nmodes, int mode, int64_t rank, const void* weights,

@@ -200,21 +200,30 @@ int run(const T* t, const int64_t* lead_shape, int nlead, int mode, const T* con
         const int64_t* fcs, int64_t rank, const T* weights, T* out, int64_t out_ld, void* workspace, const Geometry& g,
         cudaStream_t stream) {
     Carver ws(workspace);
-    T* P = g.pc > 0 ? ws.take<T>((size_t)g.A * rank) : nullptr;
-    T* Q = g.qc > 0 ? ws.take<T>((size_t)g.B * rank) : nullptr;
+    const T* P = g.pc > 0 ? ws.take<T>((size_t)g.A * rank) : nullptr;
+    const T* Q = g.qc > 0 ? ws.take<T>((size_t)g.B * rank) : nullptr;
     T* partial = g.splits > 1 ? ws.take<T>((size_t)g.splits * g.J * rank) : nullptr;
     const T* w = weights;      // folded into the first table that exists
     int st;
+    // a table made of one unweighted, row-major factor is used in place (3-way sweeps: no prep launch at all)
     if (P) {
-        st = launch_khatri_rao<T>(factors + g.pf, lead_shape + g.pf, frs + g.pf, fcs + g.pf, g.pc, rank, w, nullptr, P, rank,
-                                  rank, stream);
-        if (st) return st;
-        w = nullptr;
+        if (const T* direct = table_is_factor<T>(factors, frs, fcs, g.pf, g.pc, w, rank, rank)) {
+            P = direct;
+        } else {
+            st = launch_khatri_rao<T>(factors + g.pf, lead_shape + g.pf, frs + g.pf, fcs + g.pf, g.pc, rank, w, nullptr,
+                                      const_cast<T*>(P), rank, rank, stream);
+            if (st) return st;
+            w = nullptr;
+        }
     }
     if (Q) {
-        st = launch_khatri_rao<T>(factors + g.qf, lead_shape + g.qf, frs + g.qf, fcs + g.qf, g.qc, rank, w, nullptr, Q, rank,
-                                  rank, stream);
-        if (st) return st;
+        if (const T* direct = table_is_factor<T>(factors, frs, fcs, g.qf, g.qc, w, rank, rank)) {
+            Q = direct;
+        } else {
+            st = launch_khatri_rao<T>(factors + g.qf, lead_shape + g.qf, frs + g.qf, fcs + g.qf, g.qc, rank, w, nullptr,
+                                      const_cast<T*>(Q), rank, rank, stream);
+            if (st) return st;
+        }
     }
     T* dst = partial ? partial : out;
     const int64_t dst_ld = partial ? rank : out_ld;

@@ -97,14 +97,17 @@ hals_kernel(const HalsParams<T> p) {
         s2 += (double)v * (double)v;
     }
     __syncthreads();
-    T g[RM];
+    // The gradient is carried in DOUBLE whatever T is: it is updated incrementally R x n_iter times, and in fp32 the
+    // rounding drift of those updates (a difference of large terms) reached 2e-4 of the solution after 100 passes,
+    // whereas the reference recomputes every dot product from scratch.
+    double g[RM];
 #pragma unroll
-    for (int j = 0; j < RM; ++j) g[j] = (live && j < R) ? p.m[col * p.m_rs + j * p.m_cs] : T(0);
+    for (int j = 0; j < RM; ++j) g[j] = (live && j < R) ? (double)p.m[col * p.m_rs + j * p.m_cs] : 0.0;
     for (int k = 0; k < R; ++k) {          // g[j] -= UtU[j][k] * v_k, with UtU[j][k] = Urot[k][(j - k) mod RM]
-        const T vk = vs[k * HT + tid];
+        const double vk = (double)vs[k * HT + tid];
         const T* c = Urot + k * RM;
 #pragma unroll
-        for (int j = 0; j < RM; ++j) g[j] -= c[(j - k) & (RM - 1)] * vk;
+        for (int j = 0; j < RM; ++j) g[j] -= (double)c[(j - k) & (RM - 1)] * vk;
     }
 
     const double Rd = (double)R;
@@ -114,10 +117,10 @@ hals_kernel(const HalsParams<T> p) {
         double rec = 0.0;
         for (int k = 0; k < RM; ++k) {
             const T dkk = diag[k];
-            T delta = T(0);
+            double delta = 0.0;
             if (k < R && dkk != T(0)) {
                 const T vk = vs[k * HT + tid];
-                T num = g[0] + dkk * vk;
+                T num = (T)(g[0] + (double)dkk * (double)vk);
                 T den = dkk;
                 if (p.has_sparsity) num -= p.sparsity;
                 if (p.has_ridge) den += T(2) * p.ridge;
@@ -129,14 +132,14 @@ hals_kernel(const HalsParams<T> p) {
                     s1 += nd - (double)vk;
                     s2 += nd * nd - (double)vk * (double)vk;
                 }
-                delta = nv - vk;
+                delta = (double)nv - (double)vk;
                 vs[k * HT + tid] = nv;
             }
             // g <- rotate_left(g - delta * UtU[:, k]): coordinate k + 1 moves to register 0
             const T* c = Urot + k * RM;
-            const T g0 = g[0] - delta * c[0];
+            const double g0 = g[0] - delta * (double)c[0];
 #pragma unroll
-            for (int j = 1; j < RM; ++j) g[j - 1] = g[j] - delta * c[j];
+            for (int j = 1; j < RM; ++j) g[j - 1] = g[j] - delta * (double)c[j];
             g[RM - 1] = g0;
         }
         // global stopping statistic, fixed summation order

@@ -126,7 +126,7 @@ static int run(const T* x, const int64_t* shape, int ndim, int mode, const T* co
                const int64_t* frs, const int64_t* fcs, int64_t rank, const T* weights, T* out,
                int64_t out_ld, void* workspace, const tlb200_mttkrp_plan_t& pl, cudaStream_t stream) {
     Carver ws(workspace);
-    T* P = pl.p_count > 0 ? ws.take<T>((size_t)pl.A * pl.rank_padded) : nullptr;
+    const T* P = pl.p_count > 0 ? ws.take<T>((size_t)pl.A * pl.rank_padded) : nullptr;
     T* Q = ws.take<T>((size_t)2 * (pl.B + 64) * pl.rank_padded);
     T* partial = ws.take<T>((size_t)pl.splits * pl.J * pl.rank_padded);
 
@@ -135,10 +135,15 @@ static int run(const T* x, const int64_t* shape, int ndim, int mode, const T* co
     const T* w = ndim == 2 ? nullptr : weights;
     int st;
     if (pl.p_count > 0) {
-        st = launch_khatri_rao<T>(factors + pl.p_first, shape + pl.p_first, frs + pl.p_first, fcs + pl.p_first,
-                                  pl.p_count, rank, w, nullptr, P, pl.rank_padded, pl.rank_padded, stream);
-        if (st) return st;
-        w = nullptr;  // weights go to the first non-skipped factor only
+        // 3-way tensors with unit weights: the outer table IS the factor matrix — no prep launch
+        if (const T* direct = table_is_factor<T>(factors, frs, fcs, pl.p_first, pl.p_count, w, rank, pl.rank_padded)) {
+            P = direct;
+        } else {
+            st = launch_khatri_rao<T>(factors + pl.p_first, shape + pl.p_first, frs + pl.p_first, fcs + pl.p_first,
+                                      pl.p_count, rank, w, nullptr, const_cast<T*>(P), pl.rank_padded, pl.rank_padded, stream);
+            if (st) return st;
+            w = nullptr;  // weights go to the first non-skipped factor only
+        }
     }
     if (pl.path == TLB200_PATH_TCGEN05) {
         // the tensor-core engine takes Q transposed ([rank_padded][Bpad], K-major rows, zero padded) and already

@@ -237,8 +237,8 @@ symeig_jacobi_kernel(const T* __restrict__ a, int n, int64_t lda, T* __restrict_
 }
 
 template <typename T>
-int run(const T* z, int64_t rows, int64_t R, int64_t rs, int64_t cs, T* out, int64_t out_ld, void* workspace,
-        cudaStream_t stream) {
+int run_pass(const T* z, int64_t rows, int64_t R, int64_t rs, int64_t cs, T* out, int64_t out_ld, void* workspace,
+             cudaStream_t stream) {
     // workspace: [counter + status, 256 B][R^{-1}, fp64][partials, fp64]
     unsigned* counter = static_cast<unsigned*>(workspace);
     int* status = reinterpret_cast<int*>(counter + 1);
@@ -262,6 +262,16 @@ int run(const T* z, int64_t rows, int64_t R, int64_t rs, int64_t cs, T* out, int
 }  // namespace tlb200
 
 using namespace tlb200;
+
+// passes = 1: plain Cholesky-QR (orthogonality ~ cond(Z)^2 x 1e-16); passes = 2: a second pass on the result
+// ("CholQR2": orthogonal to the rounding of the output type whenever cond(Z)^2 < 1e16).
+template <typename T>
+int run(const T* z, int64_t rows, int64_t R, int64_t rs, int64_t cs, T* out, int64_t out_ld, void* workspace, int passes,
+        cudaStream_t stream) {
+    int st = run_pass<T>(z, rows, R, rs, cs, out, out_ld, workspace, stream);
+    if (st || passes < 2) return st;
+    return run_pass<T>(out, rows, R, out_ld, 1, out, out_ld, workspace, stream);
+}
 
 extern "C" int tlb200_symeig(const void* a, int64_t n, int64_t lda, int dtype, void* evals, void* evecs, int64_t ldv,
                              void* stream) {
@@ -288,14 +298,14 @@ extern "C" size_t tlb200_orthonormalize_workspace_bytes(int64_t rows, int64_t ra
 }
 
 extern "C" int tlb200_orthonormalize(const void* z, int64_t rows, int64_t rank, int64_t row_stride, int64_t col_stride,
-                                     int dtype, void* out, int64_t out_ld, void* workspace, size_t workspace_bytes,
-                                     void* stream) {
+                                     int dtype, void* out, int64_t out_ld, int passes, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
     if (!z || !out || !workspace || rows < 1 || rank < 1 || out_ld < rank || !dtype_valid(dtype)) return TLB200_EINVAL;
     if (rank > OR_MAX || rows < rank) return TLB200_EUNSUPPORTED;
     if (workspace_bytes < tlb200_orthonormalize_workspace_bytes(rows, rank)) return TLB200_EWORKSPACE;
     set_last_path("simt");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == TLB200_F32)
-        return run<float>((const float*)z, rows, rank, row_stride, col_stride, (float*)out, out_ld, workspace, s);
-    return run<double>((const double*)z, rows, rank, row_stride, col_stride, (double*)out, out_ld, workspace, s);
+        return run<float>((const float*)z, rows, rank, row_stride, col_stride, (float*)out, out_ld, workspace, passes, s);
+    return run<double>((const double*)z, rows, rank, row_stride, col_stride, (double*)out, out_ld, workspace, passes, s);
 }

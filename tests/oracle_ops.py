@@ -120,7 +120,7 @@ class OracleOps:
         return torch.from_numpy(np.ascontiguousarray(O.unfold(_np(x), mode)))
 
     @staticmethod
-    def orthonormalize(z, out=None):
+    def orthonormalize(z, out=None, passes=2):
         """Cholesky-QR in fp64, like tlb200_orthonormalize."""
         zz = _np(z).astype(np.float64)
         r = np.linalg.cholesky(zz.T @ zz).T
