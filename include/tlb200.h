@@ -288,6 +288,15 @@ int tlb200_orthonormalize(const void* z, int64_t rows, int64_t rank, int64_t row
                           int64_t col_stride, int dtype, void* out, int64_t out_ld, int passes,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* `steps` warm-started power steps  U <- orth(G U)  in place, fp64: G (n x n, symmetric, row stride g_ld), U (n x p,
+ * p <= 64 <= n, row stride u_ld).  Two launches per step (GEMM block + Gram partial + Cholesky/inverse in the last
+ * CTA; apply).  With tlb200_orthonormalize / tlb200_symeig this is the in-loop "SVD" of the own HOOI driver
+ * (tensorly/decomposition/_tucker.py:197-201).  Workspace: first 8 bytes zero before the first call (left zero). */
+size_t tlb200_subspace_iterate_workspace_bytes(int64_t n, int64_t p);
+
+int tlb200_subspace_iterate(const void* g, int64_t n, int64_t g_ld, void* u, int64_t p, int64_t u_ld,
+                            int steps, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Eigendecomposition of a small symmetric matrix (n <= 64): cyclic Jacobi with parallel ordering in fp64, one CTA.
  * evals (n) in DESCENDING order, evecs (n x n, row stride ldv) with the eigenvectors as columns.  The Rayleigh-Ritz
  * step of the HOOI subspace iteration (it replaces the ordering that the SVD of tensorly/tenalg/svd.py:211-235

@@ -91,6 +91,9 @@ SIGNATURES = {
     "tlb200_hals_update": (c_int, [_VPP, c_int, c_int, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64,
                                    c_int64, c_int64, c_int, c_double, POINTER(c_double), POINTER(c_double), c_double, c_int,
                                    c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tlb200_subspace_iterate_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "tlb200_subspace_iterate": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_size_t,
+                                        c_void_p]),
 }
 
 _lib = None

@@ -807,3 +807,27 @@ def hals_nnls(UtM, UtU, V=None, n_iter_max=500, tol=1e-8, sparsity_coefficient=N
     hals_update([UtU.contiguous()], -1, None, UtM.transpose(0, 1), out.transpose(0, 1), n_iter_max, tol,
                 sparsity_coefficient, ridge_coefficient, epsilon)
     return out
+
+
+def subspace_iterate(g: torch.Tensor, u: torch.Tensor, steps: int) -> torch.Tensor:
+    """`steps` power steps u <- orth(g u) IN PLACE (fp64; g symmetric n x n, u n x p with p <= 64): two launches per
+    step (tlb200_subspace_iterate).  Returns u."""
+    _check_tensor(g, "g")
+    _check_tensor(u, "u", g)
+    if g.dtype != torch.float64:
+        raise TypeError("subspace_iterate runs in float64")
+    if g.dim() != 2 or g.shape[0] != g.shape[1] or u.dim() != 2 or u.shape[0] != g.shape[0]:
+        raise ValueError(f"subspace_iterate: g {tuple(g.shape)} and u {tuple(u.shape)} do not match")
+    if g.stride(1) != 1 or u.stride(1) != 1:
+        raise ValueError("subspace_iterate needs row-major g and u")
+    n, p = u.shape
+    lib = _lib.load()
+    nbytes = lib.tlb200_subspace_iterate_workspace_bytes(n, p)
+    if nbytes == 0 or n < p:
+        raise ValueError(f"subspace_iterate: unsupported block {tuple(u.shape)} (at most 64 columns, rows >= columns)")
+    ws = _zero_workspace(nbytes, g)
+    with _Device(g):
+        st = lib.tlb200_subspace_iterate(g.data_ptr(), n, g.stride(0), u.data_ptr(), p, u.stride(0), int(steps), ws.data_ptr(),
+                                         ws.numel(), _stream(g))
+    _lib.check(st, "subspace_iterate")
+    return u

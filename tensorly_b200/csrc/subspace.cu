@@ -125,6 +125,171 @@ orth_apply_kernel(const T* __restrict__ z, int64_t rows, int R, int64_t rs, int6
     }
 }
 
+// ---- fused power step of the HOOI subspace iteration (fp64): U <- orth(G U) ------------------------------------
+// kernel A (n / 16 CTAs): a 16-row block of Z = G U, its p x p Gram partial; the last CTA to arrive sums the
+//           partials in block order, factors S = R^T R and writes R^{-1}.
+// kernel B (n / 16 CTAs): U = Z R^{-1}.
+// G (n x n) and U (n x p, p <= 64) are read from L2; nothing here is bandwidth-relevant — the step is a latency chain
+// (GEMM block ~4 us, Cholesky + triangular inverse of a 64 x 64 matrix ~20 us, apply ~3 us), which is why it is two
+// launches instead of the five (TTM prep + TTM + 2 orth kernels + copies) the generic entry points would take.
+constexpr int PS_ROWS = 16;
+constexpr int PS_KC = 64;
+
+// Cholesky S = R^T R in shared memory followed by R^{-1} (upper triangular), 256 threads.  S is [64][65].
+__device__ void chol_inverse_64(double (*S)[OR_MAX + 1], double (*Ri)[OR_MAX + 1], int R, int* bad_out) {
+    const int tid = threadIdx.x;
+    // thread t updates the 16 elements (i, j) = (ti + 16 a, tj + 16 b) — fixed, no divisions inside the k loop
+    const int ti = tid >> 4, tj = tid & 15;
+    int bad = 0;
+    for (int k = 0; k < R; ++k) {
+        if (tid == 0) {
+            double d = S[k][k];
+            if (!(d > 0.0)) { d = 1e-300; bad = 1; }
+            S[k][k] = sqrt(d);
+        }
+        __syncthreads();
+        const double inv = 1.0 / S[k][k];
+        if (tid > k && tid < R) S[k][tid] *= inv;
+        __syncthreads();
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int i = ti + 16 * a;
+            if (i <= k || i >= R) continue;
+            const double rki = S[k][i];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int j = tj + 16 * b;
+                if (j >= i && j < R) S[i][j] -= rki * S[k][j];
+            }
+        }
+        // no barrier needed before the next diagonal: S[k+1][k+1] is updated by exactly one thread, but the
+        // sqrt is taken by thread 0 -> barrier
+        __syncthreads();
+    }
+    // R^{-1} column by column: thread group of 4 per column (256 threads = 64 columns x 4), partial sums by lanes
+    {
+        const int c = tid >> 2, q = tid & 3;
+        for (int i = R - 1; i >= 0; --i) {
+            double part = 0.0;
+            if (c < R && i < c)
+                for (int j = i + 1 + q; j <= c; j += 4) part += S[i][j] * Ri[j][c];
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            if (q == 0 && c < R) Ri[i][c] = i > c ? 0.0 : ((i == c ? 1.0 : 0.0) - part) / S[i][i];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && bad_out) *bad_out = bad;
+}
+
+__global__ void __launch_bounds__(256)
+power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const double* __restrict__ U, int p,
+                    int64_t u_ld, double* __restrict__ Z, double* __restrict__ partial, unsigned* __restrict__ counter,
+                    double* __restrict__ rinv, int* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char ps_smem[];
+    typedef double Row[OR_MAX + 1];
+    // [Us: PS_KC x 64][Gs: 16 x 65]   later, in the last CTA only: [S: 64 x 65][Ri: 64 x 65]
+    double* Us = reinterpret_cast<double*>(ps_smem);                 // [PS_KC][64]
+    Row* Gs = reinterpret_cast<Row*>(Us + PS_KC * OR_MAX);           // [PS_ROWS][65]
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    const int r = tid >> 4, c4 = (tid & 15) * 4;
+    const int64_t row0 = (int64_t)blockIdx.x * PS_ROWS;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int64_t k0 = 0; k0 < n; k0 += PS_KC) {
+        __syncthreads();
+        for (int e = tid; e < PS_ROWS * PS_KC; e += 256) {
+            const int rr = e >> 6, kk = e & 63;
+            Gs[rr][kk] = (row0 + rr < n && k0 + kk < n) ? G[(row0 + rr) * g_ld + k0 + kk] : 0.0;
+        }
+        for (int e = tid; e < PS_KC * OR_MAX; e += 256) {
+            const int kk = e >> 6, c = e & 63;
+            Us[e] = (k0 + kk < n && c < p) ? U[(k0 + kk) * u_ld + c] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < PS_KC; ++kk) {
+            const double g = Gs[r][kk];
+            const double2 u0 = *reinterpret_cast<const double2*>(Us + kk * OR_MAX + c4);
+            const double2 u1 = *reinterpret_cast<const double2*>(Us + kk * OR_MAX + c4 + 2);
+            acc[0] = fma(g, u0.x, acc[0]); acc[1] = fma(g, u0.y, acc[1]);
+            acc[2] = fma(g, u1.x, acc[2]); acc[3] = fma(g, u1.y, acc[3]);
+        }
+    }
+    __syncthreads();
+    // the Z block: to global, and into shared memory (over the U tile) for its Gram partial
+    double* Zs = Us;                                                 // [PS_ROWS][64]
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        Zs[r * OR_MAX + c4 + t] = acc[t];
+        if (row0 + r < n && c4 + t < p) Z[(row0 + r) * p + c4 + t] = acc[t];
+    }
+    __syncthreads();
+    {
+        double* mine = partial + (size_t)blockIdx.x * p * p;
+        const int a0 = tid >> 4, b0 = tid & 15;                      // outputs (a0 + 16 x, b0 + 16 y)
+        for (int x = 0; x < 4; ++x)
+            for (int y = 0; y < 4; ++y) {
+                const int a = a0 + 16 * x, b = b0 + 16 * y;
+                if (a >= p || b >= p) continue;
+                double sacc = 0.0;
+#pragma unroll
+                for (int i = 0; i < PS_ROWS; ++i) sacc = fma(Zs[i * OR_MAX + a], Zs[i * OR_MAX + b], sacc);
+                mine[a * p + b] = sacc;
+            }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    Row* S = reinterpret_cast<Row*>(ps_smem);
+    Row* Ri = S + OR_MAX;
+    for (int e = tid; e < p * p; e += 256) {
+        double t = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(partial + (size_t)b * p * p + e);
+        S[e / p][e % p] = t;
+    }
+    __syncthreads();
+    chol_inverse_64(S, Ri, p, status);
+    for (int e = tid; e < p * p; e += 256) rinv[e] = Ri[e / p][e % p];
+    if (tid == 0) *counter = 0u;
+}
+
+__global__ void __launch_bounds__(256)
+power_step_b_kernel(const double* __restrict__ Z, int64_t n, int p, const double* __restrict__ rinv, double* __restrict__ U,
+                    int64_t u_ld) {
+    __shared__ double Ri[OR_MAX * OR_MAX];       // 32 KB
+    __shared__ double Zs[PS_ROWS][OR_MAX + 1];
+    const int tid = threadIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * PS_ROWS;
+    for (int e = tid; e < OR_MAX * OR_MAX; e += 256) {
+        const int i = e >> 6, j = e & 63;
+        Ri[e] = (i < p && j < p) ? rinv[i * p + j] : 0.0;
+    }
+    for (int e = tid; e < PS_ROWS * OR_MAX; e += 256) {
+        const int rr = e >> 6, c = e & 63;
+        Zs[rr][c] = (row0 + rr < n && c < p) ? Z[(row0 + rr) * p + c] : 0.0;
+    }
+    __syncthreads();
+    const int r = tid >> 4, c4 = (tid & 15) * 4;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 8
+    for (int i = 0; i < OR_MAX; ++i) {
+        const double z = Zs[r][i];
+        const double2 a0 = *reinterpret_cast<const double2*>(Ri + i * OR_MAX + c4);
+        const double2 a1 = *reinterpret_cast<const double2*>(Ri + i * OR_MAX + c4 + 2);
+        acc[0] = fma(z, a0.x, acc[0]); acc[1] = fma(z, a0.y, acc[1]);
+        acc[2] = fma(z, a1.x, acc[2]); acc[3] = fma(z, a1.y, acc[3]);
+    }
+    if (row0 + r < n)
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if (c4 + t < p) U[(row0 + r) * u_ld + c4 + t] = acc[t];
+}
+
 // ---- symmetric eigendecomposition of a small matrix (n <= 64): cyclic Jacobi, parallel ordering --------------
 // One CTA.  A round rotates n/2 disjoint index pairs (round-robin "circle" schedule, n - 1 rounds per sweep):
 // angles from the current A, rows of all pairs, then columns of A and of the eigenvector matrix V.  Sweeps repeat
@@ -271,6 +436,38 @@ int run(const T* z, int64_t rows, int64_t R, int64_t rs, int64_t cs, T* out, int
     int st = run_pass<T>(z, rows, R, rs, cs, out, out_ld, workspace, stream);
     if (st || passes < 2) return st;
     return run_pass<T>(out, rows, R, out_ld, 1, out, out_ld, workspace, stream);
+}
+
+extern "C" size_t tlb200_subspace_iterate_workspace_bytes(int64_t n, int64_t p) {
+    if (n < 1 || p < 1 || p > OR_MAX) return 0;
+    return 256 + sizeof(double) * ((size_t)n * p + align_up((size_t)p * p, 32) + (size_t)ceil_div(n, PS_ROWS) * p * p) + 256;
+}
+
+extern "C" int tlb200_subspace_iterate(const void* g, int64_t n, int64_t g_ld, void* u, int64_t p, int64_t u_ld, int steps,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+    if (!g || !u || !workspace || n < 1 || p < 1 || g_ld < n || u_ld < p || steps < 0) return TLB200_EINVAL;
+    if (p > OR_MAX || n < p) return TLB200_EUNSUPPORTED;
+    if (workspace_bytes < tlb200_subspace_iterate_workspace_bytes(n, p)) return TLB200_EWORKSPACE;
+    set_last_path("simt");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    unsigned* counter = static_cast<unsigned*>(workspace);
+    int* status = reinterpret_cast<int*>(counter + 1);
+    double* rinv = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
+    double* z = rinv + align_up((size_t)p * p, 32);
+    double* partial = z + (size_t)n * p;
+    constexpr int smem_a = 2 * OR_MAX * (OR_MAX + 1) * (int)sizeof(double);       // >= the GEMM phase's tiles
+    static_assert(smem_a >= (int)sizeof(double) * (PS_KC * OR_MAX + PS_ROWS * (OR_MAX + 1)), "tile space");
+    static std::atomic<uint64_t> attr_done{0};
+    if (ensure_dynamic_smem(power_step_a_kernel, smem_a, attr_done)) return TLB200_ECUDA;
+    const int nblk = (int)ceil_div(n, PS_ROWS);
+    for (int it = 0; it < steps; ++it) {
+        power_step_a_kernel<<<nblk, 256, smem_a, s>>>((const double*)g, n, g_ld, (const double*)u, (int)p, u_ld, z, partial,
+                                                      counter, rinv, status);
+        TLB_CHECK_LAUNCH();
+        power_step_b_kernel<<<nblk, 256, 0, s>>>(z, n, (int)p, rinv, (double*)u, u_ld);
+        TLB_CHECK_LAUNCH();
+    }
+    return TLB200_OK;
 }
 
 extern "C" int tlb200_symeig(const void* a, int64_t n, int64_t lda, int dtype, void* evals, void* evecs, int64_t ldv,

@@ -58,7 +58,10 @@ bool geom(int64_t L, int64_t J, int64_t T, int64_t I, TtmGeom* g) {
 
 bool ttm_tc_supported(int64_t L, int64_t J, int64_t T, int64_t I) {
     TtmGeom g;
-    if (I < 1 || I > 4 * kTtmRowBlock) return false;      // beyond 4 passes the SIMT kernel's single pass wins
+    // one pass over the tensor per 64 output rows.  The SIMT alternative is FMA-bound at such widths (measured:
+    // 20 ms for the 512 x 512 Gram matrix of a 512 x 262144 unfolding, i.e. 6.7 TFLOP/s, against ~0.1 ms per pass
+    // here), so up to 16 passes (1024 rows) stay on the tensor cores.
+    if (I < 1 || I > 16 * kTtmRowBlock) return false;
     if (!geom(L, J, T, I < kTtmRowBlock ? I : kTtmRowBlock, &g)) return false;
     if (L * J * T < (1 << 18) || g.M < 32 || J < 16) return false;   // launch-bound sizes: SIMT
     return tc_available();

@@ -13,8 +13,8 @@ orthonormal basis of the dominant left subspace, which is also the dominant eige
 G = unfold(Y, k) unfold(Y, k)^T (I_k x I_k).  Here:
 
     G   = mode_dot(unfold(Y, k), unfold(Y, k), 1)             one pass of the TTM engine (3xTF32), fp32
-    U  <- orth(G U)   `svd_iters` times, warm-started from the previous sweep's factors[k]
-                      G U on the SIMT fp64 TTM kernel, orth = tlb200_orthonormalize (Cholesky-QR in fp64)
+    U  <- orth(G U)   `svd_iters` times, warm-started from the previous sweep's factors[k]: tlb200_subspace_iterate,
+                      two launches per step (fp64 GEMM block + Gram partial + Cholesky-QR factor; apply)
 
 The iteration runs in fp64 on the tiny matrices because a tensor with a dominant mean component makes G U
 ill-conditioned beyond fp32 after one step.  No SVD, no eigendecomposition, no host synchronisation inside the loop.
@@ -23,7 +23,7 @@ What is (deliberately) different from the reference: the factors span the same s
 vectors themselves (any orthonormal basis gives the same reconstruction — Tucker factors are only defined up to a
 rotation that the core absorbs), and the subspace is converged by a fixed number of power steps instead of to LAPACK
 precision: the reconstruction-error trajectory agrees with the reference's to < 1e-4 relative with the default
-`svd_iters=8` (tests/test_gpu_parity.py), tighter with more.  `init="svd"` uses one library `eigh` per mode on the
+`svd_iters=16` (tests/test_gpu_parity.py), tighter with more.  `init="svd"` uses one library `eigh` per mode on the
 Gram matrix of the raw unfolding — initialisation, outside the loop.  Options outside this path (mask,
 fixed_factors, a non-default `svd`, rank > 64) are delegated to the unmodified reference driver on the b200 backend.
 """
@@ -61,7 +61,9 @@ class CudaOps:
     unfold = staticmethod(_ops.unfold)
     orthonormalize = staticmethod(_ops.orthonormalize)
     symeig = staticmethod(_ops.symeig)
+    subspace_iterate = staticmethod(_ops.subspace_iterate)
     sumsq = staticmethod(_ops.sumsq)
+    supports_graphs = True
 
 
 def _gram_of_unfolding(ops, y: torch.Tensor, mode: int) -> torch.Tensor:
@@ -75,7 +77,7 @@ class HOOI:
     """State + one sweep of HOOI over `modes` (all other modes are left untouched: partial Tucker)."""
 
     def __init__(self, tensor: torch.Tensor, rank: Sequence[int], modes: Sequence[int], factors: Sequence[torch.Tensor],
-                 svd_iters: int = 8, ops=CudaOps):
+                 svd_iters: int = 16, ops=CudaOps):
         self.ops = ops
         self.x = tensor if tensor.is_contiguous() else tensor.contiguous()
         self.modes = list(modes)
@@ -105,6 +107,15 @@ class HOOI:
         self.norm_x2 = ops.sumsq(self.x)
         self.core: Optional[torch.Tensor] = None
         self.err = torch.zeros(1, dtype=self.x.dtype, device=self.x.device)
+        self._graph = None
+        self._eager_runs = 0
+        self._stable = False
+
+    def _set_factor(self, index: int, value: torch.Tensor) -> None:
+        if self._stable:
+            self.factors[index].copy_(value)
+        else:
+            self.factors[index] = value.to(self.x.dtype).contiguous()
 
     def _update(self, index: int) -> None:
         mode, r = self.modes[index], self.rank[index]
@@ -115,29 +126,58 @@ class HOOI:
         if u is None:
             # small mode: the eigenvectors of G itself, exactly the reference's singular vectors (up to sign)
             _, vec = ops.symeig(g)
-            self.factors[index] = vec[:, :r].contiguous().to(self.x.dtype)
+            self._set_factor(index, vec[:, :r])
             return
         # without room to oversample (r already at the 64-column limit) the wanted vectors converge at the slower
         # (lambda_{r+1} / lambda_r) rate: twice the steps
         steps = self.svd_iters if u.shape[1] > r else 2 * self.svd_iters
-        for _ in range(steps):
-            z = ops.mode_dot(g, u, 1, transpose=True)           # G U  (rows of G contracted with U's rows)
-            u = ops.orthonormalize(z, out=u)
+        u = ops.subspace_iterate(g, u, steps)                    # U <- orth(G U), `steps` times, in place
         if u.shape[1] > r:
             # Rayleigh-Ritz: rotate the block so that its first r columns are the leading Ritz vectors
             z = ops.mode_dot(g, u, 1, transpose=True)
             h = ops.mode_dot(z, u, 0, transpose=True)           # U^T G U  (p x p)
             _, w = ops.symeig(h)
             u = ops.mode_dot(u, w, 1, transpose=True)           # U W
-        self.block[index] = u
-        self.factors[index] = u[:, :r].contiguous().to(self.x.dtype)
+        if u is not self.block[index]:
+            self.block[index].copy_(u)
+        self._set_factor(index, u[:, :r])
 
-    def sweep(self) -> None:
+    def sweep_eager(self) -> None:
         for index in range(len(self.modes)):
             self._update(index)
-        self.core = self.ops.multi_mode_dot(self.x, self.factors, modes=self.modes, transpose=True)
-        nc2 = self.ops.sumsq(self.core)
-        self.err = torch.sqrt(torch.abs(self.norm_x2 - nc2)) / torch.sqrt(self.norm_x2)
+        core = self.ops.multi_mode_dot(self.x, self.factors, modes=self.modes, transpose=True)
+        nc2 = self.ops.sumsq(core)
+        err = torch.sqrt(torch.abs(self.norm_x2 - nc2)) / torch.sqrt(self.norm_x2)
+        if self.core is None or self.core.shape != core.shape:
+            self.core = core
+        else:
+            self.core.copy_(core)          # stable buffers: a captured sweep keeps writing the same tensors
+        self.err.copy_(err)
+
+    def sweep(self, use_graph: bool = True) -> None:
+        """One HOOI sweep.  On the GPU the first sweep runs eagerly (it replaces the initial factors, which may
+        be the caller's), the second is captured into a CUDA graph and later sweeps replay it: ~170 small launches
+        per sweep with no host work in between."""
+        graphable = use_graph and self.x.is_cuda and getattr(self.ops, "supports_graphs", False)
+        if not graphable:
+            self.sweep_eager()
+            return
+        if self._graph is None:
+            if self._eager_runs < 1:
+                self.sweep_eager()
+                self._stabilise()
+                self._eager_runs += 1
+                return
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.sweep_eager()
+            self._graph = g
+        self._graph.replay()
+
+    def _stabilise(self) -> None:
+        """Give factors and blocks buffers of their own that every later sweep updates in place."""
+        self.factors = [f.clone() for f in self.factors]
+        self._stable = True
 
 
 def _svd_init(ops, x: torch.Tensor, rank, modes):
@@ -161,7 +201,7 @@ def _random_init(x: torch.Tensor, rank, modes, random_state):
 
 
 def partial_tucker(tensor, rank, modes=None, n_iter_max=100, init="svd", tol=10e-5, svd="truncated_svd", random_state=None,
-                   verbose=False, mask=None, svd_mask_repeats=5, *, svd_iters=8, ops=CudaOps):
+                   verbose=False, mask=None, svd_mask_repeats=5, *, svd_iters=16, ops=CudaOps):
     """Partial Tucker decomposition via HOOI — same signature and return value ((core, factors), rec_errors) as
     tensorly.decomposition.partial_tucker (tensorly/decomposition/_tucker.py:105-221).  `svd_iters` (keyword-only)
     is the number of warm-started power steps that stand in for the reference's SVD per mode and sweep."""
@@ -217,7 +257,7 @@ def partial_tucker(tensor, rank, modes=None, n_iter_max=100, init="svd", tol=10e
 
 
 def tucker(tensor, rank, fixed_factors=None, n_iter_max=100, init="svd", return_errors=False, svd="truncated_svd", tol=10e-5,
-           random_state=None, mask=None, verbose=False, *, svd_iters=8, ops=CudaOps):
+           random_state=None, mask=None, verbose=False, *, svd_iters=16, ops=CudaOps):
     """Tucker decomposition via HOOI — same signature as tensorly.decomposition.tucker
     (tensorly/decomposition/_tucker.py:224-345); returns a TuckerTensor (or the plain (core, factors) pair when
     TensorLy is not importable), plus the error list with return_errors=True."""

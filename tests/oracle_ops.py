@@ -131,3 +131,13 @@ class OracleOps:
     def symeig(a):
         w, v = np.linalg.eigh(0.5 * (_np(a) + _np(a).T))
         return torch.from_numpy(w[::-1].copy()), torch.from_numpy(np.ascontiguousarray(v[:, ::-1]))
+
+    @staticmethod
+    def subspace_iterate(g, u, steps):
+        gg, uu = _np(g).astype(np.float64), _np(u).astype(np.float64)
+        for _ in range(steps):
+            z = gg @ uu
+            r = np.linalg.cholesky(z.T @ z).T
+            uu = z @ np.linalg.inv(r)
+        u.copy_(torch.from_numpy(np.ascontiguousarray(uu)))
+        return u
