@@ -326,6 +326,23 @@ int tlb200_hals_update(const void* const* grams, int nmodes, int mode, int64_t r
                        const double* ridge, double epsilon, int dtype, void* iters_out,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * One-shot all-reduce over NVLink peer memory (one process per GPU, one node) for the small partials of the
+ * sharded CP-ALS sweep — the exchange step SURVEY.md 8(e) adds to tensorly/decomposition/_cp.py:407-428 (the
+ * reference has no distributed path).  Every rank allocates one symmetric buffer (tlb200_comm_alloc), exports its
+ * 64-byte CUDA IPC handle, maps the peers' buffers (tlb200_comm_open) and then calls tlb200_allreduce_oneshot
+ * with the same sequence of sizes on every rank: one launch pushes the vector to every peer, publishes a flag,
+ * waits for all flags and sums the `world` contributions in rank order (same bits on every rank; bounded waits
+ * trap instead of hanging).  in may equal out.  count * sizeof(dtype) <= max_payload_bytes.
+ * ------------------------------------------------------------------------- */
+size_t tlb200_comm_buffer_bytes(int world, size_t max_payload_bytes);
+int tlb200_comm_alloc(size_t bytes, void** ptr, void* ipc_handle_out);
+int tlb200_comm_open(const void* ipc_handle, void** peer_ptr);
+int tlb200_comm_close(void* peer_ptr);
+int tlb200_comm_free(void* ptr);
+int tlb200_allreduce_oneshot(const void* in, void* out, int64_t count, int dtype, void* const* bufs,
+                             int world, int rank, size_t max_payload_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

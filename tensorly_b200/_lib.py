@@ -94,6 +94,12 @@ SIGNATURES = {
     "tlb200_subspace_iterate_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "tlb200_subspace_iterate": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_size_t,
                                         c_void_p]),
+    "tlb200_comm_buffer_bytes": (c_size_t, [c_int, c_size_t]),
+    "tlb200_comm_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
+    "tlb200_comm_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "tlb200_comm_close": (c_int, [c_void_p]),
+    "tlb200_comm_free": (c_int, [c_void_p]),
+    "tlb200_allreduce_oneshot": (c_int, [c_void_p, c_void_p, c_int64, c_int, _VPP, c_int, c_int, c_size_t, c_void_p]),
 }
 
 _lib = None

@@ -97,6 +97,32 @@ class _Comm:
         self.active = bool(sharded) and ready and dist.get_world_size(group) > 1
         self.world = dist.get_world_size(group) if self.active else 1
         self.rank = dist.get_rank(group) if self.active else 0
+        # GPU ranks of one node: the small partials travel through peer memory (p2p.py, csrc/comm.cu) instead of NCCL;
+        # set up lazily on the first CUDA tensor, all ranks agreeing on whether it worked.  TLB200_P2P=0 keeps NCCL.
+        self._p2p = None
+        self._p2p_tried = False
+        self.kind = "torch.distributed all_reduce"
+
+    @property
+    def graph_safe(self) -> bool:
+        """True when the sweep contains no library collective (captured graphs then own nothing of NCCL's)."""
+        return self._p2p is not None
+
+    def _setup_p2p(self, t) -> None:
+        self._p2p_tried = True
+        if not t.is_cuda or os.environ.get("TLB200_P2P", "1") == "0" or self.dist.get_backend(self.group) != "nccl":
+            return
+        ok = torch.ones(1, dtype=torch.int32, device=t.device)
+        comm = None
+        try:
+            from .p2p import P2PComm
+            comm = P2PComm(self.dist, self.group, t.device)
+        except Exception:
+            ok.zero_()
+        self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 1:
+            self._p2p = comm
+            self.kind = "one-shot peer-memory all-reduce (own kernel, NVLink stores + flags, rank-ordered sum)"
 
     def broadcast(self, t, src_rank=0):
         """Make rank `src_rank`'s copy of `t` everyone's (replicated state must be bit-identical)."""
@@ -106,9 +132,19 @@ class _Comm:
         return t
 
     def all_reduce(self, t):
-        if self.active:
-            self.dist.all_reduce(t, group=self.group)
+        if not self.active:
+            return t
+        if not self._p2p_tried:
+            self._setup_p2p(t)
+        if self._p2p is not None and self._p2p.fits(t):
+            return self._p2p.all_reduce(t)
+        self.dist.all_reduce(t, group=self.group)
         return t
+
+    def close(self):
+        if self._p2p is not None:
+            self._p2p.close()
+            self._p2p = None
 
     def all_gather_rows(self, t):
         """Concatenate per-rank row blocks (equal or unequal row counts)."""
@@ -292,11 +328,12 @@ class CPALS:
         """One ALS sweep.  On a single GPU the first sweep runs eagerly (lazy one-time
         initialisation), the second is captured into a CUDA graph, and every later sweep
         replays that graph: one launch per sweep instead of ~20."""
-        # The sharded sweep stays eager by default: capturing the NCCL all-reduces works and is ~4 % faster at
-        # 2 GPUs, but process-group teardown then hung in our runs (torch 2.11 / NCCL 2.28).  TLB200_DIST_GRAPH=1 opts in.
+        # The sharded sweep is captured too when its exchanges run on the peer-memory kernel (no NCCL inside the
+        # graph).  With NCCL collectives it stays eager by default: capturing them works, but process-group teardown
+        # then hung in our runs (torch 2.11 / NCCL 2.28); TLB200_DIST_GRAPH=1 opts in.
         graphable = (use_graph and getattr(self.ops, "supports_graphs", False) and self.x.is_cuda
                      and self.update != "hals"          # its kernel is a cooperative launch: kept out of graph capture
-                     and (not self.comm.active or os.environ.get("TLB200_DIST_GRAPH", "0") == "1")
+                     and (not self.comm.active or self.comm.graph_safe or os.environ.get("TLB200_DIST_GRAPH", "0") == "1")
                      and not (self.comm.active and self.shard_mode == self.ndim - 1))
         if not graphable:
             self.sweep_eager(with_error)

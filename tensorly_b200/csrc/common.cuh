@@ -74,6 +74,24 @@ inline const T* table_is_factor(const T* const* factors, const int64_t* frs, con
     return factors[first];
 }
 
+#ifdef __CUDACC__
+// Sum of `n` values spaced `stride` elements apart (per-CTA partial results in global memory), in index order, with
+// the loads issued 16 at a time: a plain `acc += ldcg(p[b])` loop is a chain of L2 round trips (~0.5 us each) that
+// made the "last CTA sums the partials" tails of several kernels cost more than the work they finish.
+template <typename T>
+__device__ __forceinline__ T ordered_sum_strided(const T* __restrict__ p, int n, size_t stride) {
+    T acc = T(0);
+    for (int b0 = 0; b0 < n; b0 += 16) {
+        T v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = b0 + i < n ? __ldcg(p + (size_t)(b0 + i) * stride) : T(0);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc += v[i];
+    }
+    return acc;
+}
+#endif
+
 // ---- internal launchers shared between translation units ------------------
 // Khatri-Rao of `nmats` matrices into out[(rows), ld]; columns [rank, pad_cols) are
 // written as zero.  Unlike the public entry point, weights are applied even for a

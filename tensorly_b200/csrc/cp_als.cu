@@ -204,11 +204,8 @@ __device__ __forceinline__ void gram_tail(const GramTail<T>& gt, const T* Y, int
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int e = tid; e < R * R; e += blockDim.x) {
-        T acc = T(0);
-        for (unsigned b = 0; b < gridDim.x; ++b) acc += __ldcg(gt.partial + (size_t)b * R * R + e);
-        gt.gram[e] = acc;
-    }
+    for (int e = tid; e < R * R; e += blockDim.x)
+        gt.gram[e] = ordered_sum_strided<T>(gt.partial + e, (int)gridDim.x, (size_t)R * R);
     if (tid == 0) *gt.counter = 0u;
 }
 

@@ -21,6 +21,66 @@ constexpr int OR_MAX = 64;        // widest block
 constexpr int OR_ROWS = 64;       // rows per CTA in kernel 1
 constexpr int OR_THREADS = 256;
 
+// Shifted Cholesky S + shift I = R^T R in shared memory, then R^{-1} (upper triangular); blockDim = 256, S is
+// [64][65], R <= 64.  shift = 2^-43 x mean diagonal: invisible for a well-conditioned block (orthogonality defect
+// 1e-13), and what keeps the factorisation alive when the block is numerically rank deficient (G U on a tensor
+// with a dominant mean direction reaches cond^2 > 1e16 after two steps; the reference's SVD does not care) — the
+// weak directions then come out scaled down instead of as inf/nan, and the next pass repairs them.
+__device__ void chol_inverse_64(double (*S)[OR_MAX + 1], double (*Ri)[OR_MAX + 1], int R, int* bad_out) {
+    const int tid = threadIdx.x;
+    __shared__ double s_shift;
+    if (tid == 0) {
+        double tr = 0.0;
+        for (int i = 0; i < R; ++i) tr += S[i][i];
+        s_shift = ldexp(tr / R, -43);
+    }
+    __syncthreads();
+    const double shift = s_shift;
+    if (tid < R) S[tid][tid] += shift;
+    __syncthreads();
+    // thread t updates the 16 elements (i, j) = (ti + 16 a, tj + 16 b) — fixed, no divisions inside the k loop
+    const int ti = tid >> 4, tj = tid & 15;
+    int bad = 0;
+    for (int k = 0; k < R; ++k) {
+        if (tid == 0) {
+            double d = S[k][k];
+            if (!(d > shift)) { d = shift > 0.0 ? shift : 1e-300; bad = 1; }
+            S[k][k] = sqrt(d);
+        }
+        __syncthreads();
+        const double inv = 1.0 / S[k][k];
+        if (tid > k && tid < R) S[k][tid] *= inv;
+        __syncthreads();
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int i = ti + 16 * a;
+            if (i <= k || i >= R) continue;
+            const double rki = S[k][i];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int j = tj + 16 * b;
+                if (j >= i && j < R) S[i][j] -= rki * S[k][j];
+            }
+        }
+        __syncthreads();
+    }
+    // R^{-1} column by column: 4 lanes per column (256 threads = 64 columns x 4), partial sums combined by shuffles
+    {
+        const int c = tid >> 2, q = tid & 3;
+        for (int i = R - 1; i >= 0; --i) {
+            double part = 0.0;
+            if (c < R && i < c)
+                for (int j = i + 1 + q; j <= c; j += 4) part += S[i][j] * Ri[j][c];
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            if (q == 0 && c < R) Ri[i][c] = i > c ? 0.0 : ((i == c ? 1.0 : 0.0) - part) / S[i][i];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && bad_out) *bad_out = bad;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(OR_THREADS)
 orth_gram_chol_kernel(const T* __restrict__ z, int64_t rows, int R, int64_t rs, int64_t cs, double* __restrict__ partial,
@@ -56,48 +116,12 @@ orth_gram_chol_kernel(const T* __restrict__ z, int64_t rows, int R, int64_t rs, 
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int e = tid; e < R * R; e += OR_THREADS) {
-        double acc = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) acc += __ldcg(partial + (size_t)b * R * R + e);
-        S[e / R][e % R] = acc;
-    }
+    for (int e = tid; e < R * R; e += OR_THREADS)
+        S[e / R][e % R] = ordered_sum_strided<double>(partial + e, (int)gridDim.x, (size_t)R * R);
     __syncthreads();
-    // Cholesky S = R^T R (upper R, stored in the upper triangle of S), right-looking; thread t owns column t
-    int bad = 0;
-    for (int k = 0; k < R; ++k) {
-        if (tid == 0) {
-            double d = S[k][k];
-            if (!(d > 0.0)) { d = 1e-300; bad = 1; }      // rank-deficient block: keep going, report it
-            S[k][k] = sqrt(d);
-        }
-        __syncthreads();
-        const double dk = S[k][k];
-        if (tid > k && tid < R) S[k][tid] /= dk;
-        __syncthreads();
-        // trailing update: S[i][j] -= R[k][i] * R[k][j], k < i <= j
-        for (int e = tid; e < R * R; e += OR_THREADS) {
-            const int i = e / R, j = e - i * R;
-            if (i > k && j >= i) S[i][j] -= S[k][i] * S[k][j];
-        }
-        __syncthreads();
-    }
-    // R^{-1}: column c of the inverse by back substitution, one thread per column
-    if (tid < R) {
-        const int c = tid;
-        for (int i = R - 1; i >= 0; --i) {
-            double v = i == c ? 1.0 : 0.0;
-            if (i <= c) {
-                for (int j = i + 1; j <= c; ++j) v -= S[i][j] * Ri[j][c];
-                v /= S[i][i];
-            } else {
-                v = 0.0;
-            }
-            Ri[i][c] = v;
-        }
-    }
-    __syncthreads();
+    chol_inverse_64(S, Ri, R, status);
     for (int e = tid; e < R * R; e += OR_THREADS) rinv[e] = Ri[e / R][e % R];
-    if (tid == 0) { *status = bad; *counter = 0u; }
+    if (tid == 0) *counter = 0u;
 }
 
 template <typename T, int RM>
@@ -134,54 +158,6 @@ orth_apply_kernel(const T* __restrict__ z, int64_t rows, int R, int64_t rs, int6
 // launches instead of the five (TTM prep + TTM + 2 orth kernels + copies) the generic entry points would take.
 constexpr int PS_ROWS = 16;
 constexpr int PS_KC = 64;
-
-// Cholesky S = R^T R in shared memory followed by R^{-1} (upper triangular), 256 threads.  S is [64][65].
-__device__ void chol_inverse_64(double (*S)[OR_MAX + 1], double (*Ri)[OR_MAX + 1], int R, int* bad_out) {
-    const int tid = threadIdx.x;
-    // thread t updates the 16 elements (i, j) = (ti + 16 a, tj + 16 b) — fixed, no divisions inside the k loop
-    const int ti = tid >> 4, tj = tid & 15;
-    int bad = 0;
-    for (int k = 0; k < R; ++k) {
-        if (tid == 0) {
-            double d = S[k][k];
-            if (!(d > 0.0)) { d = 1e-300; bad = 1; }
-            S[k][k] = sqrt(d);
-        }
-        __syncthreads();
-        const double inv = 1.0 / S[k][k];
-        if (tid > k && tid < R) S[k][tid] *= inv;
-        __syncthreads();
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int i = ti + 16 * a;
-            if (i <= k || i >= R) continue;
-            const double rki = S[k][i];
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int j = tj + 16 * b;
-                if (j >= i && j < R) S[i][j] -= rki * S[k][j];
-            }
-        }
-        // no barrier needed before the next diagonal: S[k+1][k+1] is updated by exactly one thread, but the
-        // sqrt is taken by thread 0 -> barrier
-        __syncthreads();
-    }
-    // R^{-1} column by column: thread group of 4 per column (256 threads = 64 columns x 4), partial sums by lanes
-    {
-        const int c = tid >> 2, q = tid & 3;
-        for (int i = R - 1; i >= 0; --i) {
-            double part = 0.0;
-            if (c < R && i < c)
-                for (int j = i + 1 + q; j <= c; j += 4) part += S[i][j] * Ri[j][c];
-            part += __shfl_xor_sync(0xffffffffu, part, 1);
-            part += __shfl_xor_sync(0xffffffffu, part, 2);
-            if (q == 0 && c < R) Ri[i][c] = i > c ? 0.0 : ((i == c ? 1.0 : 0.0) - part) / S[i][i];
-            __syncwarp();
-        }
-    }
-    __syncthreads();
-    if (tid == 0 && bad_out) *bad_out = bad;
-}
 
 __global__ void __launch_bounds__(256)
 power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const double* __restrict__ U, int p,
@@ -247,11 +223,8 @@ power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const
     __threadfence();
     Row* S = reinterpret_cast<Row*>(ps_smem);
     Row* Ri = S + OR_MAX;
-    for (int e = tid; e < p * p; e += 256) {
-        double t = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(partial + (size_t)b * p * p + e);
-        S[e / p][e % p] = t;
-    }
+    for (int e = tid; e < p * p; e += 256)
+        S[e / p][e % p] = ordered_sum_strided<double>(partial + e, (int)gridDim.x, (size_t)p * p);
     __syncthreads();
     chol_inverse_64(S, Ri, p, status);
     for (int e = tid; e < p * p; e += 256) rinv[e] = Ri[e / p][e % p];

@@ -9,6 +9,7 @@
 // by a tiny prep kernel; the B-producer warp then streams its K slices with TMA.
 #include "ttm_tc.cuh"
 #include "tc_stream.cuh"
+#include "stream_gemm.cuh"
 
 namespace tlb200 {
 namespace {
@@ -34,6 +35,10 @@ struct TtmGeom {
     int ks;
     int64_t kpad;
     int rp;
+    // T == 1 with few row tiles (e.g. the 512 x 512 Gram matrix of an unfolding: 4 tiles): the contraction is split
+    // into `ksplit` blocks of `nb` chunks so that the items fill the machine; partials are summed in block order
+    int ksplit;
+    int nb;
 };
 
 bool geom(int64_t L, int64_t J, int64_t T, int64_t I, TtmGeom* g) {
@@ -51,6 +56,19 @@ bool geom(int64_t L, int64_t J, int64_t T, int64_t I, TtmGeom* g) {
     if (g->M >= (1LL << 31) || g->A >= (1LL << 31) || g->B >= (1LL << 31)) return false;
     g->ks = tc_chunk_k(g->layout);
     g->kpad = ceil_div(J, g->ks) * g->ks;
+    const int64_t chunks = ceil_div(g->B, g->ks);
+    g->ksplit = 1;
+    g->nb = (int)chunks;
+    if (g->layout != TC_X_MMAJOR) {
+        const int64_t m_tiles = ceil_div(g->M, 128);
+        if (m_tiles * 2 <= kNumSMs && chunks >= 8) {
+            int64_t want = kNumSMs / m_tiles;                       // items per row tile
+            int64_t nb = ceil_div(chunks, want);
+            if (nb < 4) nb = 4;                                     // keep the pipeline fill amortised
+            g->nb = (int)nb;
+            g->ksplit = (int)ceil_div(chunks, nb);
+        }
+    }
     return true;
 }
 
@@ -70,7 +88,9 @@ bool ttm_tc_supported(int64_t L, int64_t J, int64_t T, int64_t I) {
 size_t ttm_tc_workspace(int64_t L, int64_t J, int64_t T, int64_t I) {
     TtmGeom g;
     if (!geom(L, J, T, I < kTtmRowBlock ? I : kTtmRowBlock, &g)) return 0;
-    return 2 * align_up((size_t)g.rp * g.kpad * 4, 256) + 256;
+    size_t total = 2 * align_up((size_t)g.rp * g.kpad * 4, 256) + 256;
+    if (g.ksplit > 1) total += align_up((size_t)g.ksplit * g.M * g.rp * 4, 256);
+    return total;
 }
 
 // one pass: rows [0, I) of `m` (I <= 64) into output rows of an array whose mode extent is I_total
@@ -82,6 +102,7 @@ static int ttm_tc_launch_block(const float* x, int64_t L, int64_t J, int64_t T, 
     Carver ws(workspace);
     float* bhi = ws.take<float>((size_t)g.rp * g.kpad);
     float* blo = ws.take<float>((size_t)g.rp * g.kpad);
+    float* partial = g.ksplit > 1 ? ws.take<float>((size_t)g.ksplit * g.M * g.rp) : nullptr;
     {
         const int64_t total = (int64_t)g.rp * g.kpad;
         int64_t blocks = ceil_div(total, 256);
@@ -127,7 +148,7 @@ static int ttm_tc_launch_block(const float* x, int64_t L, int64_t J, int64_t T, 
     p.m_tiles = (int)ceil_div(g.M, 128);
     p.k_ranges = g.A;                         // one item per (row tile, batch): all of K
     p.a_per_range = 1;
-    p.nb = (int)p.chunks_per_a; p.n_bblocks = 1;
+    p.nb = g.nb; p.n_bblocks = g.ksplit;
     p.b_resident = 0;                         // the matrix is streamed with the tiles (re-read from L2 per item)
     p.group_units = tc_group_units();
     p.P = nullptr;
@@ -135,7 +156,19 @@ static int ttm_tc_launch_block(const float* x, int64_t L, int64_t J, int64_t T, 
     if (g.layout == TC_X_MMAJOR) { p.sOk = I_total * T; p.sOm = 1; p.sOn = T; }
     else                         { p.sOk = 0; p.sOm = I_total; p.sOn = 1; }
     p.n_valid = (int)I;
-    return tc_stream_launch(l, stream);
+    if (partial) {                            // split contraction: [ksplit][M][rp] partials, then an ordered sum
+        p.out = partial;
+        p.sOk = g.M * g.rp; p.sOm = g.rp; p.sOn = 1;
+        p.n_valid = g.rp;
+    }
+    st = tc_stream_launch(l, stream);
+    if (st || !partial) return st;
+    const int64_t total = g.M * I;
+    int64_t blocks = ceil_div(total, 256);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    splitk_reduce_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>(partial, g.ksplit, g.M, I, g.rp, out, I_total);
+    TLB_CHECK_LAUNCH();
+    return TLB200_OK;
 }
 
 // More than 64 output rows: one pass over the tensor per block of 64 rows of the matrix (row blocks of `m` and of

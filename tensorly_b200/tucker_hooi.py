@@ -132,6 +132,7 @@ class HOOI:
         # (lambda_{r+1} / lambda_r) rate: twice the steps
         steps = self.svd_iters if u.shape[1] > r else 2 * self.svd_iters
         u = ops.subspace_iterate(g, u, steps)                    # U <- orth(G U), `steps` times, in place
+        u = ops.orthonormalize(u, out=u, passes=2)               # the steps use a shifted Cholesky-QR: clean up
         if u.shape[1] > r:
             # Rayleigh-Ritz: rotate the block so that its first r columns are the leading Ritz vectors
             z = ops.mode_dot(g, u, 1, transpose=True)
