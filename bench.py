@@ -781,7 +781,10 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=env.device)
     env.comm = _Comm(None, sharded=env.world > 1)
-    env.comm_kind = getattr(env.comm, "kind", "nccl all_reduce") if env.world > 1 else None
+    env.comm_kind = None
+    if env.world > 1:
+        env.comm.all_reduce(torch.zeros(4, device=env.device))        # sets up the peer-memory path (or falls back)
+        env.comm_kind = env.comm.kind
 
     def barrier():
         if env.world > 1:
@@ -892,6 +895,7 @@ def run_ours(args):
         gc.collect()
         torch.cuda.synchronize()
         dist.barrier()
+        env.comm.close()
         dist.destroy_process_group()
     return 0
 
