@@ -50,6 +50,8 @@ WORKLOADS = {
     "c1": dict(shape=(100, 100, 100), rank=10, dtype="float64",
                name="C1: parafac CP-ALS rank 10 on random 100x100x100 float64"),
     "small": dict(shape=(256, 256, 256), rank=32, dtype="float32", name="small: parafac rank 32 on 256^3 fp32"),
+    # one rank's share of C5 at N = 8 as a single-GPU problem (profiling aid: same kernels, no exchange)
+    "c5slab": dict(shape=(256, 2048, 2048), rank=64, dtype="float32", name="C5 slab: 256x2048x2048 rank 64 (1/8 of C5)"),
 }
 METRIC = "CP-ALS sweeps/s (MTTKRP HBM GB/s in roofline)"
 UNIT = "sweeps/s"
