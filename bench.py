@@ -679,19 +679,19 @@ def tucker_leg(env, steps):
             return time.perf_counter() - t0, float(errs[-1])
         timed(1)
         ta, _ = timed(1)
-        tb_, e_ref = timed(4)
-        out["reference_driver_on_b200"] = {"value": 3.0 / max(tb_ - ta, 1e-9), "unit": UNIT, "final_rel_error_4_sweeps": e_ref,
+        tb_, e_ref = timed(6)
+        out["reference_driver_on_b200"] = {"value": 5.0 / max(tb_ - ta, 1e-9), "unit": UNIT, "final_rel_error_6_sweeps": e_ref,
                                            "what": "tensorly.decomposition.tucker (unmodified, torch.linalg.svd) on tenalg 'b200'"}
         tb.use_gram_svd()
         try:
             timed(1)
             ta, _ = timed(1)
-            tb_, _ = timed(4)
-            out["reference_driver_on_b200"]["value_gram_svd"] = 3.0 / max(tb_ - ta, 1e-9)
+            tb_, _ = timed(6)
+            out["reference_driver_on_b200"]["value_gram_svd"] = 5.0 / max(tb_ - ta, 1e-9)
         finally:
             tb.use_default_svd()
         # same init, same number of sweeps through the own driver: the errors must agree (1e-4 gate)
-        _, errs = tb.tucker(x, ranks, n_iter_max=4, init="random", random_state=1, tol=0, return_errors=True)
+        _, errs = tb.tucker(x, ranks, n_iter_max=6, init="random", random_state=1, tol=0, return_errors=True)
         out["parity_vs_reference_driver"] = {"own": errs[-1], "reference": e_ref, "rel_dev": abs(errs[-1] - e_ref) / e_ref,
                                              "gate": 1e-4, "ok": abs(errs[-1] - e_ref) / e_ref <= 1e-4}
     except Exception as exc:

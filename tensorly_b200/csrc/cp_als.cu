@@ -8,6 +8,8 @@
 // whole sweep can sit in a CUDA graph.  All of it is latency-bound R x R work.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
 namespace tlb200 {
 namespace {
 
@@ -155,7 +157,9 @@ template <typename T>
 struct GramTail {
     T* partial;          // [gridDim.x][R*R] or null = no Gram requested
     T* gram;             // [R][R]
-    unsigned* counter;   // zero on entry, zero on exit
+    unsigned* counter;   // counter[0], counter[1]: zero on entry, zero on exit
+    int parallel;        // 1: every CTA is resident (grid <= #SMs), so they may wait for each other: each CTA then
+                         //    sums a slice of the R x R entries over all partials instead of the last CTA summing all
 };
 
 // Y^T Y of the CTA's rows, 256 threads as a 16 x 16 grid, thread (tr, tc) owning the TS x TS outputs
@@ -200,6 +204,26 @@ __device__ __forceinline__ void gram_tail(const GramTail<T>& gt, const T* Y, int
     else gram_tile<T, 8>(Y, ld, R, nrows, mine);
     __threadfence();
     __syncthreads();
+    if (gt.parallel) {
+        // grid-wide rendezvous (all CTAs resident by construction), then a parallel, still rank-ordered, sum: the
+        // serial tail of one CTA walking gridDim.x partials per entry cost more than the solve it finished
+        if (tid == 0) {
+            atomicAdd(gt.counter, 1u);
+            unsigned spins = 0;
+            while (atomicAdd(gt.counter, 0u) < gridDim.x) {
+                if (++spins > (1u << 26)) asm volatile("trap;");
+            }
+        }
+        __syncthreads();
+        __threadfence();
+        const int per = (R * R + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int e0 = (int)blockIdx.x * per, e1 = min(R * R, e0 + per);
+        for (int e = e0 + tid; e < e1; e += blockDim.x)
+            gt.gram[e] = ordered_sum_strided<T>(gt.partial + e, (int)gridDim.x, (size_t)R * R);
+        __syncthreads();
+        if (tid == 0 && atomicAdd(gt.counter + 1, 1u) == gridDim.x - 1) { gt.counter[0] = 0u; gt.counter[1] = 0u; }
+        return;
+    }
     if (tid == 0) s_last = atomicAdd(gt.counter, 1u) == gridDim.x - 1;
     __syncthreads();
     if (!s_last) return;
@@ -564,35 +588,48 @@ nncp_update_kernel(GramList<T> gl, int mode, int R, const T* __restrict__ w, con
 }
 
 // ---- error ----------------------------------------------------------------------------
+// One thread-block cluster of 8 CTAs: each sums <M, F> over an eighth of the rows, the partial sums meet in CTA 0
+// through distributed shared memory and are added in CTA order (deterministic, no global scratch).  A single CTA
+// walking all of M and F was 33 us of pure latency at the end of every C5 sweep.
+constexpr int kErrCluster = 8;
+
 template <typename T>
-__global__ void __launch_bounds__(1024)
+__global__ void __cluster_dims__(kErrCluster, 1, 1) __launch_bounds__(1024)
 cp_error_kernel(GramList<T> gl, int R, const T* __restrict__ w, const T* __restrict__ m, int64_t m_ld,
                 const T* __restrict__ f, int64_t frs, int64_t fcs, int64_t rows, const T* __restrict__ norm_x2,
                 T* __restrict__ err_out) {
     __shared__ double red[2][32];
+    __shared__ double cta_sum[2];
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank();
     const int tid = threadIdx.x;
     double iprod = 0.0, ncp = 0.0;
-    const int64_t total = rows * R;
+    const int64_t rows_per = (rows + kErrCluster - 1) / kErrCluster;
+    const int64_t r0 = (int64_t)crank * rows_per, r1 = min(rows, r0 + rows_per);
+    const int64_t total = max((int64_t)0, r1 - r0) * R;
     if (total < (1LL << 31)) {
-        // 32-bit index arithmetic and four independent loads in flight: this single CTA is pure latency
+        // 32-bit index arithmetic and four independent loads in flight
         const int tot = (int)total, step = (int)blockDim.x;
 #pragma unroll 4
         for (int e = tid; e < tot; e += step) {
             const int i = e / R, r = e - i * R;
-            iprod += (double)__ldg(m + (int64_t)i * m_ld + r) * (double)__ldg(f + (int64_t)i * frs + (int64_t)r * fcs);
+            iprod += (double)__ldg(m + (r0 + i) * m_ld + r) * (double)__ldg(f + (r0 + i) * frs + (int64_t)r * fcs);
         }
     } else {
         for (int64_t e = tid; e < total; e += blockDim.x) {
             const int64_t i = e / R, r = e - i * R;
-            iprod += (double)m[i * m_ld + r] * (double)f[i * frs + r * fcs];
+            iprod += (double)m[(r0 + i) * m_ld + r] * (double)f[(r0 + i) * frs + r * fcs];
         }
     }
-    for (int e = tid; e < R * R; e += blockDim.x) {
-        const int r = e / R, s = e - r * R;
-        T v = T(1);
-        for (int i = 0; i < gl.n; ++i) v = v * gl.g[i][(int64_t)r * R + s];
-        if (w) v = v * (w[r] * w[s]);
-        ncp += (double)v;
+    if (crank == 0) {
+        for (int e = tid; e < R * R; e += blockDim.x) {
+            const int r = e / R, s = e - r * R;
+            T v = T(1);
+            for (int i = 0; i < gl.n; ++i) v = v * gl.g[i][(int64_t)r * R + s];
+            if (w) v = v * (w[r] * w[s]);
+            ncp += (double)v;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -609,15 +646,21 @@ cp_error_kernel(GramList<T> gl, int R, const T* __restrict__ w, const T* __restr
             iprod += __shfl_xor_sync(0xffffffffu, iprod, o);
             ncp += __shfl_xor_sync(0xffffffffu, ncp, o);
         }
-        if (tid == 0) {
-            const double nx2 = (double)norm_x2[0];
-            double d = nx2 + ncp - 2.0 * iprod;
-            d = d < 0 ? -d : d;
-            err_out[0] = (T)(sqrt(d) / sqrt(nx2));
-            err_out[1] = (T)iprod;
-            err_out[2] = (T)ncp;
-        }
+        if (tid == 0) { cta_sum[0] = iprod; cta_sum[1] = ncp; }
     }
+    cluster.sync();
+    if (crank == 0 && tid == 0) {
+        double ip = 0.0;
+        for (int c = 0; c < kErrCluster; ++c) ip += cluster.map_shared_rank(cta_sum, c)[0];
+        const double nc = cta_sum[1];
+        const double nx2 = (double)norm_x2[0];
+        double d = nx2 + nc - 2.0 * ip;
+        d = d < 0 ? -d : d;
+        err_out[0] = (T)(sqrt(d) / sqrt(nx2));
+        err_out[1] = (T)ip;
+        err_out[2] = (T)nc;
+    }
+    cluster.sync();          // nobody leaves while CTA 0 may still read its shared memory
 }
 
 // ---- sum of squares ---------------------------------------------------------------------
@@ -724,6 +767,7 @@ int cp_update_launch(const void* const* grams, int nmodes, int mode, int64_t R, 
     if (nblk == 0) return TLB200_OK;
     GramTail<T> gt;
     gt.partial = nullptr; gt.gram = gram_out; gt.counter = nullptr;
+    gt.parallel = nblk > 1 && nblk <= kNumSMs;          // one CTA per SM at most: all of them are resident
     if (gram_out != nullptr) {      // workspace: [ticket counter, 256 bytes][nblk][R*R]
         gt.counter = static_cast<unsigned*>(workspace);
         gt.partial = reinterpret_cast<T*>(static_cast<char*>(workspace) + 256);
@@ -832,14 +876,14 @@ extern "C" int tlb200_cp_error(const void* const* grams, int nmodes, int64_t ran
         GramList<float> gl;
         int st = fill_grams<float>(&gl, grams, nmodes, -1);
         if (st) return st;
-        cp_error_kernel<float><<<1, 1024, 0, s>>>(gl, (int)rank, (const float*)weights, (const float*)m_last, m_ld,
+        cp_error_kernel<float><<<kErrCluster, 1024, 0, s>>>(gl, (int)rank, (const float*)weights, (const float*)m_last, m_ld,
                                                   (const float*)f_last, f_row_stride, f_col_stride, rows,
                                                   (const float*)norm_x2, (float*)err_out);
     } else {
         GramList<double> gl;
         int st = fill_grams<double>(&gl, grams, nmodes, -1);
         if (st) return st;
-        cp_error_kernel<double><<<1, 1024, 0, s>>>(gl, (int)rank, (const double*)weights, (const double*)m_last, m_ld,
+        cp_error_kernel<double><<<kErrCluster, 1024, 0, s>>>(gl, (int)rank, (const double*)weights, (const double*)m_last, m_ld,
                                                    (const double*)f_last, f_row_stride, f_col_stride, rows,
                                                    (const double*)norm_x2, (double*)err_out);
     }

@@ -17,6 +17,9 @@
 namespace tlb200 {
 namespace {
 
+__device__ long long g_ps_trace[8];        // perf triage: phase timestamps of the factoring CTA of the last call
+#define PS_TRACE(i) do { if (threadIdx.x == 0) g_ps_trace[i] = clock64(); } while (0)
+
 constexpr int OR_MAX = 64;        // widest block
 constexpr int OR_ROWS = 64;       // rows per CTA in kernel 1
 constexpr int OR_THREADS = 256;
@@ -64,6 +67,7 @@ __device__ void chol_inverse_64(double (*S)[OR_MAX + 1], double (*Ri)[OR_MAX + 1
         }
         __syncthreads();
     }
+    PS_TRACE(3);
     // R^{-1} column by column: 4 lanes per column (256 threads = 64 columns x 4), partial sums combined by shuffles
     {
         const int c = tid >> 2, q = tid & 3;
@@ -159,10 +163,11 @@ orth_apply_kernel(const T* __restrict__ z, int64_t rows, int R, int64_t rs, int6
 constexpr int PS_ROWS = 16;
 constexpr int PS_KC = 64;
 
+
 __global__ void __launch_bounds__(256)
 power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const double* __restrict__ U, int p,
-                    int64_t u_ld, double* __restrict__ Z, double* __restrict__ partial, unsigned* __restrict__ counter,
-                    double* __restrict__ rinv, int* __restrict__ status) {
+                    int64_t u_ld, double* __restrict__ Z, double* __restrict__ partial, double* __restrict__ ssum,
+                    unsigned* __restrict__ counter, double* __restrict__ rinv, int* __restrict__ status, int parallel) {
     extern __shared__ __align__(16) unsigned char ps_smem[];
     typedef double Row[OR_MAX + 1];
     // [Us: PS_KC x 64][Gs: 16 x 65]   later, in the last CTA only: [S: 64 x 65][Ri: 64 x 65]
@@ -173,6 +178,7 @@ power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const
     const int r = tid >> 4, c4 = (tid & 15) * 4;
     const int64_t row0 = (int64_t)blockIdx.x * PS_ROWS;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const long long t_start = clock64();
     for (int64_t k0 = 0; k0 < n; k0 += PS_KC) {
         __syncthreads();
         for (int e = tid; e < PS_ROWS * PS_KC; e += 256) {
@@ -217,18 +223,49 @@ power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const
     }
     __threadfence();
     __syncthreads();
-    if (tid == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
+    const long long t_gemm = clock64();
     Row* S = reinterpret_cast<Row*>(ps_smem);
     Row* Ri = S + OR_MAX;
-    for (int e = tid; e < p * p; e += 256)
-        S[e / p][e % p] = ordered_sum_strided<double>(partial + e, (int)gridDim.x, (size_t)p * p);
+    if (parallel) {
+        // every CTA is resident (grid <= #SMs): rendezvous, then each CTA sums a slice of the p x p entries over all
+        // partials (in block order) into `ssum`; the last CTA to finish its slice gathers S and factors it
+        if (tid == 0) {
+            atomicAdd(counter, 1u);
+            unsigned spins = 0;
+            while (atomicAdd(counter, 0u) < gridDim.x) {
+                if (++spins > (1u << 26)) asm volatile("trap;");
+            }
+        }
+        __syncthreads();
+        __threadfence();
+        const int per = (p * p + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int e0 = (int)blockIdx.x * per, e1 = min(p * p, e0 + per);
+        for (int e = e0 + tid; e < e1; e += 256)
+            ssum[e] = ordered_sum_strided<double>(partial + e, (int)gridDim.x, (size_t)p * p);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(counter + 2, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        for (int e = tid; e < p * p; e += 256) S[e / p][e % p] = __ldcg(ssum + e);
+        if (tid == 0) { counter[0] = 0u; counter[2] = 0u; }
+    } else {
+        if (tid == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        for (int e = tid; e < p * p; e += 256)
+            S[e / p][e % p] = ordered_sum_strided<double>(partial + e, (int)gridDim.x, (size_t)p * p);
+        if (tid == 0) *counter = 0u;
+    }
     __syncthreads();
+    if (tid == 0) { g_ps_trace[0] = t_start; g_ps_trace[1] = t_gemm; }
+    PS_TRACE(2);
     chol_inverse_64(S, Ri, p, status);
+    PS_TRACE(4);
     for (int e = tid; e < p * p; e += 256) rinv[e] = Ri[e / p][e % p];
-    if (tid == 0) *counter = 0u;
+    PS_TRACE(5);
 }
 
 __global__ void __launch_bounds__(256)
@@ -413,7 +450,7 @@ int run(const T* z, int64_t rows, int64_t R, int64_t rs, int64_t cs, T* out, int
 
 extern "C" size_t tlb200_subspace_iterate_workspace_bytes(int64_t n, int64_t p) {
     if (n < 1 || p < 1 || p > OR_MAX) return 0;
-    return 256 + sizeof(double) * ((size_t)n * p + align_up((size_t)p * p, 32) + (size_t)ceil_div(n, PS_ROWS) * p * p) + 256;
+    return 256 + sizeof(double) * ((size_t)n * p + 2 * align_up((size_t)p * p, 32) + (size_t)ceil_div(n, PS_ROWS) * p * p) + 256;
 }
 
 extern "C" int tlb200_subspace_iterate(const void* g, int64_t n, int64_t g_ld, void* u, int64_t p, int64_t u_ld, int steps,
@@ -426,7 +463,8 @@ extern "C" int tlb200_subspace_iterate(const void* g, int64_t n, int64_t g_ld, v
     unsigned* counter = static_cast<unsigned*>(workspace);
     int* status = reinterpret_cast<int*>(counter + 1);
     double* rinv = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
-    double* z = rinv + align_up((size_t)p * p, 32);
+    double* ssum = rinv + align_up((size_t)p * p, 32);
+    double* z = ssum + align_up((size_t)p * p, 32);
     double* partial = z + (size_t)n * p;
     constexpr int smem_a = 2 * OR_MAX * (OR_MAX + 1) * (int)sizeof(double);       // >= the GEMM phase's tiles
     static_assert(smem_a >= (int)sizeof(double) * (PS_KC * OR_MAX + PS_ROWS * (OR_MAX + 1)), "tile space");
@@ -435,7 +473,7 @@ extern "C" int tlb200_subspace_iterate(const void* g, int64_t n, int64_t g_ld, v
     const int nblk = (int)ceil_div(n, PS_ROWS);
     for (int it = 0; it < steps; ++it) {
         power_step_a_kernel<<<nblk, 256, smem_a, s>>>((const double*)g, n, g_ld, (const double*)u, (int)p, u_ld, z, partial,
-                                                      counter, rinv, status);
+                                                      ssum, counter, rinv, status, nblk > 1 && nblk <= kNumSMs);
         TLB_CHECK_LAUNCH();
         power_step_b_kernel<<<nblk, 256, 0, s>>>(z, n, (int)p, rinv, (double*)u, u_ld);
         TLB_CHECK_LAUNCH();
@@ -478,4 +516,9 @@ extern "C" int tlb200_orthonormalize(const void* z, int64_t rows, int64_t rank, 
     if (dtype == TLB200_F32)
         return run<float>((const float*)z, rows, rank, row_stride, col_stride, (float*)out, out_ld, workspace, passes, s);
     return run<double>((const double*)z, rows, rank, row_stride, col_stride, (double*)out, out_ld, workspace, passes, s);
+}
+
+// perf triage hook (not part of the public ABI): copies the 8 phase timestamps of the last factoring CTA to the host
+extern "C" int tlb200_debug_subspace_trace(long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, tlb200::g_ps_trace, sizeof(long long) * 8) == cudaSuccess ? 0 : -3;
 }

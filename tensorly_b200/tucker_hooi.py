@@ -23,7 +23,7 @@ What is (deliberately) different from the reference: the factors span the same s
 vectors themselves (any orthonormal basis gives the same reconstruction — Tucker factors are only defined up to a
 rotation that the core absorbs), and the subspace is converged by a fixed number of power steps instead of to LAPACK
 precision: the reconstruction-error trajectory agrees with the reference's to < 1e-4 relative with the default
-`svd_iters=16` (tests/test_gpu_parity.py), tighter with more.  `init="svd"` uses one library `eigh` per mode on the
+`svd_iters=8` (tests/test_gpu_parity.py), tighter with more.  `init="svd"` uses one library `eigh` per mode on the
 Gram matrix of the raw unfolding — initialisation, outside the loop.  Options outside this path (mask,
 fixed_factors, a non-default `svd`, rank > 64) are delegated to the unmodified reference driver on the b200 backend.
 """
@@ -66,10 +66,13 @@ class CudaOps:
     supports_graphs = True
 
 
-def _gram_of_unfolding(ops, y: torch.Tensor, mode: int) -> torch.Tensor:
+def _gram_of_unfolding(ops, y: torch.Tensor, mode: int, double: bool = False) -> torch.Tensor:
     """unfold(y, mode) unfold(y, mode)^T as ONE call of the TTM kernel: contracting the unfolding's long side with
-    itself, out[i, i'] = sum_c U[i', c] U[i, c]."""
+    itself, out[i, i'] = sum_c U[i', c] U[i, c].  `double`: form it in fp64 (SIMT path) — squaring halves the dynamic
+    range, and an fp32 Gram matrix loses every direction whose singular value is below 2.4e-4 of the largest."""
     unf = ops.unfold(y, mode, contiguous=True) if mode != 0 else y.reshape(y.shape[0], -1)
+    if double and unf.dtype != torch.float64:
+        unf = unf.to(torch.float64)
     return ops.mode_dot(unf, unf, 1)
 
 
@@ -77,7 +80,7 @@ class HOOI:
     """State + one sweep of HOOI over `modes` (all other modes are left untouched: partial Tucker)."""
 
     def __init__(self, tensor: torch.Tensor, rank: Sequence[int], modes: Sequence[int], factors: Sequence[torch.Tensor],
-                 svd_iters: int = 16, ops=CudaOps):
+                 svd_iters: int = 8, ops=CudaOps):
         self.ops = ops
         self.x = tensor if tensor.is_contiguous() else tensor.contiguous()
         self.modes = list(modes)
@@ -110,6 +113,7 @@ class HOOI:
         self._graph = None
         self._eager_runs = 0
         self._stable = False
+        self._orthonormal = False        # becomes True once every factor has been replaced by an orthonormal basis
 
     def _set_factor(self, index: int, value: torch.Tensor) -> None:
         if self._stable:
@@ -121,7 +125,10 @@ class HOOI:
         mode, r = self.modes[index], self.rank[index]
         ops = self.ops
         y = ops.multi_mode_dot(self.x, self.factors, modes=self.modes, skip=index, transpose=True)
-        g = _gram_of_unfolding(ops, y, mode).to(torch.float64)
+        # While the projections still use factors that are not orthonormal (the first sweep of a random init), Y is
+        # nearly rank one — its interesting directions sit 1e-3..1e-4 below the leading singular value, beyond what an
+        # fp32 Gram matrix resolves — so that sweep forms G in fp64; afterwards the tcgen05 engine (3xTF32) does.
+        g = _gram_of_unfolding(ops, y, mode, double=not self._orthonormal).to(torch.float64)
         u = self.block[index]
         if u is None:
             # small mode: the eigenvectors of G itself, exactly the reference's singular vectors (up to sign)
@@ -146,6 +153,7 @@ class HOOI:
     def sweep_eager(self) -> None:
         for index in range(len(self.modes)):
             self._update(index)
+        self._orthonormal = True
         core = self.ops.multi_mode_dot(self.x, self.factors, modes=self.modes, transpose=True)
         nc2 = self.ops.sumsq(core)
         err = torch.sqrt(torch.abs(self.norm_x2 - nc2)) / torch.sqrt(self.norm_x2)
@@ -187,7 +195,7 @@ def _svd_init(ops, x: torch.Tensor, rank, modes):
     I_k x I_k matrix — initialisation only)."""
     factors = []
     for r, m in zip(rank, modes):
-        g = _gram_of_unfolding(ops, x, m).to(torch.float64)
+        g = _gram_of_unfolding(ops, x, m, double=True)
         _, vec = torch.linalg.eigh(g)
         factors.append(torch.flip(vec[:, -int(r):], dims=(1,)).contiguous())
     return factors
@@ -202,7 +210,7 @@ def _random_init(x: torch.Tensor, rank, modes, random_state):
 
 
 def partial_tucker(tensor, rank, modes=None, n_iter_max=100, init="svd", tol=10e-5, svd="truncated_svd", random_state=None,
-                   verbose=False, mask=None, svd_mask_repeats=5, *, svd_iters=16, ops=CudaOps):
+                   verbose=False, mask=None, svd_mask_repeats=5, *, svd_iters=8, ops=CudaOps):
     """Partial Tucker decomposition via HOOI — same signature and return value ((core, factors), rec_errors) as
     tensorly.decomposition.partial_tucker (tensorly/decomposition/_tucker.py:105-221).  `svd_iters` (keyword-only)
     is the number of warm-started power steps that stand in for the reference's SVD per mode and sweep."""
@@ -258,7 +266,7 @@ def partial_tucker(tensor, rank, modes=None, n_iter_max=100, init="svd", tol=10e
 
 
 def tucker(tensor, rank, fixed_factors=None, n_iter_max=100, init="svd", return_errors=False, svd="truncated_svd", tol=10e-5,
-           random_state=None, mask=None, verbose=False, *, svd_iters=16, ops=CudaOps):
+           random_state=None, mask=None, verbose=False, *, svd_iters=8, ops=CudaOps):
     """Tucker decomposition via HOOI — same signature as tensorly.decomposition.tucker
     (tensorly/decomposition/_tucker.py:224-345); returns a TuckerTensor (or the plain (core, factors) pair when
     TensorLy is not importable), plus the error list with return_errors=True."""
