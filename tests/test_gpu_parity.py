@@ -895,7 +895,7 @@ def test_orthonormalize_and_symeig(rows, rank, dtype):
     assert np.linalg.norm(q.T @ q - np.eye(rank)) <= tol * rank
     q1 = host(tb.orthonormalize(dev(z), passes=1)).astype(np.float64)   # one pass: defect ~ cond^2 * 1e-16
     cond = np.linalg.cond(z.astype(np.float64))
-    assert np.linalg.norm(q1.T @ q1 - np.eye(rank)) <= max(tol * rank, 50 * cond ** 2 * 1e-16)
+    assert np.linalg.norm(q1.T @ q1 - np.eye(rank)) <= max(tol * rank, 1e3 * cond ** 2 * 1e-16)    # incl. the 2^-43 shift
     tol = 5e-5 if dtype == np.float32 else 1e-9
     # same span: projecting z on q reproduces z
     z64 = z.astype(np.float64)
