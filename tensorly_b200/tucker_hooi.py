@@ -23,7 +23,7 @@ What is (deliberately) different from the reference: the factors span the same s
 vectors themselves (any orthonormal basis gives the same reconstruction — Tucker factors are only defined up to a
 rotation that the core absorbs), and the subspace is converged by a fixed number of power steps instead of to LAPACK
 precision: the reconstruction-error trajectory agrees with the reference's to < 1e-4 relative with the default
-`svd_iters=8` (tests/test_gpu_parity.py), tighter with more.  `init="svd"` uses one library `eigh` per mode on the
+`svd_iters=6` (tests/test_gpu_parity.py), tighter with more.  `init="svd"` uses one library `eigh` per mode on the
 Gram matrix of the raw unfolding — initialisation, outside the loop.  Options outside this path (mask,
 fixed_factors, a non-default `svd`, rank > 64) are delegated to the unmodified reference driver on the b200 backend.
 """
@@ -65,6 +65,14 @@ class CudaOps:
     sumsq = staticmethod(_ops.sumsq)
     supports_graphs = True
 
+    @staticmethod
+    def eigh_top(g, p):
+        """Leading p eigenvectors of a symmetric fp64 matrix by a library eigendecomposition — used ONLY while the
+        projections still run on factors that are not orthonormal (the first sweep of a random / user-given init,
+        and init="svd" itself), i.e. as part of the initialisation; the steady-state loop never calls it."""
+        _, vec = torch.linalg.eigh(g)
+        return torch.flip(vec[:, -int(p):], dims=(1,)).contiguous()
+
 
 def _gram_of_unfolding(ops, y: torch.Tensor, mode: int, double: bool = False) -> torch.Tensor:
     """unfold(y, mode) unfold(y, mode)^T as ONE call of the TTM kernel: contracting the unfolding's long side with
@@ -80,7 +88,7 @@ class HOOI:
     """State + one sweep of HOOI over `modes` (all other modes are left untouched: partial Tucker)."""
 
     def __init__(self, tensor: torch.Tensor, rank: Sequence[int], modes: Sequence[int], factors: Sequence[torch.Tensor],
-                 svd_iters: int = 8, ops=CudaOps):
+                 svd_iters: int = 6, ops=CudaOps):
         self.ops = ops
         self.x = tensor if tensor.is_contiguous() else tensor.contiguous()
         self.modes = list(modes)
@@ -134,6 +142,15 @@ class HOOI:
             # small mode: the eigenvectors of G itself, exactly the reference's singular vectors (up to sign)
             _, vec = ops.symeig(g)
             self._set_factor(index, vec[:, :r])
+            return
+        if not self._orthonormal:
+            # First sweep on factors that are not orthonormal (a random init is all-positive: Y is almost rank one,
+            # lambda_1 / lambda_2 of G ~ 1e8 and beyond).  Power steps with a Cholesky-QR cannot hold on to the
+            # subdominant directions there (measured at C3: the more steps, the worse the first sweep), so this
+            # one sweep takes the exact eigenvectors of the fp64 Gram matrix and hands the iteration a proper start.
+            u = ops.eigh_top(g, u.shape[1])
+            self.block[index].copy_(u)
+            self._set_factor(index, u[:, :r])
             return
         # without room to oversample (r already at the 64-column limit) the wanted vectors converge at the slower
         # (lambda_{r+1} / lambda_r) rate: twice the steps
@@ -195,9 +212,9 @@ def _svd_init(ops, x: torch.Tensor, rank, modes):
     I_k x I_k matrix — initialisation only)."""
     factors = []
     for r, m in zip(rank, modes):
-        g = _gram_of_unfolding(ops, x, m, double=True)
-        _, vec = torch.linalg.eigh(g)
-        factors.append(torch.flip(vec[:, -int(r):], dims=(1,)).contiguous())
+        # fp64 Gram matrix when its fp64 copy of the unfolding is affordable (<= 2 GiB), else the tensor-core one
+        g = _gram_of_unfolding(ops, x, m, double=x.numel() <= (1 << 28))
+        factors.append(ops.eigh_top(g.to(torch.float64), r))
     return factors
 
 
@@ -210,7 +227,7 @@ def _random_init(x: torch.Tensor, rank, modes, random_state):
 
 
 def partial_tucker(tensor, rank, modes=None, n_iter_max=100, init="svd", tol=10e-5, svd="truncated_svd", random_state=None,
-                   verbose=False, mask=None, svd_mask_repeats=5, *, svd_iters=8, ops=CudaOps):
+                   verbose=False, mask=None, svd_mask_repeats=5, *, svd_iters=6, ops=CudaOps):
     """Partial Tucker decomposition via HOOI — same signature and return value ((core, factors), rec_errors) as
     tensorly.decomposition.partial_tucker (tensorly/decomposition/_tucker.py:105-221).  `svd_iters` (keyword-only)
     is the number of warm-started power steps that stand in for the reference's SVD per mode and sweep."""
@@ -244,6 +261,8 @@ def partial_tucker(tensor, rank, modes=None, n_iter_max=100, init="svd", tol=10e
         _, factors = init
         factors = [torch.as_tensor(f, device=x.device) for f in factors]
     state = HOOI(x, rank, modes, factors, svd_iters=svd_iters, ops=ops)
+    if isinstance(init, str) and init == "svd":
+        state._orthonormal = True            # eigenvectors of the raw unfoldings' Gram matrices: orthonormal already
     errs = torch.zeros(max(n_iter_max, 1), dtype=x.dtype, device=x.device)
     rec_errors: List[float] = []
     done = 0
@@ -266,7 +285,7 @@ def partial_tucker(tensor, rank, modes=None, n_iter_max=100, init="svd", tol=10e
 
 
 def tucker(tensor, rank, fixed_factors=None, n_iter_max=100, init="svd", return_errors=False, svd="truncated_svd", tol=10e-5,
-           random_state=None, mask=None, verbose=False, *, svd_iters=8, ops=CudaOps):
+           random_state=None, mask=None, verbose=False, *, svd_iters=6, ops=CudaOps):
     """Tucker decomposition via HOOI — same signature as tensorly.decomposition.tucker
     (tensorly/decomposition/_tucker.py:224-345); returns a TuckerTensor (or the plain (core, factors) pair when
     TensorLy is not importable), plus the error list with return_errors=True."""

@@ -141,3 +141,8 @@ class OracleOps:
             uu = z @ np.linalg.inv(r)
         u.copy_(torch.from_numpy(np.ascontiguousarray(uu)))
         return u
+
+    @staticmethod
+    def eigh_top(g, p):
+        w, v = np.linalg.eigh(_np(g).astype(np.float64))
+        return torch.from_numpy(np.ascontiguousarray(v[:, ::-1][:, :int(p)]))

@@ -1010,3 +1010,27 @@ def test_hals_large_factor_many_ctas():
     tb.hals_update([dev(UtU)], -1, None, dev(np.ascontiguousarray(UtM.T)), f, n_iter_max=30, iters_out=iters)
     assert rel_fro(host(f).T, ref) <= 2e-4
     assert 1 <= int(iters[0]) <= 30
+
+
+def test_own_tucker_c3_sized_random_init_vs_exact_fp64_hooi():
+    """256^3, ranks 48 (no room to oversample beyond 64 columns) from the reference's random init: the own driver
+    against exact HOOI with an fp64 SVD of the projected unfolding (library SVD as the checker) — 1e-4 on every
+    sweep, including the first one, where the all-positive random factors make the projected tensor almost rank one."""
+    n, R, sweeps = 256, 48, 4
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.rand((n, n, n), generator=g, device="cuda")
+    rs = np.random.RandomState(1)
+    rs.random_sample([R, R, R])
+    fs = [torch.as_tensor(rs.random_sample((n, R))).cuda().float() for _ in range(3)]
+    nx2 = float(tb.sumsq(x))
+    exact = []
+    for _ in range(sweeps):
+        for k in range(3):
+            y = tb.multi_mode_dot(x, fs, skip=k, transpose=True)
+            u, _, _ = torch.linalg.svd(tb.unfold(y, k, contiguous=True).double(), full_matrices=False)
+            fs[k] = u[:, :R].float().contiguous()
+        core = tb.multi_mode_dot(x, fs, transpose=True)
+        exact.append((abs(nx2 - float(tb.sumsq(core))) / nx2) ** 0.5)
+    _, errs = tb.tucker(x, [R, R, R], n_iter_max=sweeps, init="random", random_state=1, tol=0, return_errors=True)
+    dev_ = max(abs(a - b) / b for a, b in zip(errs, exact))
+    assert dev_ <= 1e-4, (errs, exact)
