@@ -27,6 +27,8 @@ int launch_stream_gemm<float>(const StreamGemmParams<float>& p, int TR, bool km,
 
 template <>
 int launch_stream_gemm<double>(const StreamGemmParams<double>& p, int TR, bool km, cudaStream_t s) {
+    // the DMMA kernel covers the SIMT tile widths 16 / 32 (TN = 32) and 64 (TN = 64) with the same column blocking
+    if (stream_gemm_dmma_enabled() && (TR == 2 || TR == 4 || TR == 8)) return launch_stream_gemm_dmma(p, TR == 8 ? 64 : 32, km, s);
     if (TR == 2) return km ? launch_one<double, 2, true>(p, s) : launch_one<double, 2, false>(p, s);
     if (TR == 4) return km ? launch_one<double, 4, true>(p, s) : launch_one<double, 4, false>(p, s);
     if (TR == 8) return km ? launch_one<double, 8, true>(p, s) : launch_one<double, 8, false>(p, s);

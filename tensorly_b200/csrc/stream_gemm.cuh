@@ -244,6 +244,11 @@ splitk_reduce_f4_kernel(const float4* __restrict__ partial, int nsplit, int64_t 
 template <typename T>
 int launch_stream_gemm(const StreamGemmParams<T>& p, int TR, bool a_kmajor, cudaStream_t stream);
 
+// fp64 on the double-precision tensor cores (stream_gemm_dmma.cu): same parameters, TN in {32, 64}.
+// TLB200_FP64_SIMT=1 keeps the SIMT kernel (A/B comparison).
+bool stream_gemm_dmma_enabled();
+int launch_stream_gemm_dmma(const StreamGemmParams<double>& p, int TN, bool a_kmajor, cudaStream_t stream);
+
 // Tile configuration chosen for N output columns.
 inline int stream_gemm_tr_for(int64_t N, int dtype) {
     const int vw = dtype == TLB200_F64 ? 2 : 4;
