@@ -218,6 +218,43 @@ int tlb200_cp_update_gram(const void* const* grams, int nmodes, int mode, int64_
                           int64_t rows, int dtype, void* out, int64_t out_ld, void* gram_out,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* Split-K partials of an MTTKRP, left unsummed for tlb200_cp_update_fused: element (split s, row i, column r) at
+ * data[s * split_stride + i * ld + r]; the MTTKRP is their sum over s in index order.  `data` points into the
+ * workspace of the call that produced it and stays valid until that workspace is reused. */
+typedef struct {
+    const void* data;
+    int64_t splits, split_stride, ld;
+    int64_t rows, rank;
+} tlb200_partials_t;
+
+/* tlb200_mttkrp / tlb200_mttkrp_from_ttm without their final reduction launch: same arguments minus `out`, the
+ * partials are described in *partials.  TLB200_EUNSUPPORTED for rank > 64 on the tensor-core path (several passes). */
+int tlb200_mttkrp_partials(const void* x, const int64_t* shape, int ndim, int mode,
+                           const void* const* factors, const int64_t* f_row_stride,
+                           const int64_t* f_col_stride, int64_t rank, const void* weights,
+                           int dtype, void* workspace, size_t workspace_bytes, int path,
+                           tlb200_partials_t* partials, void* stream);
+
+int tlb200_mttkrp_from_ttm_partials(const void* t, const int64_t* lead_shape, int nlead, int mode,
+                                    const void* const* factors, const int64_t* f_row_stride,
+                                    const int64_t* f_col_stride, int64_t rank, const void* weights,
+                                    int dtype, void* workspace, size_t workspace_bytes,
+                                    tlb200_partials_t* partials, void* stream);
+
+/* tlb200_cp_update_gram whose right-hand sides are those partials: they are summed (split order) while the LU runs,
+ * so the reduction costs neither a launch nor time on the critical path.  m_out (optional, rows x rank) receives the
+ * summed MTTKRP; iprod_out (optional device scalar) receives <M, F_new> = sum(M o F_new), the inner-product term of
+ * the fast error (tensorly/decomposition/_cp.py:222) — tlb200_cp_error_iprod finishes the error from it.
+ * Workspace: tlb200_cp_update_gram_workspace_bytes, same zero-ticket convention. */
+int tlb200_cp_update_fused(const void* const* grams, int nmodes, int mode, int64_t rank,
+                           const void* weights, double l2_reg, const tlb200_partials_t* m, int dtype,
+                           void* out, int64_t out_ld, void* gram_out, void* m_out, int64_t m_out_ld,
+                           void* iprod_out, void* workspace, size_t workspace_bytes, void* stream);
+
+int tlb200_cp_error_iprod(const void* const* grams, int nmodes, int64_t rank, const void* weights,
+                          const void* iprod, const void* norm_x2, int dtype, void* err_out,
+                          void* stream);
+
 /* Fast CP reconstruction error — replaces error_calc's MTTKRP shortcut
  * (tensorly/decomposition/_cp.py:217-225 with cp_norm, tensorly/cp_tensor.py:614-644):
  *   iprod = sum(M_last o F_last);  norm_cp^2 = sum_{r,s} w_r w_s prod_n G_n[r,s];

@@ -37,6 +37,13 @@ class MttkrpPlan(ctypes.Structure):
     ]
 
 
+class Partials(ctypes.Structure):
+    """Mirror of tlb200_partials_t."""
+
+    _fields_ = [("data", c_void_p), ("splits", c_int64), ("split_stride", c_int64), ("ld", c_int64), ("rows", c_int64),
+                ("rank", c_int64)]
+
+
 _I64P = POINTER(c_int64)
 _VPP = POINTER(c_void_p)
 _INTP = POINTER(c_int)
@@ -100,6 +107,13 @@ SIGNATURES = {
     "tlb200_comm_close": (c_int, [c_void_p]),
     "tlb200_comm_free": (c_int, [c_void_p]),
     "tlb200_allreduce_oneshot": (c_int, [c_void_p, c_void_p, c_int64, c_int, _VPP, c_int, c_int, c_size_t, c_void_p]),
+    "tlb200_mttkrp_partials": (c_int, [c_void_p, _I64P, c_int, c_int, _VPP, _I64P, _I64P, c_int64, c_void_p, c_int, c_void_p,
+                                       c_size_t, c_int, POINTER(Partials), c_void_p]),
+    "tlb200_mttkrp_from_ttm_partials": (c_int, [c_void_p, _I64P, c_int, c_int, _VPP, _I64P, _I64P, c_int64, c_void_p, c_int,
+                                                c_void_p, c_size_t, POINTER(Partials), c_void_p]),
+    "tlb200_cp_update_fused": (c_int, [_VPP, c_int, c_int, c_int64, c_void_p, c_double, POINTER(Partials), c_int, c_void_p,
+                                       c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tlb200_cp_error_iprod": (c_int, [_VPP, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -268,7 +268,22 @@ def unfolding_dot_khatri_rao(tensor: torch.Tensor, cp_tensor, mode: int) -> torc
     return mttkrp(tensor, cp_tensor, mode)
 
 
-def mttkrp(tensor: torch.Tensor, cp_tensor, mode: int, out: torch.Tensor | None = None) -> torch.Tensor:
+class PartialMttkrp:
+    """Unsummed split-K partials of an MTTKRP (tlb200_partials_t) plus the workspace that holds them.  Valid until the
+    next tlb200 call that uses the per-stream workspace; consumed by cp_update_fused."""
+
+    def __init__(self, info, ws, dtype, device):
+        self.info, self.ws, self.dtype, self.device = info, ws, dtype, device
+        self.shape = (int(info.rows), int(info.rank))
+
+
+def mttkrp_partials(tensor: torch.Tensor, cp_tensor, mode: int) -> "PartialMttkrp":
+    """unfolding_dot_khatri_rao without its final split-K reduction launch (the solve sums the partials while it loads
+    them).  Raises NotImplementedError where the MTTKRP needs several passes (rank > 64 on the tensor-core path)."""
+    return mttkrp(tensor, cp_tensor, mode, _partials=True)
+
+
+def mttkrp(tensor: torch.Tensor, cp_tensor, mode: int, out: torch.Tensor | None = None, _partials: bool = False):
     """unfolding_dot_khatri_rao with an optional preallocated contiguous result (rows, rank) — the reference
     signature has no such argument, the drivers use it to place the result inside a packed all-reduce buffer."""
     _check_tensor(tensor, "tensor")
@@ -304,10 +319,13 @@ def mttkrp(tensor: torch.Tensor, cp_tensor, mode: int, out: torch.Tensor | None 
         if w.numel() != rank:
             raise ValueError(f"weights has {w.numel()} entries but the factors have {rank} columns")
     x = tensor if tensor.is_contiguous() else tensor.contiguous()
-    out = (torch.empty((x.shape[mode], rank), dtype=x.dtype, device=x.device) if out is None
-           else _check_out(out, x.shape[mode], rank, x))
-    if x.numel() == 0:
-        return out.zero_()
+    if not _partials:
+        out = (torch.empty((x.shape[mode], rank), dtype=x.dtype, device=x.device) if out is None
+               else _check_out(out, x.shape[mode], rank, x))
+        if x.numel() == 0:
+            return out.zero_()
+    elif x.numel() == 0:
+        raise NotImplementedError("mttkrp_partials of an empty tensor")
     lib = _lib.load()
     dt = _DTYPES[x.dtype]
     path = _lib.PATHS[_path]
@@ -319,6 +337,16 @@ def mttkrp(tensor: torch.Tensor, cp_tensor, mode: int, out: torch.Tensor | None 
     ptrs = [0 if i == mode else f.data_ptr() for i, f in enumerate(factors)]
     rs = [0 if i == mode else f.stride(0) for i, f in enumerate(factors)]
     cs = [0 if i == mode else f.stride(1) for i, f in enumerate(factors)]
+    if _partials:
+        info = _lib.Partials()
+        with _Device(x):
+            st = lib.tlb200_mttkrp_partials(x.data_ptr(), shape, ndim, mode, _lib.ptr_array(ptrs), _lib.i64_array(rs),
+                                            _lib.i64_array(cs), rank, w.data_ptr() if w is not None else None, dt,
+                                            ws.data_ptr(), ws.numel(), path, info, _stream(x))
+        if st == _lib.TLB200_EUNSUPPORTED:
+            raise NotImplementedError("mttkrp_partials: this problem runs in several passes")
+        _lib.check(st, "mttkrp_partials")
+        return PartialMttkrp(info, ws, x.dtype, x.device)
     with _Device(x):
         st = lib.tlb200_mttkrp(x.data_ptr(), shape, ndim, mode, _lib.ptr_array(ptrs), _lib.i64_array(rs),
                                _lib.i64_array(cs), rank, w.data_ptr() if w is not None else None, dt, out.data_ptr(),
@@ -327,7 +355,12 @@ def mttkrp(tensor: torch.Tensor, cp_tensor, mode: int, out: torch.Tensor | None 
     return out
 
 
-def mttkrp_from_ttm(contracted: torch.Tensor, cp_tensor, mode: int, out: torch.Tensor | None = None) -> torch.Tensor:
+def mttkrp_from_ttm_partials(contracted: torch.Tensor, cp_tensor, mode: int) -> "PartialMttkrp":
+    """mttkrp_from_ttm without its final reduction launch (see mttkrp_partials)."""
+    return mttkrp_from_ttm(contracted, cp_tensor, mode, _partials=True)
+
+
+def mttkrp_from_ttm(contracted: torch.Tensor, cp_tensor, mode: int, out: torch.Tensor | None = None, _partials: bool = False):
     """MTTKRP of mode `mode` < N-1 from T = mode_dot(tensor, factors[N-1], N-1, transpose=True)
     (shape I_0 x .. x I_{N-2} x rank): equals unfolding_dot_khatri_rao(tensor, cp_tensor, mode) while
     factors[N-1] is unchanged, reading T (rank / I_{N-1} of the tensor) instead of the tensor.
@@ -356,10 +389,13 @@ def mttkrp_from_ttm(contracted: torch.Tensor, cp_tensor, mode: int, out: torch.T
         if w.numel() != rank:
             raise ValueError(f"weights has {w.numel()} entries but the factors have {rank} columns")
     t = contracted if contracted.is_contiguous() else contracted.contiguous()
-    out = (torch.empty((t.shape[mode], rank), dtype=t.dtype, device=t.device) if out is None
-           else _check_out(out, t.shape[mode], rank, t))
-    if t.numel() == 0:
-        return out.zero_()
+    if not _partials:
+        out = (torch.empty((t.shape[mode], rank), dtype=t.dtype, device=t.device) if out is None
+               else _check_out(out, t.shape[mode], rank, t))
+        if t.numel() == 0:
+            return out.zero_()
+    elif t.numel() == 0:
+        raise NotImplementedError("mttkrp_from_ttm_partials of an empty tensor")
     lib = _lib.load()
     dt = _DTYPES[t.dtype]
     lead = _lib.i64_array(t.shape[:nlead])
@@ -370,6 +406,14 @@ def mttkrp_from_ttm(contracted: torch.Tensor, cp_tensor, mode: int, out: torch.T
     ptrs = [0 if i == mode else factors[i].data_ptr() for i in range(nlead)]
     rs = [0 if i == mode else factors[i].stride(0) for i in range(nlead)]
     cs = [0 if i == mode else factors[i].stride(1) for i in range(nlead)]
+    if _partials:
+        info = _lib.Partials()
+        with _Device(t):
+            st = lib.tlb200_mttkrp_from_ttm_partials(t.data_ptr(), lead, nlead, mode, _lib.ptr_array(ptrs), _lib.i64_array(rs),
+                                                     _lib.i64_array(cs), rank, w.data_ptr() if w is not None else None, dt,
+                                                     ws.data_ptr(), ws.numel(), info, _stream(t))
+        _lib.check(st, "mttkrp_from_ttm_partials")
+        return PartialMttkrp(info, ws, t.dtype, t.device)
     with _Device(t):
         st = lib.tlb200_mttkrp_from_ttm(t.data_ptr(), lead, nlead, mode, _lib.ptr_array(ptrs), _lib.i64_array(rs),
                                         _lib.i64_array(cs), rank, w.data_ptr() if w is not None else None, dt,
@@ -831,3 +875,54 @@ def subspace_iterate(g: torch.Tensor, u: torch.Tensor, steps: int) -> torch.Tens
                                          ws.numel(), _stream(g))
     _lib.check(st, "subspace_iterate")
     return u
+
+
+def cp_update_fused(grams, mode: int, weights, partials: "PartialMttkrp", l2_reg: float = 0.0, out: torch.Tensor | None = None,
+                    gram_out: torch.Tensor | None = None, m_out: torch.Tensor | None = None,
+                    iprod_out: torch.Tensor | None = None) -> torch.Tensor:
+    """cp_update whose right-hand sides are the unsummed partials of mttkrp_partials / mttkrp_from_ttm_partials: one
+    launch sums them (split order), solves, forms the Gram matrix of the new factor and — on request — writes the
+    summed MTTKRP (`m_out`) and <M, F_new> (`iprod_out`, a device scalar for cp_error_iprod)."""
+    rows, rank = partials.shape
+    dtype, device = partials.dtype, partials.device
+    if out is None:
+        out = torch.empty((rows, rank), dtype=dtype, device=device)
+    if gram_out is None:
+        gram_out = torch.empty((rank, rank), dtype=dtype, device=device)
+    if tuple(gram_out.shape) != (rank, rank) or not gram_out.is_contiguous():
+        raise ValueError("gram_out must be a contiguous (rank, rank) tensor")
+    lib = _lib.load()
+    dt = _DTYPES[dtype]
+    with _Device(out):
+        ws = _zero_workspace(lib.tlb200_cp_update_gram_workspace_bytes(rows, rank, dt), out)
+        st = lib.tlb200_cp_update_fused(_gram_ptrs(grams, mode), len(grams), mode, rank,
+                                        weights.data_ptr() if weights is not None else None, float(l2_reg or 0.0),
+                                        ctypes_byref(partials.info), dt, out.data_ptr(), out.stride(0), gram_out.data_ptr(),
+                                        m_out.data_ptr() if m_out is not None else None,
+                                        m_out.stride(0) if m_out is not None else 0,
+                                        iprod_out.data_ptr() if iprod_out is not None else None, ws.data_ptr(), ws.numel(),
+                                        _stream(out))
+    if st == _lib.TLB200_EUNSUPPORTED:
+        raise NotImplementedError("cp_update_fused: <M, F> is only formed on the register-LU path (rank <= 64 fp32 / 32 fp64)")
+    _lib.check(st, "cp_update_fused")
+    return out
+
+
+def ctypes_byref(obj):
+    import ctypes
+    return ctypes.byref(obj)
+
+
+def cp_error_iprod(grams, weights, iprod: torch.Tensor, norm_x2: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """cp_error from a device-resident <M_last, F_last> (cp_update_fused's iprod_out)."""
+    _check_tensor(iprod, "iprod")
+    rank = next(g for g in grams if g is not None).shape[0]
+    if out is None:
+        out = torch.empty(3, dtype=iprod.dtype, device=iprod.device)
+    lib = _lib.load()
+    with _Device(iprod):
+        st = lib.tlb200_cp_error_iprod(_gram_ptrs(grams, -1), len(grams), rank,
+                                       weights.data_ptr() if weights is not None else None, iprod.data_ptr(),
+                                       norm_x2.data_ptr(), _DTYPES[iprod.dtype], out.data_ptr(), _stream(iprod))
+    _lib.check(st, "cp_error_iprod")
+    return out

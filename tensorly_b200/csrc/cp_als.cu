@@ -162,6 +162,28 @@ struct GramTail {
                          //    sums a slice of the R x R entries over all partials instead of the last CTA summing all
 };
 
+// Where the right-hand sides come from: the MTTKRP itself (splits == 1), or the split-K partials of the MTTKRP
+// kernel [splits][rows][ld], which the solve sums in split order while it loads them (the separate reduction
+// launch disappears; on the register-LU path the 192 threads that do not factor do the summing meanwhile).
+template <typename T>
+struct MSource {
+    const T* m;
+    int64_t ld;
+    int splits;
+    int64_t split_stride;
+    T* m_out;            // optional: the summed MTTKRP (rows x R, row stride m_out_ld) for callers that need it
+    int64_t m_out_ld;
+    double* iprod_partial;   // optional [gridDim.x]: per-CTA sum of M o F_new (the <X, model> term of the fast error)
+    T* iprod_out;            // device scalar receiving the ordered sum of the above
+};
+
+template <typename T>
+__device__ __forceinline__ T msource_load(const MSource<T>& ms, int64_t row, int c) {
+    const T* p = ms.m + row * ms.ld + c;
+    if (ms.splits == 1) return *p;
+    return ordered_sum_strided<T>(p, ms.splits, (size_t)ms.split_stride);
+}
+
 // Y^T Y of the CTA's rows, 256 threads as a 16 x 16 grid, thread (tr, tc) owning the TS x TS outputs
 // (tr + 16a, tc + 16b): per row TS + TS shared-memory reads (conflict-free / broadcast) feed TS*TS FMAs.
 template <typename T, int TS>
@@ -193,7 +215,17 @@ __device__ __forceinline__ void gram_tile(const T* Y, int ld, int R, int nrows, 
 }
 
 template <typename T>
-__device__ __forceinline__ void gram_tail(const GramTail<T>& gt, const T* Y, int ld, int R, int nrows) {
+__device__ __forceinline__ void iprod_finish(const MSource<T>& ms) {      // one warp: ordered sum of the per-CTA terms
+    if (threadIdx.x >= 32) return;
+    double t = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += 32) t += __ldcg(ms.iprod_partial + b);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) *ms.iprod_out = (T)t;
+}
+
+template <typename T>
+__device__ __forceinline__ void gram_tail(const GramTail<T>& gt, const MSource<T>& ms, const T* Y, int ld, int R, int nrows) {
     if (gt.partial == nullptr) return;
     __shared__ int s_last;
     const int tid = threadIdx.x;
@@ -220,6 +252,7 @@ __device__ __forceinline__ void gram_tail(const GramTail<T>& gt, const T* Y, int
         const int e0 = (int)blockIdx.x * per, e1 = min(R * R, e0 + per);
         for (int e = e0 + tid; e < e1; e += blockDim.x)
             gt.gram[e] = ordered_sum_strided<T>(gt.partial + e, (int)gridDim.x, (size_t)R * R);
+        if (ms.iprod_out != nullptr && blockIdx.x == 0) iprod_finish<T>(ms);
         __syncthreads();
         if (tid == 0 && atomicAdd(gt.counter + 1, 1u) == gridDim.x - 1) { gt.counter[0] = 0u; gt.counter[1] = 0u; }
         return;
@@ -230,6 +263,7 @@ __device__ __forceinline__ void gram_tail(const GramTail<T>& gt, const T* Y, int
     __threadfence();
     for (int e = tid; e < R * R; e += blockDim.x)
         gt.gram[e] = ordered_sum_strided<T>(gt.partial + e, (int)gridDim.x, (size_t)R * R);
+    if (ms.iprod_out != nullptr) iprod_finish<T>(ms);
     if (tid == 0) *gt.counter = 0u;
 }
 
@@ -370,23 +404,14 @@ __device__ __forceinline__ void lu_factor_rot(int R, const SolveSmem<T, RM>& sm,
 // right-hand sides, fetched by the caller before the factorisation so the loads are long done.
 template <typename T, int RM>
 __device__ __forceinline__ void solve_fast(unsigned char* raw, const GramList<T>& gl, int mode, int R, const T* __restrict__ w,
-                                           T l2, const T* __restrict__ m, int64_t m_ld, int64_t rows, T* __restrict__ out,
+                                           T l2, const MSource<T>& ms, int64_t rows, T* __restrict__ out,
                                            int64_t out_ld, const GramTail<T>& gtail) {
     constexpr int kRows = kFastRows;
     const SolveSmem<T, RM> sm(raw, R);
     const int ld = R + 1;
     const int tid = threadIdx.x;
     const int64_t row0 = (int64_t)blockIdx.x * kRows;
-    constexpr int kPer = kRows * RM / 256;
-    T tmp[kPer];
     CP_TRACE(0);
-#pragma unroll
-    for (int it = 0; it < kPer; ++it) {
-        const int e = tid + it * 256;
-        const int rr = e / R, c = e - rr * R;
-        const int64_t gr = row0 + rr;
-        tmp[it] = (e < kRows * R && gr < rows) ? m[gr * m_ld + c] : T(0);
-    }
     {   // V^T into shared memory: same evaluation order as form_v, Gram pointers in registers, loads batched
         const T* gp[TLB200_MAX_NDIM];
 #pragma unroll
@@ -405,12 +430,18 @@ __device__ __forceinline__ void solve_fast(unsigned char* raw, const GramList<T>
     }
     __syncthreads();
     CP_TRACE(1);
-    if (tid < RM) lu_factor_rot<T, RM>(R, sm, ld);
-#pragma unroll
-    for (int it = 0; it < kPer; ++it) {
-        const int e = tid + it * 256;
-        const int rr = e / R, c = e - rr * R;
-        if (e < kRows * R) sm.Y[rr * ld + c] = tmp[it];
+    if (tid < RM) {
+        lu_factor_rot<T, RM>(R, sm, ld);
+    } else {
+        // the 256 - RM threads that do not factor fetch the right-hand sides meanwhile — summing the MTTKRP's
+        // split-K partials in split order when that is what they were given
+        for (int e = tid - RM; e < kRows * R; e += 256 - RM) {
+            const int rr = e / R, c = e - rr * R;
+            const int64_t gr = row0 + rr;
+            const T v = gr < rows ? msource_load<T>(ms, gr, c) : T(0);
+            sm.Y[rr * ld + c] = v;
+            if (ms.m_out != nullptr && gr < rows) ms.m_out[gr * ms.m_out_ld + c] = v;
+        }
     }
     CP_TRACE(2);
     __syncthreads();
@@ -429,6 +460,7 @@ __device__ __forceinline__ void solve_fast(unsigned char* raw, const GramList<T>
     // (axpy form, like trsm): RM / 16 FMAs per lane and step, the shuffle is the only thing on the dependency chain.
     constexpr int NS = RM / 16;
     const int grp = tid >> 4, l16 = tid & 15;
+    double ip_acc = 0.0;
 #pragma unroll 1
     for (int pass = 0; pass < kRows / 16; ++pass) {
         T* y = sm.Y + (pass * 16 + grp) * ld;
@@ -468,6 +500,14 @@ __device__ __forceinline__ void solve_fast(unsigned char* raw, const GramList<T>
             }
         }
         __syncwarp();
+        if (ms.iprod_partial != nullptr) {          // <M_row, F_row>: y still holds the right-hand side here
+#pragma unroll
+            for (int t = 0; t < NS; ++t) {
+                const int i = t * 16 + l16;
+                if (i < R) ip_acc += (double)y[i] * (double)b[t];
+            }
+        }
+        __syncwarp();
 #pragma unroll
         for (int t = 0; t < NS; ++t) {
             const int i = t * 16 + l16;
@@ -476,18 +516,30 @@ __device__ __forceinline__ void solve_fast(unsigned char* raw, const GramList<T>
     }
     CP_TRACE(5);
     __syncthreads();
+    if (ms.iprod_partial != nullptr) {
+        __shared__ double ip_red[8];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ip_acc += __shfl_xor_sync(0xffffffffu, ip_acc, o);
+        if ((tid & 31) == 0) ip_red[tid >> 5] = ip_acc;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int i = 0; i < 8; ++i) t += ip_red[i];
+            ms.iprod_partial[blockIdx.x] = t;
+        }
+    }
     for (int e = tid; e < kRows * R; e += 256) {
         const int r2 = e / R, c = e - r2 * R;
         const int64_t gr = row0 + r2;
         if (gr < rows) out[gr * out_ld + c] = sm.Y[r2 * ld + c];
     }
     CP_TRACE(6);
-    gram_tail<T>(gtail, sm.Y, ld, R, (int)min((int64_t)kRows, rows - row0));
+    gram_tail<T>(gtail, ms, sm.Y, ld, R, (int)min((int64_t)kRows, rows - row0));
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kSolveThreads, 1)
-cp_update_kernel(GramList<T> gl, int mode, int R, const T* __restrict__ w, T l2, const T* __restrict__ m, int64_t m_ld,
+cp_update_kernel(GramList<T> gl, int mode, int R, const T* __restrict__ w, T l2, MSource<T> ms,
                  int64_t rows, T* __restrict__ out, int64_t out_ld, GramTail<T> gtail) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ld = R + 1;
@@ -498,9 +550,9 @@ cp_update_kernel(GramList<T> gl, int mode, int R, const T* __restrict__ w, T l2,
     const int tid = threadIdx.x;
     const int64_t row0 = (int64_t)blockIdx.x * kSolveRows;
 
-    if (R <= 32) { solve_fast<T, 32>(smem_raw, gl, mode, R, w, l2, m, m_ld, rows, out, out_ld, gtail); return; }
+    if (R <= 32) { solve_fast<T, 32>(smem_raw, gl, mode, R, w, l2, ms, rows, out, out_ld, gtail); return; }
     if constexpr (sizeof(T) == 4) {
-        if (R <= 64) { solve_fast<T, 64>(smem_raw, gl, mode, R, w, l2, m, m_ld, rows, out, out_ld, gtail); return; }
+        if (R <= 64) { solve_fast<T, 64>(smem_raw, gl, mode, R, w, l2, ms, rows, out, out_ld, gtail); return; }
     }
     {
         for (int e = tid; e < R * R; e += blockDim.x) {
@@ -514,7 +566,7 @@ cp_update_kernel(GramList<T> gl, int mode, int R, const T* __restrict__ w, T l2,
         for (int e = tid; e < kSolveRows * R; e += blockDim.x) {
             const int rr = e / R, c = e - rr * R;
             const int64_t gr = row0 + rr;
-            Y[rr * ld + c] = gr < rows ? m[gr * m_ld + perm[c]] : T(0);
+            Y[rr * ld + c] = gr < rows ? msource_load<T>(ms, gr, perm[c]) : T(0);
         }
         __syncthreads();
     }
@@ -550,7 +602,7 @@ cp_update_kernel(GramList<T> gl, int mode, int R, const T* __restrict__ w, T l2,
         if (gr < rows) out[gr * out_ld + c] = Y[r2 * ld + c];
     }
     CP_TRACE(6);
-    gram_tail<T>(gtail, Y, ld, R, (int)min((int64_t)kSolveRows, rows - row0));
+    gram_tail<T>(gtail, ms, Y, ld, R, (int)min((int64_t)kSolveRows, rows - row0));
 }
 
 // ---- NN-CP multiplicative update -------------------------------------------------------
@@ -750,8 +802,8 @@ int fill_grams(GramList<T>* gl, const void* const* grams, int nmodes, int skip) 
 }
 
 template <typename T>
-int cp_update_launch(const void* const* grams, int nmodes, int mode, int64_t R, const T* w, double l2, const T* m,
-                     int64_t m_ld, int64_t rows, T* out, int64_t out_ld, T* gram_out, void* workspace, cudaStream_t stream) {
+int cp_update_launch(const void* const* grams, int nmodes, int mode, int64_t R, const T* w, double l2, MSource<T> ms,
+                     int64_t rows, T* out, int64_t out_ld, T* gram_out, void* workspace, cudaStream_t stream) {
     GramList<T> gl;
     int st = fill_grams<T>(&gl, grams, nmodes, mode);
     if (st) return st;
@@ -768,11 +820,16 @@ int cp_update_launch(const void* const* grams, int nmodes, int mode, int64_t R, 
     GramTail<T> gt;
     gt.partial = nullptr; gt.gram = gram_out; gt.counter = nullptr;
     gt.parallel = nblk > 1 && nblk <= kNumSMs;          // one CTA per SM at most: all of them are resident
-    if (gram_out != nullptr) {      // workspace: [ticket counter, 256 bytes][nblk][R*R]
+    if (gram_out != nullptr) {      // workspace: [ticket counters, 256 bytes][nblk][R*R][nblk doubles: <M, F> terms]
         gt.counter = static_cast<unsigned*>(workspace);
         gt.partial = reinterpret_cast<T*>(static_cast<char*>(workspace) + 256);
+        ms.iprod_partial = ms.iprod_out ? reinterpret_cast<double*>(static_cast<char*>(workspace) + 256 +
+                                                                    align_up((size_t)nblk * R * R * sizeof(T), 256)) : nullptr;
+    } else {
+        ms.iprod_partial = nullptr; ms.iprod_out = nullptr;
     }
-    cp_update_kernel<T><<<nblk, kSolveThreads, smem, stream>>>(gl, mode, (int)R, w, (T)l2, m, m_ld, rows, out, out_ld, gt);
+    if (ms.iprod_out != nullptr && !fast) return TLB200_EUNSUPPORTED;      // only the register-LU path forms <M, F>
+    cp_update_kernel<T><<<nblk, kSolveThreads, smem, stream>>>(gl, mode, (int)R, w, (T)l2, ms, rows, out, out_ld, gt);
     TLB_CHECK_LAUNCH();
     return TLB200_OK;
 }
@@ -814,6 +871,14 @@ extern "C" int tlb200_gram(const void* f, int64_t rows, int64_t rank, int64_t ro
     return gram_launch<double>((const double*)f, rows, rank, row_stride, col_stride, (double*)gram, workspace, s);
 }
 
+template <typename T>
+static MSource<T> plain_source(const void* m, int64_t m_ld) {
+    MSource<T> ms;
+    ms.m = static_cast<const T*>(m); ms.ld = m_ld; ms.splits = 1; ms.split_stride = 0;
+    ms.m_out = nullptr; ms.m_out_ld = 0; ms.iprod_partial = nullptr; ms.iprod_out = nullptr;
+    return ms;
+}
+
 extern "C" int tlb200_cp_update(const void* const* grams, int nmodes, int mode, int64_t rank, const void* weights,
                                 double l2_reg, const void* m, int64_t m_ld, int64_t rows, int dtype, void* out,
                                 int64_t out_ld, void* stream) {
@@ -823,15 +888,16 @@ extern "C" int tlb200_cp_update(const void* const* grams, int nmodes, int mode, 
     set_last_path("simt");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == TLB200_F32)
-        return cp_update_launch<float>(grams, nmodes, mode, rank, (const float*)weights, l2_reg, (const float*)m, m_ld, rows,
+        return cp_update_launch<float>(grams, nmodes, mode, rank, (const float*)weights, l2_reg, plain_source<float>(m, m_ld), rows,
                                        (float*)out, out_ld, nullptr, nullptr, s);
-    return cp_update_launch<double>(grams, nmodes, mode, rank, (const double*)weights, l2_reg, (const double*)m, m_ld, rows,
+    return cp_update_launch<double>(grams, nmodes, mode, rank, (const double*)weights, l2_reg, plain_source<double>(m, m_ld), rows,
                                     (double*)out, out_ld, nullptr, nullptr, s);
 }
 
 extern "C" size_t tlb200_cp_update_gram_workspace_bytes(int64_t rows, int64_t rank, int dtype) {
     if (rows < 0 || rank < 1 || !dtype_valid(dtype)) return 0;
-    return 256 + align_up((size_t)ceil_div(rows > 0 ? rows : 1, kFastRows) * rank * rank * dtype_size(dtype), 256);
+    const size_t nblk = (size_t)ceil_div(rows > 0 ? rows : 1, kFastRows);
+    return 256 + align_up(nblk * rank * rank * dtype_size(dtype), 256) + align_up(nblk * sizeof(double), 256);
 }
 
 extern "C" int tlb200_cp_update_gram(const void* const* grams, int nmodes, int mode, int64_t rank, const void* weights,
@@ -844,10 +910,88 @@ extern "C" int tlb200_cp_update_gram(const void* const* grams, int nmodes, int m
     set_last_path("simt");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == TLB200_F32)
-        return cp_update_launch<float>(grams, nmodes, mode, rank, (const float*)weights, l2_reg, (const float*)m, m_ld, rows,
+        return cp_update_launch<float>(grams, nmodes, mode, rank, (const float*)weights, l2_reg, plain_source<float>(m, m_ld), rows,
                                        (float*)out, out_ld, (float*)gram_out, workspace, s);
-    return cp_update_launch<double>(grams, nmodes, mode, rank, (const double*)weights, l2_reg, (const double*)m, m_ld, rows,
+    return cp_update_launch<double>(grams, nmodes, mode, rank, (const double*)weights, l2_reg, plain_source<double>(m, m_ld), rows,
                                     (double*)out, out_ld, (double*)gram_out, workspace, s);
+}
+
+// The fused form the own driver uses: right-hand sides = split-K partials of the MTTKRP (summed in split order while
+// they are loaded), plus optionally the summed MTTKRP itself (m_out) and <M, F_new> (iprod_out, one device scalar).
+extern "C" int tlb200_cp_update_fused(const void* const* grams, int nmodes, int mode, int64_t rank, const void* weights,
+                                      double l2_reg, const tlb200_partials_t* m, int dtype, void* out, int64_t out_ld,
+                                      void* gram_out, void* m_out, int64_t m_out_ld, void* iprod_out, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+    if (!m || !m->data || !out || !gram_out || !workspace || rank < 1 || rank > kMaxRank || m->rows < 1 || mode < 0 ||
+        mode >= nmodes || m->ld < rank || out_ld < rank || m->splits < 1 || !dtype_valid(dtype) ||
+        (m_out && m_out_ld < rank))
+        return TLB200_EINVAL;
+    if (workspace_bytes < tlb200_cp_update_gram_workspace_bytes(m->rows, rank, dtype)) return TLB200_EWORKSPACE;
+    set_last_path("simt");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    auto go = [&](auto tag) {
+        using T = decltype(tag);
+        MSource<T> ms;
+        ms.m = static_cast<const T*>(m->data); ms.ld = m->ld; ms.splits = (int)m->splits; ms.split_stride = m->split_stride;
+        ms.m_out = static_cast<T*>(m_out); ms.m_out_ld = m_out_ld;
+        ms.iprod_partial = nullptr; ms.iprod_out = static_cast<T*>(iprod_out);
+        return cp_update_launch<T>(grams, nmodes, mode, rank, static_cast<const T*>(weights), l2_reg, ms, m->rows,
+                                   static_cast<T*>(out), out_ld, static_cast<T*>(gram_out), workspace, s);
+    };
+    return dtype == TLB200_F32 ? go(float()) : go(double());
+}
+
+// err_out = [sqrt(|norm_x2 + norm_cp^2 - 2 iprod|) / sqrt(norm_x2), iprod, norm_cp^2] from a device-resident <M, F>
+// (tlb200_cp_update_fused's iprod_out): the R x R part of tlb200_cp_error alone.
+template <typename T>
+__global__ void __launch_bounds__(256)
+cp_error_iprod_kernel(GramList<T> gl, int R, const T* __restrict__ w, const T* __restrict__ iprod,
+                      const T* __restrict__ norm_x2, T* __restrict__ err_out) {
+    __shared__ double red[8];
+    double ncp = 0.0;
+    for (int e = threadIdx.x; e < R * R; e += 256) {
+        const int r = e / R, s2 = e - r * R;
+        T v = T(1);
+        for (int i = 0; i < gl.n; ++i) v = v * gl.g[i][e];
+        if (w) v = v * (w[r] * w[s2]);
+        ncp += (double)v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ncp += __shfl_xor_sync(0xffffffffu, ncp, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ncp;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double nc = 0.0;
+        for (int i = 0; i < 8; ++i) nc += red[i];
+        const double ip = (double)iprod[0], nx2 = (double)norm_x2[0];
+        double d = nx2 + nc - 2.0 * ip;
+        d = d < 0 ? -d : d;
+        err_out[0] = (T)(sqrt(d) / sqrt(nx2));
+        err_out[1] = (T)ip;
+        err_out[2] = (T)nc;
+    }
+}
+
+extern "C" int tlb200_cp_error_iprod(const void* const* grams, int nmodes, int64_t rank, const void* weights,
+                                     const void* iprod, const void* norm_x2, int dtype, void* err_out, void* stream) {
+    if (!iprod || !norm_x2 || !err_out || rank < 1 || rank > kMaxRank || !dtype_valid(dtype)) return TLB200_EINVAL;
+    set_last_path("simt");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == TLB200_F32) {
+        GramList<float> gl;
+        int st = fill_grams<float>(&gl, grams, nmodes, -1);
+        if (st) return st;
+        cp_error_iprod_kernel<float><<<1, 256, 0, s>>>(gl, (int)rank, (const float*)weights, (const float*)iprod,
+                                                       (const float*)norm_x2, (float*)err_out);
+    } else {
+        GramList<double> gl;
+        int st = fill_grams<double>(&gl, grams, nmodes, -1);
+        if (st) return st;
+        cp_error_iprod_kernel<double><<<1, 256, 0, s>>>(gl, (int)rank, (const double*)weights, (const double*)iprod,
+                                                        (const double*)norm_x2, (double*)err_out);
+    }
+    TLB_CHECK_LAUNCH();
+    return TLB200_OK;
 }
 
 extern "C" int tlb200_nncp_update(const void* const* grams, int nmodes, int mode, int64_t rank, const void* weights,

@@ -173,7 +173,7 @@ size_t workspace_for(const Geometry& g, int64_t rank, int dtype) {
     size_t total = 256;
     if (g.pc > 0) total += align_up((size_t)g.A * rank * es, 256);
     if (g.qc > 0) total += align_up((size_t)g.B * rank * es, 256);
-    if (g.splits > 1) total += align_up((size_t)g.splits * g.J * rank * es, 256);
+    total += align_up((size_t)g.splits * g.J * rank * es, 256);       // also for one split: the *_partials entry point
     return total;
 }
 
@@ -198,11 +198,11 @@ int launch(const T* t, const Geometry& g, int R, const T* P, const T* Q, T* dst,
 template <typename T>
 int run(const T* t, const int64_t* lead_shape, int nlead, int mode, const T* const* factors, const int64_t* frs,
         const int64_t* fcs, int64_t rank, const T* weights, T* out, int64_t out_ld, void* workspace, const Geometry& g,
-        cudaStream_t stream) {
+        cudaStream_t stream, tlb200_partials_t* info = nullptr) {
     Carver ws(workspace);
     const T* P = g.pc > 0 ? ws.take<T>((size_t)g.A * rank) : nullptr;
     const T* Q = g.qc > 0 ? ws.take<T>((size_t)g.B * rank) : nullptr;
-    T* partial = g.splits > 1 ? ws.take<T>((size_t)g.splits * g.J * rank) : nullptr;
+    T* partial = (g.splits > 1 || info != nullptr) ? ws.take<T>((size_t)g.splits * g.J * rank) : nullptr;
     const T* w = weights;      // folded into the first table that exists
     int st;
     // a table made of one unweighted, row-major factor is used in place (3-way sweeps: no prep launch at all)
@@ -236,6 +236,15 @@ int run(const T* t, const int64_t* lead_shape, int nlead, int mode, const T* con
     st = vec_ok ? launch<T, VMAX>(t, g, R, P, Q, dst, dst_ld, dst_split, stream)
                 : launch<T, 1>(t, g, R, P, Q, dst, dst_ld, dst_split, stream);
     if (st) return st;
+    if (info != nullptr) {          // leave the partials unsummed for tlb200_cp_update_fused
+        info->data = partial;
+        info->splits = g.splits;
+        info->split_stride = g.J * rank;
+        info->ld = rank;
+        info->rows = g.J;
+        info->rank = rank;
+        return TLB200_OK;
+    }
     if (partial) {
         int64_t blocks = ceil_div(g.J * rank, 256);
         if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
@@ -276,4 +285,26 @@ extern "C" int tlb200_mttkrp_from_ttm(const void* t, const int64_t* lead_shape, 
                           f_col_stride, rank, (const float*)weights, (float*)out, out_ld, workspace, g, s);
     return run<double>((const double*)t, lead_shape, nlead, mode, reinterpret_cast<const double* const*>(factors), f_row_stride,
                        f_col_stride, rank, (const double*)weights, (double*)out, out_ld, workspace, g, s);
+}
+
+extern "C" int tlb200_mttkrp_from_ttm_partials(const void* t, const int64_t* lead_shape, int nlead, int mode,
+                                               const void* const* factors, const int64_t* f_row_stride,
+                                               const int64_t* f_col_stride, int64_t rank, const void* weights, int dtype,
+                                               void* workspace, size_t workspace_bytes, tlb200_partials_t* partials,
+                                               void* stream) {
+    Geometry g;
+    if (!dtype_valid(dtype) || !partials) return TLB200_EINVAL;
+    int st = make_geometry(lead_shape, nlead, mode, rank, dtype, &g);
+    if (st) return st;
+    if (!t || !factors || !f_row_stride || !f_col_stride || !workspace) return TLB200_EINVAL;
+    for (int i = 0; i < nlead; ++i)
+        if (i != mode && !factors[i]) return TLB200_EINVAL;
+    if (workspace_bytes < workspace_for(g, rank, dtype)) return TLB200_EWORKSPACE;
+    set_last_path("simt");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == TLB200_F32)
+        return run<float>((const float*)t, lead_shape, nlead, mode, reinterpret_cast<const float* const*>(factors), f_row_stride,
+                          f_col_stride, rank, (const float*)weights, nullptr, rank, workspace, g, s, partials);
+    return run<double>((const double*)t, lead_shape, nlead, mode, reinterpret_cast<const double* const*>(factors), f_row_stride,
+                       f_col_stride, rank, (const double*)weights, nullptr, rank, workspace, g, s, partials);
 }

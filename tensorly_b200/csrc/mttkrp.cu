@@ -124,7 +124,8 @@ static size_t workspace_for(const tlb200_mttkrp_plan_t& pl, int dtype) {
 template <typename T>
 static int run(const T* x, const int64_t* shape, int ndim, int mode, const T* const* factors,
                const int64_t* frs, const int64_t* fcs, int64_t rank, const T* weights, T* out,
-               int64_t out_ld, void* workspace, const tlb200_mttkrp_plan_t& pl, cudaStream_t stream) {
+               int64_t out_ld, void* workspace, const tlb200_mttkrp_plan_t& pl, cudaStream_t stream,
+               tlb200_partials_t* info = nullptr) {
     Carver ws(workspace);
     const T* P = pl.p_count > 0 ? ws.take<T>((size_t)pl.A * pl.rank_padded) : nullptr;
     T* Q = ws.take<T>((size_t)2 * (pl.B + 64) * pl.rank_padded);
@@ -185,6 +186,15 @@ static int run(const T* x, const int64_t* shape, int ndim, int mode, const T* co
         p.nsplit = pl.splits;
         st = launch_stream_gemm<T>(p, stream_gemm_tr_for(rank, dtype), pl.sb == 1, stream);
         if (st) return st;
+    }
+    if (info != nullptr) {          // leave the split-K partials unsummed for tlb200_cp_update_fused
+        info->data = partial;
+        info->splits = pl.splits;
+        info->split_stride = pl.J * pl.rank_padded;
+        info->ld = pl.rank_padded;
+        info->rows = pl.J;
+        info->rank = rank;
+        return TLB200_OK;
     }
     const int64_t total = pl.J * rank;
     if constexpr (sizeof(T) == 4) {
@@ -279,4 +289,31 @@ extern "C" int tlb200_mttkrp(const void* x, const int64_t* shape, int ndim, int 
                           f_col_stride, rank, (const float*)weights, (float*)out, out_ld, workspace, pl, s);
     return run<double>((const double*)x, shape, ndim, mode, reinterpret_cast<const double* const*>(factors), f_row_stride,
                        f_col_stride, rank, (const double*)weights, (double*)out, out_ld, workspace, pl, s);
+}
+
+extern "C" int tlb200_mttkrp_partials(const void* x, const int64_t* shape, int ndim, int mode, const void* const* factors,
+                                      const int64_t* f_row_stride, const int64_t* f_col_stride, int64_t rank,
+                                      const void* weights, int dtype, void* workspace, size_t workspace_bytes, int path,
+                                      tlb200_partials_t* partials, void* stream) {
+    tlb200_mttkrp_plan_t pl;
+    if (!partials) return TLB200_EINVAL;
+    int st = make_plan(shape, ndim, mode, rank, dtype, path, &pl);
+    if (st) return st;
+    if (pl.rank_passes > 1) return TLB200_EUNSUPPORTED;
+    if (!x || !factors || !f_row_stride || !f_col_stride || !workspace) return TLB200_EINVAL;
+    for (int i = 0; i < ndim; ++i)
+        if (i != mode && !factors[i]) return TLB200_EINVAL;
+    if (pl.path == TLB200_PATH_TCGEN05 && reinterpret_cast<uintptr_t>(x) % 16) {
+        if (path == TLB200_PATH_TCGEN05) return TLB200_EUNSUPPORTED;
+        st = make_plan(shape, ndim, mode, rank, dtype, TLB200_PATH_SIMT, &pl);
+        if (st) return st;
+    }
+    if (workspace_bytes < workspace_for(pl, dtype)) return TLB200_EWORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) % 256) return TLB200_EINVAL;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == TLB200_F32)
+        return run<float>((const float*)x, shape, ndim, mode, reinterpret_cast<const float* const*>(factors), f_row_stride,
+                          f_col_stride, rank, (const float*)weights, nullptr, 0, workspace, pl, s, partials);
+    return run<double>((const double*)x, shape, ndim, mode, reinterpret_cast<const double* const*>(factors), f_row_stride,
+                       f_col_stride, rank, (const double*)weights, nullptr, 0, workspace, pl, s, partials);
 }

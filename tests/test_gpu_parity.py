@@ -1034,3 +1034,63 @@ def test_own_tucker_c3_sized_random_init_vs_exact_fp64_hooi():
     _, errs = tb.tucker(x, [R, R, R], n_iter_max=sweeps, init="random", random_state=1, tol=0, return_errors=True)
     dev_ = max(abs(a - b) / b for a, b in zip(errs, exact))
     assert dev_ <= 1e-4, (errs, exact)
+
+
+# --------------------------------------------------------------------------- fused right-hand sides (round 2)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape,rank", [((96, 80, 112), 16), ((300, 64, 150), 32), ((256, 200, 260), 64), ((40, 24, 20, 12), 8),
+                                        ((130, 70, 45), 10)])
+def test_fused_update_equals_unfused(shape, rank, dtype):
+    """mttkrp_partials + cp_update_fused (+ cp_error_iprod) against mttkrp + cp_update + cp_error: same factor rows, Gram,
+    summed MTTKRP, inner product and error — the partial sums are only added in a different (fixed) order."""
+    rng = np.random.RandomState(23)
+    x = dev(rng.random_sample(shape).astype(dtype))
+    fs = [dev(rng.random_sample((s, rank)).astype(dtype)) for s in shape]
+    w = torch.ones(rank, dtype=x.dtype, device="cuda")
+    grams = [tb.gram(f) for f in fs]
+    nx2 = tb.sumsq(x)
+    tol = 2e-5 if dtype == np.float32 else 1e-11
+    t = tb.mode_dot(x, fs[-1], len(shape) - 1, transpose=True)
+    for mode in range(len(shape)):
+        m = tb.unfolding_dot_khatri_rao(x, (None, fs), mode)
+        g_ref = torch.empty((rank, rank), dtype=x.dtype, device="cuda")
+        f_ref = tb.cp_update(grams, mode, w, m, gram_out=g_ref)
+        kinds = ["tensor"] + (["tree"] if mode < len(shape) - 1 and len(shape) >= 3 else [])
+        for kind in kinds:
+            # the partials live in the per-stream workspace: produce them right before the call that consumes them
+            part = (tb._ops.mttkrp_partials(x, (None, fs), mode) if kind == "tensor"
+                    else tb._ops.mttkrp_from_ttm_partials(t, (None, fs), mode))
+            g_new = torch.empty((rank, rank), dtype=x.dtype, device="cuda")
+            m_out = torch.empty_like(m)
+            ip = torch.zeros(1, dtype=x.dtype, device="cuda")
+            f_new = tb._ops.cp_update_fused(grams, mode, w, part, gram_out=g_new, m_out=m_out, iprod_out=ip)
+            assert rel_fro(host(m_out), host(m)) <= tol
+            cond = float(torch.linalg.cond(g_ref.double()))
+            assert rel_fro(host(f_new), host(f_ref)) <= max(tol, 50 * cond * np.finfo(dtype).eps)
+            assert rel_fro(host(g_new), host(g_ref)) <= max(tol, 50 * cond * np.finfo(dtype).eps)
+            ip_ref = float((m.double() * f_ref.double()).sum())
+            assert abs(float(ip) - ip_ref) <= max(tol, 50 * cond * np.finfo(dtype).eps) * abs(ip_ref)
+            new_grams = [g_new if i == mode else g for i, g in enumerate(grams)]
+            e1 = host(tb._ops.cp_error_iprod(new_grams, w, ip, nx2))
+            e2 = host(tb.cp_error(new_grams, w, m_out, f_new, nx2))
+            assert abs(e1[2] - e2[2]) <= tol * abs(e2[2]) and abs(e1[1] - e2[1]) <= 10 * tol * abs(e2[1])
+
+
+def test_fused_sweep_same_trajectory_as_unfused(monkeypatch):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand((200, 180, 160), generator=g, device="cuda")
+    fs = [torch.rand(s, 32, generator=g, device="cuda") for s in x.shape]
+    w = torch.ones(32, device="cuda")
+    runs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("TLB200_FUSED_UPDATE", flag)
+        st = tb.CPALS(x, w, fs)
+        assert st._fuse == (flag == "1")
+        errs = []
+        for _ in range(6):
+            st.sweep(True)
+            errs.append(float(st.err[0]))
+        runs.append((errs, [f.clone() for f in st.factors], tb.launch_count()))
+    assert max(abs(a - b) / b for a, b in zip(runs[0][0], runs[1][0])) <= 1e-5
+    for a, b in zip(runs[0][1], runs[1][1]):
+        assert float(torch.linalg.norm(a - b) / torch.linalg.norm(b)) <= 1e-3
