@@ -566,7 +566,9 @@ cp_update_kernel(GramList<T> gl, int mode, int R, const T* __restrict__ w, T l2,
         for (int e = tid; e < kSolveRows * R; e += blockDim.x) {
             const int rr = e / R, c = e - rr * R;
             const int64_t gr = row0 + rr;
-            Y[rr * ld + c] = gr < rows ? msource_load<T>(ms, gr, perm[c]) : T(0);
+            const T v = gr < rows ? msource_load<T>(ms, gr, perm[c]) : T(0);
+            Y[rr * ld + c] = v;
+            if (ms.m_out != nullptr && gr < rows) ms.m_out[gr * ms.m_out_ld + perm[c]] = v;
         }
         __syncthreads();
     }
