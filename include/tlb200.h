@@ -379,6 +379,12 @@ int tlb200_comm_close(void* peer_ptr);
 int tlb200_comm_free(void* ptr);
 int tlb200_allreduce_oneshot(const void* in, void* out, int64_t count, int dtype, void* const* bufs,
                              int world, int rank, size_t max_payload_bytes, void* stream);
+/* The same exchange with the split-K reduction of the MTTKRP fused into its push phase (compute + collective in
+ * one kernel): the local contribution is the ordered sum over splits of *m, followed by tail_count plain elements
+ * of `tail` (may be NULL; the R x R Gram partial that shares the exchange).  out: contiguous. */
+int tlb200_allreduce_partials(const tlb200_partials_t* m, const void* tail, int64_t tail_count, void* out,
+                              int dtype, void* const* bufs, int world, int rank,
+                              size_t max_payload_bytes, void* stream);
 
 #ifdef __cplusplus
 }

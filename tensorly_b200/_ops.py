@@ -277,6 +277,17 @@ class PartialMttkrp:
         self.shape = (int(info.rows), int(info.rank))
 
 
+def plain_partials(m: torch.Tensor) -> "PartialMttkrp":
+    """A summed MTTKRP (rows x rank, unit column stride) dressed as a one-split PartialMttkrp for cp_update_fused."""
+    _check_tensor(m, "m")
+    if m.dim() != 2 or m.stride(1) != 1:
+        raise ValueError("plain_partials expects a row-major matrix")
+    info = _lib.Partials()
+    info.data, info.splits, info.split_stride = m.data_ptr(), 1, 0
+    info.ld, info.rows, info.rank = m.stride(0), m.shape[0], m.shape[1]
+    return PartialMttkrp(info, m, m.dtype, m.device)
+
+
 def mttkrp_partials(tensor: torch.Tensor, cp_tensor, mode: int) -> "PartialMttkrp":
     """unfolding_dot_khatri_rao without its final split-K reduction launch (the solve sums the partials while it loads
     them).  Raises NotImplementedError where the MTTKRP needs several passes (rank > 64 on the tensor-core path)."""

@@ -147,6 +147,13 @@ class _Comm:
         self.dist.all_reduce(t, group=self.group)
         return t
 
+    def all_reduce_partials(self, part, tail, out):
+        """Fused split-K sum + exchange; only with the peer-memory path (the caller checks `graph_safe`)."""
+        return self._p2p.all_reduce_partials(part, tail, out)
+
+    def fits_p2p(self, t) -> bool:
+        return self._p2p is not None and self._p2p.fits(t)
+
     def close(self):
         if self._p2p is not None:
             self._p2p.close()
@@ -224,6 +231,7 @@ class CPALS:
         self.norm_x2 = torch.empty(1, dtype=dt, device=dev)
         self.mttkrp_last: Optional[torch.Tensor] = None
         self.iprod = torch.zeros(1, dtype=dt, device=dev)
+        self._mbuf = {}
         self._iprod_fresh = False
         self._fuse = (update == "ls" and hasattr(self.ops, "cp_update_fused") and tensor_local.is_cuda
                       and os.environ.get("TLB200_FUSED_UPDATE", "1") != "0")
@@ -296,12 +304,47 @@ class CPALS:
             self.mttkrp_last = None
         return True
 
+    def _update_mode_fused_exchange(self, mode: int) -> bool:
+        """LS update of a mode whose MTTKRP is a partial sum over the slabs, on the peer-memory path: the exchange kernel
+        sums the split-K partials while it pushes them (no reduction launch), the solve takes the exchanged MTTKRP and
+        returns <M, F> for the error."""
+        packed = self._pack is not None and mode == self._pack_mode
+        rows = self.x.shape[mode]
+        if packed:
+            buf, m = self._pack, self._pack_m
+        else:
+            if self._mbuf.get(mode) is None:
+                self._mbuf[mode] = torch.empty((rows, self.rank), dtype=self.x.dtype, device=self.x.device)
+            buf = m = self._mbuf[mode]
+        if not self.comm.fits_p2p(buf):
+            return False
+        last = mode == self.ndim - 1
+        try:
+            if self._contracted is not None and not last:
+                part = self.ops.mttkrp_from_ttm_partials(self._contracted, (self._w, self.factors), mode)
+            else:
+                part = self.ops.mttkrp_partials(self.x, (self._w, self.factors), mode)
+            self.comm.all_reduce_partials(part, self.grams[self.shard_mode] if packed else None, buf.reshape(-1))
+            self.ops.cp_update_fused(self.grams, mode, self.weights, _ops.plain_partials(m), self.l2_reg,
+                                     out=self.factors[mode], gram_out=self.grams[mode],
+                                     iprod_out=self.iprod if last else None)
+        except NotImplementedError:
+            self._fuse = False
+            return False
+        if last:
+            self._iprod_fresh = True
+            self.mttkrp_last = None
+        return True
+
     def _update_mode(self, mode: int) -> None:
         if self.mask is not None and self.update == "mu":
             self._impute()
         # the fused form applies when this rank's MTTKRP rows are final as they are: single GPU, or the sharded mode
         local = self.shard_mode is None or (self.shard_mode == mode and mode != self.ndim - 1)
         if self._fuse and local and self._update_mode_fused(mode):
+            return
+        if (self._fuse and not local and self.shard_mode is not None and mode != self.shard_mode and self.comm.graph_safe
+                and self._update_mode_fused_exchange(mode)):
             return
         if mode == self.ndim - 1:
             self._iprod_fresh = False

@@ -51,11 +51,34 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
+// What this rank contributes: a plain vector, or — fused split-K reduction — the unsummed partials of an MTTKRP
+// ([splits][rows][ld], summed in split order while they are pushed) optionally followed by a plain tail (the R x R
+// Gram partial that travels in the same exchange).
+template <typename T>
+struct CommSource {
+    const T* in;            // plain vector of `count` elements, or the partials
+    int splits;             // 1: plain
+    int64_t split_stride;
+    int64_t cols, ld;       // partials: element e <-> (row e / cols, column e % cols) at row * ld + column
+    int64_t count1;         // elements coming from `in`
+    const T* in2;           // plain tail (count - count1 elements) or null
+};
+
+template <typename T>
+__device__ __forceinline__ T comm_fetch(const CommSource<T>& src, int64_t e) {
+    if (e >= src.count1) return src.in2[e - src.count1];
+    if (src.splits == 1 && src.ld == src.cols) return src.in[e];
+    const int64_t row = e / src.cols, c = e - row * src.cols;
+    const T* p = src.in + row * src.ld + c;
+    return src.splits == 1 ? *p : ordered_sum_strided<T>(p, src.splits, (size_t)src.split_stride);
+}
+
 // slot_bytes: size of one rank's slot; data region of a buffer = [2 parities][world slots][slot_bytes]
 template <typename T>
 __global__ void __launch_bounds__(kCommThreads)
-allreduce_oneshot_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t count, CommPeers peers, int world, int rank,
+allreduce_oneshot_kernel(const CommSource<T> src, T* __restrict__ out, int64_t count, CommPeers peers, int world, int rank,
                          size_t slot_bytes) {
+    const T* __restrict__ in = src.in;
     __shared__ unsigned long long s_epoch;
     __shared__ int s_last;
     CommHeader* me = reinterpret_cast<CommHeader*>(peers.buf[rank]);
@@ -67,23 +90,33 @@ allreduce_oneshot_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t 
     const size_t my_slot = kCommHeader + ((size_t)par * world + rank) * slot_bytes;
     constexpr int VW = 16 / sizeof(T);
     const int64_t nvec = count / VW;
-    const bool vec_ok = (reinterpret_cast<uintptr_t>(in) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+    const bool plain = src.splits == 1 && src.ld == src.cols && src.in2 == nullptr;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+    const bool vec_in = plain && (reinterpret_cast<uintptr_t>(in) % 16 == 0);
     const int64_t stride = (int64_t)gridDim.x * kCommThreads;
     const int64_t first = (int64_t)blockIdx.x * kCommThreads + tid;
 
     // ---- push ----
     if (vec_ok) {
         for (int64_t v = first; v < nvec; v += stride) {
-            const int4 x = reinterpret_cast<const int4*>(in)[v];
+            int4 x;
+            if (vec_in) {
+                x = reinterpret_cast<const int4*>(in)[v];
+            } else {
+                T t[VW];
+#pragma unroll
+                for (int k = 0; k < VW; ++k) t[k] = comm_fetch<T>(src, v * VW + k);
+                memcpy(&x, t, 16);
+            }
             for (int p = 0; p < world; ++p) reinterpret_cast<int4*>(peers.buf[p] + my_slot)[v] = x;
         }
         for (int64_t e = nvec * VW + first; e < count; e += stride) {
-            const T x = in[e];
+            const T x = comm_fetch<T>(src, e);
             for (int p = 0; p < world; ++p) reinterpret_cast<T*>(peers.buf[p] + my_slot)[e] = x;
         }
     } else {
         for (int64_t e = first; e < count; e += stride) {
-            const T x = in[e];
+            const T x = comm_fetch<T>(src, e);
             for (int p = 0; p < world; ++p) reinterpret_cast<T*>(peers.buf[p] + my_slot)[e] = x;
         }
     }
@@ -190,6 +223,33 @@ extern "C" int tlb200_comm_close(void* peer_ptr) {
 
 extern "C" int tlb200_comm_free(void* ptr) { return ptr && cudaFree(ptr) == cudaSuccess ? TLB200_OK : TLB200_ECUDA; }
 
+namespace tlb200 {
+namespace {
+template <typename T>
+int launch_allreduce(const CommSource<T>& src, T* out, int64_t count, void* const* bufs, int world, int rank,
+                     size_t max_payload_bytes, cudaStream_t s) {
+    const size_t slot = align_up(max_payload_bytes, 256);
+    if ((size_t)count * sizeof(T) > slot) return TLB200_EWORKSPACE;
+    if (count == 0) return TLB200_OK;
+    CommPeers peers;
+    for (int p = 0; p < kCommMaxWorld; ++p) peers.buf[p] = p < world ? static_cast<unsigned char*>(bufs[p]) : nullptr;
+    for (int p = 0; p < world; ++p)
+        if (!peers.buf[p]) return TLB200_EINVAL;
+    set_last_path("p2p");
+    const int64_t vecs = ceil_div((int64_t)count * (int64_t)sizeof(T), 16);
+    // every CTA must be resident (they wait for each other): at most 128.  A fused split-K sum wants the threads
+    // (one vector each, `splits` loads behind it), a plain push wants few CTAs (>= 4 vectors per thread)
+    int grid = (int)ceil_div(vecs, kCommThreads * (src.splits > 1 ? 1 : 4));
+    if (grid < 1) grid = 1;
+    const int cap = src.splits > 1 ? 128 : 32;
+    if (grid > cap) grid = cap;
+    allreduce_oneshot_kernel<T><<<grid, kCommThreads, 0, s>>>(src, out, count, peers, world, rank, slot);
+    TLB_CHECK_LAUNCH();
+    return TLB200_OK;
+}
+}  // namespace
+}  // namespace tlb200
+
 // Sum `count` elements over `world` ranks; in may equal out.  bufs[p] = rank p's symmetric buffer as mapped in THIS
 // process (bufs[rank] = the local allocation), each of tlb200_comm_buffer_bytes(world, max_payload_bytes) bytes.
 // Every rank must issue the same sequence of calls on its buffer.
@@ -198,23 +258,34 @@ extern "C" int tlb200_allreduce_oneshot(const void* in, void* out, int64_t count
     if (!in || !out || !bufs || count < 0 || world < 1 || world > kCommMaxWorld || rank < 0 || rank >= world ||
         !dtype_valid(dtype))
         return TLB200_EINVAL;
-    const size_t slot = align_up(max_payload_bytes, 256);
-    if ((size_t)count * dtype_size(dtype) > slot) return TLB200_EWORKSPACE;
-    if (count == 0) return TLB200_OK;
-    CommPeers peers;
-    for (int p = 0; p < kCommMaxWorld; ++p) peers.buf[p] = p < world ? static_cast<unsigned char*>(bufs[p]) : nullptr;
-    for (int p = 0; p < world; ++p)
-        if (!peers.buf[p]) return TLB200_EINVAL;
-    set_last_path("p2p");
-    const int64_t vecs = ceil_div((int64_t)count * (int64_t)dtype_size(dtype), 16);
-    int grid = (int)ceil_div(vecs, kCommThreads * 4);          // >= 4 vectors per thread
-    if (grid < 1) grid = 1;
-    if (grid > 32) grid = 32;                                  // every CTA must be resident: they wait for each other
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (dtype == TLB200_F32)
-        allreduce_oneshot_kernel<float><<<grid, kCommThreads, 0, s>>>((const float*)in, (float*)out, count, peers, world, rank, slot);
-    else
-        allreduce_oneshot_kernel<double><<<grid, kCommThreads, 0, s>>>((const double*)in, (double*)out, count, peers, world, rank, slot);
-    TLB_CHECK_LAUNCH();
-    return TLB200_OK;
+    auto go = [&](auto tag) {
+        using T = decltype(tag);
+        CommSource<T> src;
+        src.in = static_cast<const T*>(in); src.splits = 1; src.split_stride = 0; src.cols = count; src.ld = count;
+        src.count1 = count; src.in2 = nullptr;
+        return launch_allreduce<T>(src, static_cast<T*>(out), count, bufs, world, rank, max_payload_bytes, s);
+    };
+    return dtype == TLB200_F32 ? go(float()) : go(double());
+}
+
+// The same exchange with the split-K reduction of an MTTKRP fused into its push phase: rank-local contribution =
+// sum over splits of `m` (tlb200_partials_t), followed by `tail_count` plain elements of `tail` (may be null: the
+// R x R Gram partial that shares the exchange).  out: contiguous, m->rows * m->rank + tail_count elements.
+extern "C" int tlb200_allreduce_partials(const tlb200_partials_t* m, const void* tail, int64_t tail_count, void* out,
+                                         int dtype, void* const* bufs, int world, int rank, size_t max_payload_bytes,
+                                         void* stream) {
+    if (!m || !m->data || !out || !bufs || tail_count < 0 || (tail_count > 0 && !tail) || world < 1 || world > kCommMaxWorld ||
+        rank < 0 || rank >= world || !dtype_valid(dtype) || m->splits < 1 || m->rows < 1 || m->rank < 1 || m->ld < m->rank)
+        return TLB200_EINVAL;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t count1 = m->rows * m->rank;
+    auto go = [&](auto tag) {
+        using T = decltype(tag);
+        CommSource<T> src;
+        src.in = static_cast<const T*>(m->data); src.splits = (int)m->splits; src.split_stride = m->split_stride;
+        src.cols = m->rank; src.ld = m->ld; src.count1 = count1; src.in2 = tail_count > 0 ? static_cast<const T*>(tail) : nullptr;
+        return launch_allreduce<T>(src, static_cast<T*>(out), count1 + tail_count, bufs, world, rank, max_payload_bytes, s);
+    };
+    return dtype == TLB200_F32 ? go(float()) : go(double());
 }

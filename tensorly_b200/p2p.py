@@ -59,6 +59,22 @@ class P2PComm:
         _lib.check(st, "allreduce_oneshot")
         return t
 
+    def all_reduce_partials(self, part, tail, out: torch.Tensor) -> torch.Tensor:
+        """out[: rows * rank] = sum over ranks of (sum over splits of the MTTKRP partials), out[rows * rank:] = sum over
+        ranks of `tail` (a small contiguous tensor, or None) — the split-K reduction rides in the push phase of the
+        exchange (tlb200_allreduce_partials)."""
+        rows, rank = part.shape
+        n_tail = 0 if tail is None else tail.numel()
+        if out.numel() != rows * rank + n_tail or not out.is_contiguous():
+            raise ValueError("all_reduce_partials: out must be contiguous with rows * rank + tail elements")
+        with torch.cuda.device(self.device):
+            st = self.lib.tlb200_allreduce_partials(ctypes.byref(part.info), tail.data_ptr() if tail is not None else None,
+                                                    n_tail, out.data_ptr(), _DTYPES[out.dtype], self._bufs, self.world,
+                                                    self.rank, self.max_payload,
+                                                    torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(st, "allreduce_partials")
+        return out
+
     def close(self) -> None:
         if getattr(self, "peers", None) is None:
             return
