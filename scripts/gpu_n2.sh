@@ -7,7 +7,8 @@ echo "== bench 2 GPUs (driver command) =="; timeout 600 $TR --master-port 29512 
 python - <<'P'
 import json
 try:
-    d=json.loads(open('gpurun_out/bench_n${NG:-2}.json').read().strip().splitlines()[-1])
+    import os
+    d=json.loads(open('gpurun_out/bench_n%s.json' % os.environ.get('NG','2')).read().strip().splitlines()[-1])
     print('c5', d['value'], d['ms_per_step'], d['config']['collective'], d['parity'], d['launches_per_sweep'])
     print('c2', d['c2']['value'], d['c2']['ms_per_step'])
     print('e2e', d['e2e'])
