@@ -162,43 +162,142 @@ orth_apply_kernel(const T* __restrict__ z, int64_t rows, int R, int64_t rs, int6
 // launches instead of the five (TTM prep + TTM + 2 orth kernels + copies) the generic entry points would take.
 constexpr int PS_ROWS = 16;
 constexpr int PS_KC = 64;
+constexpr int PS_GLD = 66;                                          // G tile row stride: 528 bytes, 16-byte aligned
+constexpr int PS_STAGES = 3;
+constexpr int PS_STAGE_DOUBLES = PS_KC * OR_MAX + PS_ROWS * PS_GLD;  // 5152 doubles = 41 216 bytes
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int bytes = valid ? 16 : 0;                               // 0: the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gsrc), "r"(bytes) : "memory");
+}
+
+
+// Shifted Cholesky S + shift I = R^T R for the power step: ONE barrier per pivot (row k of S is final once pivot
+// k - 1 is done, so the scaled row R[k][k:] goes to a separate matrix while the trailing update reads the unscaled
+// one), rsqrt instead of sqrt + divide, no explicit inverse — kernel B solves the triangular system directly.
+// Rm[k][j] = R[k][j] for j >= k (untouched below the diagonal), invd[k] = 1 / R[k][k].  blockDim = 256.
+__device__ void chol_upper_64(double (*S)[OR_MAX + 1], double* __restrict__ Rm, double* __restrict__ invd, int R,
+                              int* bad_out) {
+    const int tid = threadIdx.x;
+    __shared__ double s_shift2;
+    if (tid == 0) {
+        double tr = 0.0;
+        for (int i = 0; i < R; ++i) tr += S[i][i];
+        s_shift2 = ldexp(tr / R, -43);
+    }
+    __syncthreads();
+    const double shift = s_shift2;
+    if (tid < R) S[tid][tid] += shift;
+    __syncthreads();
+    const int ti = tid >> 4, tj = tid & 15;
+    int bad = 0;
+    for (int k = 0; k < R; ++k) {
+        double d = S[k][k];
+        if (!(d > shift)) { d = shift > 0.0 ? shift : 1e-300; bad = 1; }
+        const double rs = rsqrt(d);
+        if (tid >= k && tid < R) Rm[k * R + tid] = tid == k ? d * rs : S[k][tid] * rs;
+        if (tid == k) invd[k] = rs;
+        const double id = rs * rs;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int i = ti + 16 * a;
+            if (i <= k || i >= R) continue;
+            const double ski = S[k][i] * id;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int j = tj + 16 * b;
+                if (j >= i && j < R) S[i][j] -= ski * S[k][j];
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && bad_out) *bad_out = bad;
+}
 
 __global__ void __launch_bounds__(256)
 power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const double* __restrict__ U, int p,
                     int64_t u_ld, double* __restrict__ Z, double* __restrict__ partial, double* __restrict__ ssum,
-                    unsigned* __restrict__ counter, double* __restrict__ rinv, int* __restrict__ status, int parallel) {
+                    unsigned* __restrict__ counter, double* __restrict__ rinv, int* __restrict__ status, int parallel,
+                    int pipelined) {
     extern __shared__ __align__(16) unsigned char ps_smem[];
     typedef double Row[OR_MAX + 1];
-    // [Us: PS_KC x 64][Gs: 16 x 65]   later, in the last CTA only: [S: 64 x 65][Ri: 64 x 65]
-    double* Us = reinterpret_cast<double*>(ps_smem);                 // [PS_KC][64]
-    Row* Gs = reinterpret_cast<Row*>(Us + PS_KC * OR_MAX);           // [PS_ROWS][65]
+    // GEMM phase: PS_STAGES stages of [Us: PS_KC x 64][Gs: 16 x PS_GLD]; later, in the factoring CTA only:
+    // [S: 64 x 65][Ri: 64 x 65]
     __shared__ int s_last;
     const int tid = threadIdx.x;
     const int r = tid >> 4, c4 = (tid & 15) * 4;
     const int64_t row0 = (int64_t)blockIdx.x * PS_ROWS;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     const long long t_start = clock64();
-    for (int64_t k0 = 0; k0 < n; k0 += PS_KC) {
+    double* stage0 = reinterpret_cast<double*>(ps_smem);
+    const int nchunks = (int)((n + PS_KC - 1) / PS_KC);
+    if (pipelined) {
+        // Every CTA streams all of U (n x p) and 16 rows of G out of L2; with plain loads the phase was a chain of
+        // exposed L2 round trips (70 us of a 150 us step at n = 512).  cp.async keeps PS_STAGES - 1 chunks in flight.
+        const int pc = (p + 1) / 2;                                  // 16-byte pieces per row of U
+        for (int e = tid; e < PS_STAGES * PS_STAGE_DOUBLES; e += 256) stage0[e] = 0.0;     // columns >= p stay zero
         __syncthreads();
-        for (int e = tid; e < PS_ROWS * PS_KC; e += 256) {
-            const int rr = e >> 6, kk = e & 63;
-            Gs[rr][kk] = (row0 + rr < n && k0 + kk < n) ? G[(row0 + rr) * g_ld + k0 + kk] : 0.0;
+        auto issue = [&](int chunk) {
+            double* us = stage0 + (chunk % PS_STAGES) * PS_STAGE_DOUBLES;
+            double* gs = us + PS_KC * OR_MAX;
+            const int64_t k0 = (int64_t)chunk * PS_KC;
+            for (int e = tid; e < PS_KC * pc; e += 256) {
+                const int kk = e / pc, c2 = e - kk * pc;
+                const bool ok = k0 + kk < n;
+                cp_async16(us + kk * OR_MAX + 2 * c2, U + (ok ? (k0 + kk) * u_ld + 2 * c2 : 0), ok);
+            }
+            for (int e = tid; e < PS_ROWS * (PS_KC / 2); e += 256) {
+                const int rr = e / (PS_KC / 2), k2 = e - rr * (PS_KC / 2);
+                const bool ok = row0 + rr < n && k0 + 2 * k2 < n;
+                cp_async16(gs + rr * PS_GLD + 2 * k2, G + (ok ? (row0 + rr) * g_ld + k0 + 2 * k2 : 0), ok);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        for (int c = 0; c < PS_STAGES - 1; ++c) {
+            if (c < nchunks) issue(c); else asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        for (int e = tid; e < PS_KC * OR_MAX; e += 256) {
-            const int kk = e >> 6, c = e & 63;
-            Us[e] = (k0 + kk < n && c < p) ? U[(k0 + kk) * u_ld + c] : 0.0;
-        }
-        __syncthreads();
+        for (int c = 0; c < nchunks; ++c) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(PS_STAGES - 2) : "memory");
+            __syncthreads();                       // chunk c has landed for everyone; chunk c - 1 is fully consumed
+            if (c + PS_STAGES - 1 < nchunks) issue(c + PS_STAGES - 1); else asm volatile("cp.async.commit_group;" ::: "memory");
+            const double* us = stage0 + (c % PS_STAGES) * PS_STAGE_DOUBLES;
+            const double* gs = us + PS_KC * OR_MAX + r * PS_GLD;
 #pragma unroll 8
-        for (int kk = 0; kk < PS_KC; ++kk) {
-            const double g = Gs[r][kk];
-            const double2 u0 = *reinterpret_cast<const double2*>(Us + kk * OR_MAX + c4);
-            const double2 u1 = *reinterpret_cast<const double2*>(Us + kk * OR_MAX + c4 + 2);
-            acc[0] = fma(g, u0.x, acc[0]); acc[1] = fma(g, u0.y, acc[1]);
-            acc[2] = fma(g, u1.x, acc[2]); acc[3] = fma(g, u1.y, acc[3]);
+            for (int kk = 0; kk < PS_KC; ++kk) {
+                const double g = gs[kk];
+                const double2 u0 = *reinterpret_cast<const double2*>(us + kk * OR_MAX + c4);
+                const double2 u1 = *reinterpret_cast<const double2*>(us + kk * OR_MAX + c4 + 2);
+                acc[0] = fma(g, u0.x, acc[0]); acc[1] = fma(g, u0.y, acc[1]);
+                acc[2] = fma(g, u1.x, acc[2]); acc[3] = fma(g, u1.y, acc[3]);
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
+        double* Us0 = stage0;                                        // [PS_KC][64]
+        double* Gs0 = Us0 + PS_KC * OR_MAX;                          // [PS_ROWS][PS_GLD]
+        for (int64_t k0 = 0; k0 < n; k0 += PS_KC) {
+            __syncthreads();
+            for (int e = tid; e < PS_ROWS * PS_KC; e += 256) {
+                const int rr = e >> 6, kk = e & 63;
+                Gs0[rr * PS_GLD + kk] = (row0 + rr < n && k0 + kk < n) ? G[(row0 + rr) * g_ld + k0 + kk] : 0.0;
+            }
+            for (int e = tid; e < PS_KC * OR_MAX; e += 256) {
+                const int kk = e >> 6, c = e & 63;
+                Us0[e] = (k0 + kk < n && c < p) ? U[(k0 + kk) * u_ld + c] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int kk = 0; kk < PS_KC; ++kk) {
+                const double g = Gs0[r * PS_GLD + kk];
+                const double2 u0 = *reinterpret_cast<const double2*>(Us0 + kk * OR_MAX + c4);
+                const double2 u1 = *reinterpret_cast<const double2*>(Us0 + kk * OR_MAX + c4 + 2);
+                acc[0] = fma(g, u0.x, acc[0]); acc[1] = fma(g, u0.y, acc[1]);
+                acc[2] = fma(g, u1.x, acc[2]); acc[3] = fma(g, u1.y, acc[3]);
+            }
         }
     }
+    double* Us = stage0;
     __syncthreads();
     // the Z block: to global, and into shared memory (over the U tile) for its Gram partial
     double* Zs = Us;                                                 // [PS_ROWS][64]
@@ -262,42 +361,54 @@ power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const
     __syncthreads();
     if (tid == 0) { g_ps_trace[0] = t_start; g_ps_trace[1] = t_gemm; }
     PS_TRACE(2);
-    chol_inverse_64(S, Ri, p, status);
+    chol_upper_64(S, rinv, rinv + (size_t)p * p, p, status);          // rinv buffer: [R factor, p x p][1 / diagonal, p]
+    PS_TRACE(3);
     PS_TRACE(4);
-    for (int e = tid; e < p * p; e += 256) rinv[e] = Ri[e / p][e % p];
     PS_TRACE(5);
 }
 
+// U = Z R^{-1} without forming R^{-1}: rows of U solve q R = z.  16 lanes per row (axpy form, like the substitution of
+// cp_update_kernel): step k — the owner of entry k scales it by 1 / R_kk and broadcasts it inside the group, every
+// lane subtracts R[k][i] q_k from the entries i > k it owns.  One shuffle per step on the dependency chain.
 __global__ void __launch_bounds__(256)
-power_step_b_kernel(const double* __restrict__ Z, int64_t n, int p, const double* __restrict__ rinv, double* __restrict__ U,
+power_step_b_kernel(const double* __restrict__ Z, int64_t n, int p, const double* __restrict__ rfac, double* __restrict__ U,
                     int64_t u_ld) {
-    __shared__ double Ri[OR_MAX * OR_MAX];       // 32 KB
-    __shared__ double Zs[PS_ROWS][OR_MAX + 1];
+    __shared__ double Rs[OR_MAX * OR_MAX];       // Rs[k][i] = R[k][i] for i > k, else 0       (32 KB)
+    __shared__ double invd[OR_MAX];
     const int tid = threadIdx.x;
-    const int64_t row0 = (int64_t)blockIdx.x * PS_ROWS;
+    const int64_t row = (int64_t)blockIdx.x * PS_ROWS + (tid >> 4);
+    const int l16 = tid & 15;
     for (int e = tid; e < OR_MAX * OR_MAX; e += 256) {
-        const int i = e >> 6, j = e & 63;
-        Ri[e] = (i < p && j < p) ? rinv[i * p + j] : 0.0;
+        const int k = e >> 6, i = e & 63;
+        Rs[e] = (k < p && i < p && i > k) ? rfac[k * p + i] : 0.0;
     }
-    for (int e = tid; e < PS_ROWS * OR_MAX; e += 256) {
-        const int rr = e >> 6, c = e & 63;
-        Zs[rr][c] = (row0 + rr < n && c < p) ? Z[(row0 + rr) * p + c] : 0.0;
+    if (tid < OR_MAX) invd[tid] = tid < p ? rfac[(size_t)p * p + tid] : 0.0;
+    double b[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int i = t * 16 + l16;
+        b[t] = (row < n && i < p) ? Z[row * p + i] : 0.0;
     }
     __syncthreads();
-    const int r = tid >> 4, c4 = (tid & 15) * 4;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 8
-    for (int i = 0; i < OR_MAX; ++i) {
-        const double z = Zs[r][i];
-        const double2 a0 = *reinterpret_cast<const double2*>(Ri + i * OR_MAX + c4);
-        const double2 a1 = *reinterpret_cast<const double2*>(Ri + i * OR_MAX + c4 + 2);
-        acc[0] = fma(z, a0.x, acc[0]); acc[1] = fma(z, a0.y, acc[1]);
-        acc[2] = fma(z, a1.x, acc[2]); acc[3] = fma(z, a1.y, acc[3]);
-    }
-    if (row0 + r < n)
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
-            if (c4 + t < p) U[(row0 + r) * u_ld + c4 + t] = acc[t];
+    for (int sl = 0; sl < 4; ++sl) {
+#pragma unroll 4
+        for (int kk = 0; kk < 16; ++kk) {
+            const int k = sl * 16 + kk;
+            if (k >= p) break;
+            const double qk = __shfl_sync(0xffffffffu, b[sl] * invd[k], kk, 16);
+            if (l16 == kk) b[sl] = qk;
+            const double* c = Rs + k * OR_MAX + l16;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) b[t] = fma(-c[t * 16], qk, b[t]);
+        }
+    }
+    if (row < n)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int i = t * 16 + l16;
+            if (i < p) U[row * u_ld + i] = b[t];
+        }
 }
 
 // ---- symmetric eigendecomposition of a small matrix (n <= 64): cyclic Jacobi, parallel ordering --------------
@@ -450,7 +561,7 @@ int run(const T* z, int64_t rows, int64_t R, int64_t rs, int64_t cs, T* out, int
 
 extern "C" size_t tlb200_subspace_iterate_workspace_bytes(int64_t n, int64_t p) {
     if (n < 1 || p < 1 || p > OR_MAX) return 0;
-    return 256 + sizeof(double) * ((size_t)n * p + 2 * align_up((size_t)p * p, 32) + (size_t)ceil_div(n, PS_ROWS) * p * p) + 256;
+    return 256 + sizeof(double) * ((size_t)n * p + 2 * align_up((size_t)p * p + OR_MAX, 32) + (size_t)ceil_div(n, PS_ROWS) * p * p) + 256;
 }
 
 extern "C" int tlb200_subspace_iterate(const void* g, int64_t n, int64_t g_ld, void* u, int64_t p, int64_t u_ld, int steps,
@@ -463,17 +574,20 @@ extern "C" int tlb200_subspace_iterate(const void* g, int64_t n, int64_t g_ld, v
     unsigned* counter = static_cast<unsigned*>(workspace);
     int* status = reinterpret_cast<int*>(counter + 1);
     double* rinv = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
-    double* ssum = rinv + align_up((size_t)p * p, 32);
-    double* z = ssum + align_up((size_t)p * p, 32);
+    double* ssum = rinv + align_up((size_t)p * p + OR_MAX, 32);
+    double* z = ssum + align_up((size_t)p * p + OR_MAX, 32);
     double* partial = z + (size_t)n * p;
-    constexpr int smem_a = 2 * OR_MAX * (OR_MAX + 1) * (int)sizeof(double);       // >= the GEMM phase's tiles
-    static_assert(smem_a >= (int)sizeof(double) * (PS_KC * OR_MAX + PS_ROWS * (OR_MAX + 1)), "tile space");
+    constexpr int smem_a = PS_STAGES * PS_STAGE_DOUBLES * (int)sizeof(double);    // 123 648 bytes: 3 GEMM stages
+    static_assert(smem_a >= 2 * OR_MAX * (OR_MAX + 1) * (int)sizeof(double), "the factoring phase reuses the stages");
+    // cp.async moves 16-byte pieces: rows of G and U must start 16-byte aligned
+    const int pipelined = g_ld % 2 == 0 && u_ld % 2 == 0 && reinterpret_cast<uintptr_t>(g) % 16 == 0 &&
+                          reinterpret_cast<uintptr_t>(u) % 16 == 0;
     static std::atomic<uint64_t> attr_done{0};
     if (ensure_dynamic_smem(power_step_a_kernel, smem_a, attr_done)) return TLB200_ECUDA;
     const int nblk = (int)ceil_div(n, PS_ROWS);
     for (int it = 0; it < steps; ++it) {
         power_step_a_kernel<<<nblk, 256, smem_a, s>>>((const double*)g, n, g_ld, (const double*)u, (int)p, u_ld, z, partial,
-                                                      ssum, counter, rinv, status, nblk > 1 && nblk <= kNumSMs);
+                                                      ssum, counter, rinv, status, nblk > 1 && nblk <= kNumSMs, pipelined);
         TLB_CHECK_LAUNCH();
         power_step_b_kernel<<<nblk, 256, 0, s>>>(z, n, (int)p, rinv, (double*)u, u_ld);
         TLB_CHECK_LAUNCH();
