@@ -173,14 +173,25 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, boo
 }
 
 
-// Shifted Cholesky S + shift I = R^T R for the power step: ONE barrier per pivot (row k of S is final once pivot
-// k - 1 is done, so the scaled row R[k][k:] goes to a separate matrix while the trailing update reads the unscaled
-// one), rsqrt instead of sqrt + divide, no explicit inverse — kernel B solves the triangular system directly.
+// Shifted Cholesky S + shift I = R^T R for the power step, S held in REGISTERS: thread (ti, tj) owns the 4 x 4 entries
+// S[ti + 16a][tj + 16b].  Pivot k: the 16 threads that own row k publish it through a double-buffered shared row
+// (one barrier per pivot), everyone forms 1 / d from a float rsqrt seed + two Newton steps and updates its 16
+// entries with FMAs — no shared-memory traffic in the trailing update (the all-in-shared-memory version moved ~50
+// words per thread and pivot: 625 clk per pivot).  No explicit inverse: kernel B solves the triangular system.
 // Rm[k][j] = R[k][j] for j >= k (untouched below the diagonal), invd[k] = 1 / R[k][k].  blockDim = 256.
+__device__ __forceinline__ double fast_rsqrt(double d) {
+    if (!(d > 1e-30 && d < 1e30)) return rsqrt(d);
+    double r = (double)rsqrtf((float)d);
+    r = r * (1.5 - 0.5 * d * r * r);
+    r = r * (1.5 - 0.5 * d * r * r);
+    return r;
+}
+
 __device__ void chol_upper_64(double (*S)[OR_MAX + 1], double* __restrict__ Rm, double* __restrict__ invd, int R,
                               int* bad_out) {
     const int tid = threadIdx.x;
     __shared__ double s_shift2;
+    __shared__ double rowk[2][OR_MAX];
     if (tid == 0) {
         double tr = 0.0;
         for (int i = 0; i < R; ++i) tr += S[i][i];
@@ -188,29 +199,59 @@ __device__ void chol_upper_64(double (*S)[OR_MAX + 1], double* __restrict__ Rm, 
     }
     __syncthreads();
     const double shift = s_shift2;
-    if (tid < R) S[tid][tid] += shift;
-    __syncthreads();
     const int ti = tid >> 4, tj = tid & 15;
-    int bad = 0;
-    for (int k = 0; k < R; ++k) {
-        double d = S[k][k];
-        if (!(d > shift)) { d = shift > 0.0 ? shift : 1e-300; bad = 1; }
-        const double rs = rsqrt(d);
-        if (tid >= k && tid < R) Rm[k * R + tid] = tid == k ? d * rs : S[k][tid] * rs;
-        if (tid == k) invd[k] = rs;
-        const double id = rs * rs;
+    double a[4][4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int i = ti + 16 * a;
-            if (i <= k || i >= R) continue;
-            const double ski = S[k][i] * id;
+    for (int x = 0; x < 4; ++x)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int j = tj + 16 * b;
-                if (j >= i && j < R) S[i][j] -= ski * S[k][j];
-            }
+        for (int y = 0; y < 4; ++y) {
+            const int i = ti + 16 * x, j = tj + 16 * y;
+            a[x][y] = (i < R && j < R) ? S[i][j] + (i == j ? shift : 0.0) : (i == j ? 1.0 : 0.0);
         }
-        __syncthreads();
+    int bad = 0;
+    // publish row 0
+    if (ti == 0) {
+#pragma unroll
+        for (int y = 0; y < 4; ++y) rowk[0][tj + 16 * y] = a[0][y];
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int kb = 0; kb < 4; ++kb) {                 // k = 16 kb + kl: the register index kb is static inside the body
+#pragma unroll 1
+        for (int kl = 0; kl < 16; ++kl) {
+            const int k = 16 * kb + kl;
+            if (k >= R) break;
+            const double* rk = rowk[k & 1];
+            double d = rk[k];
+            if (!(d > shift)) { d = shift > 0.0 ? shift : 1e-300; bad = 1; }
+            const double rs = fast_rsqrt(d);
+            const double id = rs * rs;
+            // row k of R goes out (threads 0..63, one column each)
+            if (tid >= k && tid < R) Rm[k * R + tid] = tid == k ? d * rs : rk[tid] * rs;
+            if (tid == k) invd[k] = rs;
+            double ri[4], rj[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) { ri[x] = rk[ti + 16 * x] * id; rj[x] = rk[tj + 16 * x]; }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const int i = ti + 16 * x, j = tj + 16 * y;
+                    if (i > k && j >= i) a[x][y] = fma(-ri[x], rj[y], a[x][y]);
+                }
+            // publish row k + 1 (owners: ti == (k + 1) % 16, register row (k + 1) / 16) into the other buffer
+            const int kn = k + 1;
+            if (kn < R && ti == (kn & 15)) {
+                const int xn = kn >> 4;
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+                    if (x == xn) {
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) rowk[kn & 1][tj + 16 * y] = a[x][y];
+                    }
+            }
+            __syncthreads();
+        }
     }
     if (tid == 0 && bad_out) *bad_out = bad;
 }
@@ -226,7 +267,9 @@ power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const
     // [S: 64 x 65][Ri: 64 x 65]
     __shared__ int s_last;
     const int tid = threadIdx.x;
-    const int r = tid >> 4, c4 = (tid & 15) * 4;
+    // thread (r, l): row r of the block, columns {2l, 2l+1, 32+2l, 33+2l} — a 16-lane group reads 256 contiguous
+    // bytes per LDS.128 (columns 4l..4l+3 per thread put the lanes 32 bytes apart: 4-way bank conflicts)
+    const int r = tid >> 4, cl = (tid & 15) * 2, ch = 32 + cl;
     const int64_t row0 = (int64_t)blockIdx.x * PS_ROWS;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     const long long t_start = clock64();
@@ -266,8 +309,8 @@ power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const
 #pragma unroll 8
             for (int kk = 0; kk < PS_KC; ++kk) {
                 const double g = gs[kk];
-                const double2 u0 = *reinterpret_cast<const double2*>(us + kk * OR_MAX + c4);
-                const double2 u1 = *reinterpret_cast<const double2*>(us + kk * OR_MAX + c4 + 2);
+                const double2 u0 = *reinterpret_cast<const double2*>(us + kk * OR_MAX + cl);
+                const double2 u1 = *reinterpret_cast<const double2*>(us + kk * OR_MAX + ch);
                 acc[0] = fma(g, u0.x, acc[0]); acc[1] = fma(g, u0.y, acc[1]);
                 acc[2] = fma(g, u1.x, acc[2]); acc[3] = fma(g, u1.y, acc[3]);
             }
@@ -290,8 +333,8 @@ power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const
 #pragma unroll 8
             for (int kk = 0; kk < PS_KC; ++kk) {
                 const double g = Gs0[r * PS_GLD + kk];
-                const double2 u0 = *reinterpret_cast<const double2*>(Us0 + kk * OR_MAX + c4);
-                const double2 u1 = *reinterpret_cast<const double2*>(Us0 + kk * OR_MAX + c4 + 2);
+                const double2 u0 = *reinterpret_cast<const double2*>(Us0 + kk * OR_MAX + cl);
+                const double2 u1 = *reinterpret_cast<const double2*>(Us0 + kk * OR_MAX + ch);
                 acc[0] = fma(g, u0.x, acc[0]); acc[1] = fma(g, u0.y, acc[1]);
                 acc[2] = fma(g, u1.x, acc[2]); acc[3] = fma(g, u1.y, acc[3]);
             }
@@ -303,8 +346,9 @@ power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const
     double* Zs = Us;                                                 // [PS_ROWS][64]
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-        Zs[r * OR_MAX + c4 + t] = acc[t];
-        if (row0 + r < n && c4 + t < p) Z[(row0 + r) * p + c4 + t] = acc[t];
+        const int c = (t < 2 ? cl : ch) + (t & 1);
+        Zs[r * OR_MAX + c] = acc[t];
+        if (row0 + r < n && c < p) Z[(row0 + r) * p + c] = acc[t];
     }
     __syncthreads();
     {
