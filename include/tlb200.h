@@ -244,12 +244,15 @@ int tlb200_mttkrp_from_ttm_partials(const void* t, const int64_t* lead_shape, in
 /* tlb200_cp_update_gram whose right-hand sides are those partials: they are summed (split order) while the LU runs,
  * so the reduction costs neither a launch nor time on the critical path.  m_out (optional, rows x rank) receives the
  * summed MTTKRP; iprod_out (optional device scalar) receives <M, F_new> = sum(M o F_new), the inner-product term of
- * the fast error (tensorly/decomposition/_cp.py:222) — tlb200_cp_error_iprod finishes the error from it.
+ * the fast error (tensorly/decomposition/_cp.py:222) — tlb200_cp_error_iprod finishes the error from it, or, when
+ * `mode` is the LAST mode, this launch does it itself: with err_out (3 scalars, needs iprod_out and norm_x2) the
+ * tail also forms ||cp||^2 from the Gram matrices and writes [rel_error, <M, F>, ||cp||^2] like tlb200_cp_error.
  * Workspace: tlb200_cp_update_gram_workspace_bytes, same zero-ticket convention. */
 int tlb200_cp_update_fused(const void* const* grams, int nmodes, int mode, int64_t rank,
                            const void* weights, double l2_reg, const tlb200_partials_t* m, int dtype,
                            void* out, int64_t out_ld, void* gram_out, void* m_out, int64_t m_out_ld,
-                           void* iprod_out, void* workspace, size_t workspace_bytes, void* stream);
+                           void* iprod_out, const void* norm_x2, void* err_out, void* workspace,
+                           size_t workspace_bytes, void* stream);
 
 int tlb200_cp_error_iprod(const void* const* grams, int nmodes, int64_t rank, const void* weights,
                           const void* iprod, const void* norm_x2, int dtype, void* err_out,

@@ -890,10 +890,12 @@ def subspace_iterate(g: torch.Tensor, u: torch.Tensor, steps: int) -> torch.Tens
 
 def cp_update_fused(grams, mode: int, weights, partials: "PartialMttkrp", l2_reg: float = 0.0, out: torch.Tensor | None = None,
                     gram_out: torch.Tensor | None = None, m_out: torch.Tensor | None = None,
-                    iprod_out: torch.Tensor | None = None) -> torch.Tensor:
+                    iprod_out: torch.Tensor | None = None, norm_x2: torch.Tensor | None = None,
+                    err_out: torch.Tensor | None = None) -> torch.Tensor:
     """cp_update whose right-hand sides are the unsummed partials of mttkrp_partials / mttkrp_from_ttm_partials: one
     launch sums them (split order), solves, forms the Gram matrix of the new factor and — on request — writes the
-    summed MTTKRP (`m_out`) and <M, F_new> (`iprod_out`, a device scalar for cp_error_iprod)."""
+    summed MTTKRP (`m_out`) and <M, F_new> (`iprod_out`, a device scalar for cp_error_iprod).  With `err_out` (and
+    `norm_x2`, `iprod_out`) — for the LAST mode — the same launch finishes the fast reconstruction error like cp_error."""
     rows, rank = partials.shape
     dtype, device = partials.dtype, partials.device
     if out is None:
@@ -911,7 +913,9 @@ def cp_update_fused(grams, mode: int, weights, partials: "PartialMttkrp", l2_reg
                                         ctypes_byref(partials.info), dt, out.data_ptr(), out.stride(0), gram_out.data_ptr(),
                                         m_out.data_ptr() if m_out is not None else None,
                                         m_out.stride(0) if m_out is not None else 0,
-                                        iprod_out.data_ptr() if iprod_out is not None else None, ws.data_ptr(), ws.numel(),
+                                        iprod_out.data_ptr() if iprod_out is not None else None,
+                                        norm_x2.data_ptr() if norm_x2 is not None else None,
+                                        err_out.data_ptr() if err_out is not None else None, ws.data_ptr(), ws.numel(),
                                         _stream(out))
     if st == _lib.TLB200_EUNSUPPORTED:
         raise NotImplementedError("cp_update_fused: <M, F> is only formed on the register-LU path (rank <= 64 fp32 / 32 fp64)")

@@ -233,6 +233,8 @@ class CPALS:
         self.iprod = torch.zeros(1, dtype=dt, device=dev)
         self._mbuf = {}
         self._iprod_fresh = False
+        self._want_error = True       # set per sweep: lets the last mode's solve finish the error in its own tail
+        self._err_done = False
         self._fuse = (update == "ls" and hasattr(self.ops, "cp_update_fused") and tensor_local.is_cuda
                       and os.environ.get("TLB200_FUSED_UPDATE", "1") != "0")
         self._graph = None
@@ -292,8 +294,10 @@ class CPALS:
             else:
                 part = self.ops.mttkrp_partials(self.x, (self._w, self.factors), mode)
             want_ip = last and self.shard_mode != mode
+            fold = want_ip and self._want_error and self.mask is None
             self.ops.cp_update_fused(self.grams, mode, self.weights, part, self.l2_reg, out=self.factors[mode],
-                                     gram_out=self.grams[mode], iprod_out=self.iprod if want_ip else None)
+                                     gram_out=self.grams[mode], iprod_out=self.iprod if want_ip else None,
+                                     norm_x2=self.norm_x2 if fold else None, err_out=self.err if fold else None)
         except NotImplementedError:
             self._fuse = False
             return False
@@ -301,6 +305,7 @@ class CPALS:
             self.comm.all_reduce(self.grams[mode])
         if last:
             self._iprod_fresh = want_ip
+            self._err_done = fold
             self.mttkrp_last = None
         return True
 
@@ -325,14 +330,17 @@ class CPALS:
             else:
                 part = self.ops.mttkrp_partials(self.x, (self._w, self.factors), mode)
             self.comm.all_reduce_partials(part, self.grams[self.shard_mode] if packed else None, buf.reshape(-1))
+            fold = last and self._want_error and self.mask is None
             self.ops.cp_update_fused(self.grams, mode, self.weights, _ops.plain_partials(m), self.l2_reg,
                                      out=self.factors[mode], gram_out=self.grams[mode],
-                                     iprod_out=self.iprod if last else None)
+                                     iprod_out=self.iprod if last else None,
+                                     norm_x2=self.norm_x2 if fold else None, err_out=self.err if fold else None)
         except NotImplementedError:
             self._fuse = False
             return False
         if last:
             self._iprod_fresh = True
+            self._err_done = fold
             self.mttkrp_last = None
         return True
 
@@ -348,6 +356,7 @@ class CPALS:
             return
         if mode == self.ndim - 1:
             self._iprod_fresh = False
+            self._err_done = False
         packed = self._pack is not None and mode == self._pack_mode
         out = self._pack_m if packed else None
         if self._contracted is not None and mode < self.ndim - 1:
@@ -379,6 +388,8 @@ class CPALS:
 
     def _error(self) -> None:
         last = self.ndim - 1
+        if self._err_done:          # the last mode's solve already wrote self.err
+            return
         if self._iprod_fresh:
             self.ops.cp_error_iprod(self.grams, self.weights, self.iprod, self.norm_x2, out=self.err)
             return
@@ -390,6 +401,7 @@ class CPALS:
             self.err[0] = torch.sqrt(torch.abs(nx2 + self.err[2] - 2 * self.err[1])) / torch.sqrt(nx2)
 
     def sweep_eager(self, with_error: bool = True) -> None:
+        self._want_error, self._err_done = bool(with_error), False
         if self.dimtree:
             self._contracted = self.ops.mode_dot(self.x, self.factors[-1], self.ndim - 1, transpose=True)
         for mode in self.modes:
@@ -403,7 +415,7 @@ class CPALS:
         if with_error:
             if self.modes[-1] != self.ndim - 1:
                 # the fast error needs the last mode's MTTKRP with the current factors
-                self._iprod_fresh = False
+                self._iprod_fresh = self._err_done = False
                 self.mttkrp_last = self.ops.mttkrp(self.x, (self._w, self.factors), self.ndim - 1)
                 if self.shard_mode is not None and self.shard_mode != self.ndim - 1:
                     self.comm.all_reduce(self.mttkrp_last)

@@ -175,6 +175,11 @@ struct MSource {
     int64_t m_out_ld;
     double* iprod_partial;   // optional [gridDim.x]: per-CTA sum of M o F_new (the <X, model> term of the fast error)
     T* iprod_out;            // device scalar receiving the ordered sum of the above
+    // optional: finish the fast reconstruction error (tensorly/decomposition/_cp.py:217-225) in the tail of this
+    // launch — err_out = [sqrt(|norm_x2 + ||cp||^2 - 2 <M, F>|) / sqrt(norm_x2), <M, F>, ||cp||^2] — for the LAST mode
+    T* err_out;
+    const T* norm_x2;
+    double* ncp_partial;     // [gridDim.x]
 };
 
 template <typename T>
@@ -225,8 +230,38 @@ __device__ __forceinline__ void iprod_finish(const MSource<T>& ms) {      // one
 }
 
 template <typename T>
-__device__ __forceinline__ void gram_tail(const GramTail<T>& gt, const MSource<T>& ms, const T* Y, int ld, int R, int nrows) {
+__device__ __forceinline__ void error_finish(const MSource<T>& ms) {      // one warp of the CTA that finishes last
+    if (threadIdx.x >= 32) return;
+    double t = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += 32) t += __ldcg(ms.ncp_partial + b);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) {
+        const double ip = (double)__ldcg(ms.iprod_out), nx2 = (double)ms.norm_x2[0];
+        double d = nx2 + t - 2.0 * ip;
+        d = d < 0 ? -d : d;
+        ms.err_out[0] = (T)(sqrt(d) / sqrt(nx2));
+        ms.err_out[1] = (T)ip;
+        ms.err_out[2] = (T)t;
+    }
+}
+
+// entry e = (r, s) of w_r w_s prod_{i != mode} G_i[r, s], times the freshly summed Gram entry of `mode`
+template <typename T>
+__device__ __forceinline__ double ncp_term(const GramList<T>& gl, int mode, const T* __restrict__ w, int R, int e, T g_new) {
+    T v = T(1);
+    for (int i = 0; i < gl.n; ++i)
+        if (i != mode) v = v * gl.g[i][e];
+    v = v * g_new;
+    if (w) { const int r = e / R, s2 = e - r * R; v = v * (w[r] * w[s2]); }
+    return (double)v;
+}
+
+template <typename T>
+__device__ __forceinline__ void gram_tail(const GramTail<T>& gt, const MSource<T>& ms, const GramList<T>& gl, int mode,
+                                          const T* __restrict__ w, const T* Y, int ld, int R, int nrows) {
     if (gt.partial == nullptr) return;
+    __shared__ double ncp_red[8];
     __shared__ int s_last;
     const int tid = threadIdx.x;
     T* mine = gt.partial + (size_t)blockIdx.x * R * R;
@@ -250,20 +285,60 @@ __device__ __forceinline__ void gram_tail(const GramTail<T>& gt, const MSource<T
         __threadfence();
         const int per = (R * R + (int)gridDim.x - 1) / (int)gridDim.x;
         const int e0 = (int)blockIdx.x * per, e1 = min(R * R, e0 + per);
-        for (int e = e0 + tid; e < e1; e += blockDim.x)
-            gt.gram[e] = ordered_sum_strided<T>(gt.partial + e, (int)gridDim.x, (size_t)R * R);
+        double ncp = 0.0;
+        for (int e = e0 + tid; e < e1; e += blockDim.x) {
+            const T g = ordered_sum_strided<T>(gt.partial + e, (int)gridDim.x, (size_t)R * R);
+            gt.gram[e] = g;
+            if (ms.err_out != nullptr) ncp += ncp_term<T>(gl, mode, w, R, e, g);
+        }
         if (ms.iprod_out != nullptr && blockIdx.x == 0) iprod_finish<T>(ms);
+        if (ms.err_out != nullptr) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ncp += __shfl_xor_sync(0xffffffffu, ncp, o);
+            if ((tid & 31) == 0) ncp_red[tid >> 5] = ncp;
+            __syncthreads();
+            if (tid == 0) {
+                double t = 0.0;
+                for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += ncp_red[i];
+                ms.ncp_partial[blockIdx.x] = t;
+            }
+        }
+        __threadfence();
         __syncthreads();
-        if (tid == 0 && atomicAdd(gt.counter + 1, 1u) == gridDim.x - 1) { gt.counter[0] = 0u; gt.counter[1] = 0u; }
+        if (tid == 0) s_last = atomicAdd(gt.counter + 1, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            if (ms.err_out != nullptr) error_finish<T>(ms);
+            if (tid == 0) { gt.counter[0] = 0u; gt.counter[1] = 0u; }
+        }
         return;
     }
     if (tid == 0) s_last = atomicAdd(gt.counter, 1u) == gridDim.x - 1;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int e = tid; e < R * R; e += blockDim.x)
-        gt.gram[e] = ordered_sum_strided<T>(gt.partial + e, (int)gridDim.x, (size_t)R * R);
+    double ncp = 0.0;
+    for (int e = tid; e < R * R; e += blockDim.x) {
+        const T g = ordered_sum_strided<T>(gt.partial + e, (int)gridDim.x, (size_t)R * R);
+        gt.gram[e] = g;
+        if (ms.err_out != nullptr) ncp += ncp_term<T>(gl, mode, w, R, e, g);
+    }
     if (ms.iprod_out != nullptr) iprod_finish<T>(ms);
+    if (ms.err_out != nullptr) {          // this CTA is alone here: its sum is the whole ||cp||^2
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ncp += __shfl_xor_sync(0xffffffffu, ncp, o);
+        if ((tid & 31) == 0) ncp_red[tid >> 5] = ncp;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += ncp_red[i];
+            for (unsigned b = 0; b < gridDim.x; ++b) ms.ncp_partial[b] = b == 0 ? t : 0.0;
+        }
+        __threadfence();
+        __syncthreads();
+        error_finish<T>(ms);
+    }
     if (tid == 0) *gt.counter = 0u;
 }
 
@@ -534,7 +609,7 @@ __device__ __forceinline__ void solve_fast(unsigned char* raw, const GramList<T>
         if (gr < rows) out[gr * out_ld + c] = sm.Y[r2 * ld + c];
     }
     CP_TRACE(6);
-    gram_tail<T>(gtail, ms, sm.Y, ld, R, (int)min((int64_t)kRows, rows - row0));
+    gram_tail<T>(gtail, ms, gl, mode, w, sm.Y, ld, R, (int)min((int64_t)kRows, rows - row0));
 }
 
 template <typename T>
@@ -604,7 +679,7 @@ cp_update_kernel(GramList<T> gl, int mode, int R, const T* __restrict__ w, T l2,
         if (gr < rows) out[gr * out_ld + c] = Y[r2 * ld + c];
     }
     CP_TRACE(6);
-    gram_tail<T>(gtail, ms, Y, ld, R, (int)min((int64_t)kSolveRows, rows - row0));
+    gram_tail<T>(gtail, ms, gl, mode, w, Y, ld, R, (int)min((int64_t)kSolveRows, rows - row0));
 }
 
 // ---- NN-CP multiplicative update -------------------------------------------------------
@@ -825,11 +900,13 @@ int cp_update_launch(const void* const* grams, int nmodes, int mode, int64_t R, 
     if (gram_out != nullptr) {      // workspace: [ticket counters, 256 bytes][nblk][R*R][nblk doubles: <M, F> terms]
         gt.counter = static_cast<unsigned*>(workspace);
         gt.partial = reinterpret_cast<T*>(static_cast<char*>(workspace) + 256);
-        ms.iprod_partial = ms.iprod_out ? reinterpret_cast<double*>(static_cast<char*>(workspace) + 256 +
-                                                                    align_up((size_t)nblk * R * R * sizeof(T), 256)) : nullptr;
+        double* scal = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256 + align_up((size_t)nblk * R * R * sizeof(T), 256));
+        ms.iprod_partial = ms.iprod_out ? scal : nullptr;
+        ms.ncp_partial = ms.err_out ? scal + nblk : nullptr;
     } else {
-        ms.iprod_partial = nullptr; ms.iprod_out = nullptr;
+        ms.iprod_partial = nullptr; ms.iprod_out = nullptr; ms.err_out = nullptr; ms.ncp_partial = nullptr;
     }
+    if (ms.err_out != nullptr && (ms.iprod_out == nullptr || ms.norm_x2 == nullptr)) return TLB200_EINVAL;
     if (ms.iprod_out != nullptr && !fast) return TLB200_EUNSUPPORTED;      // only the register-LU path forms <M, F>
     cp_update_kernel<T><<<nblk, kSolveThreads, smem, stream>>>(gl, mode, (int)R, w, (T)l2, ms, rows, out, out_ld, gt);
     TLB_CHECK_LAUNCH();
@@ -878,6 +955,7 @@ static MSource<T> plain_source(const void* m, int64_t m_ld) {
     MSource<T> ms;
     ms.m = static_cast<const T*>(m); ms.ld = m_ld; ms.splits = 1; ms.split_stride = 0;
     ms.m_out = nullptr; ms.m_out_ld = 0; ms.iprod_partial = nullptr; ms.iprod_out = nullptr;
+    ms.err_out = nullptr; ms.norm_x2 = nullptr; ms.ncp_partial = nullptr;
     return ms;
 }
 
@@ -899,7 +977,7 @@ extern "C" int tlb200_cp_update(const void* const* grams, int nmodes, int mode, 
 extern "C" size_t tlb200_cp_update_gram_workspace_bytes(int64_t rows, int64_t rank, int dtype) {
     if (rows < 0 || rank < 1 || !dtype_valid(dtype)) return 0;
     const size_t nblk = (size_t)ceil_div(rows > 0 ? rows : 1, kFastRows);
-    return 256 + align_up(nblk * rank * rank * dtype_size(dtype), 256) + align_up(nblk * sizeof(double), 256);
+    return 256 + align_up(nblk * rank * rank * dtype_size(dtype), 256) + align_up(2 * nblk * sizeof(double), 256);
 }
 
 extern "C" int tlb200_cp_update_gram(const void* const* grams, int nmodes, int mode, int64_t rank, const void* weights,
@@ -922,8 +1000,8 @@ extern "C" int tlb200_cp_update_gram(const void* const* grams, int nmodes, int m
 // they are loaded), plus optionally the summed MTTKRP itself (m_out) and <M, F_new> (iprod_out, one device scalar).
 extern "C" int tlb200_cp_update_fused(const void* const* grams, int nmodes, int mode, int64_t rank, const void* weights,
                                       double l2_reg, const tlb200_partials_t* m, int dtype, void* out, int64_t out_ld,
-                                      void* gram_out, void* m_out, int64_t m_out_ld, void* iprod_out, void* workspace,
-                                      size_t workspace_bytes, void* stream) {
+                                      void* gram_out, void* m_out, int64_t m_out_ld, void* iprod_out, const void* norm_x2,
+                                      void* err_out, void* workspace, size_t workspace_bytes, void* stream) {
     if (!m || !m->data || !out || !gram_out || !workspace || rank < 1 || rank > kMaxRank || m->rows < 1 || mode < 0 ||
         mode >= nmodes || m->ld < rank || out_ld < rank || m->splits < 1 || !dtype_valid(dtype) ||
         (m_out && m_out_ld < rank))
@@ -937,6 +1015,7 @@ extern "C" int tlb200_cp_update_fused(const void* const* grams, int nmodes, int 
         ms.m = static_cast<const T*>(m->data); ms.ld = m->ld; ms.splits = (int)m->splits; ms.split_stride = m->split_stride;
         ms.m_out = static_cast<T*>(m_out); ms.m_out_ld = m_out_ld;
         ms.iprod_partial = nullptr; ms.iprod_out = static_cast<T*>(iprod_out);
+        ms.err_out = static_cast<T*>(err_out); ms.norm_x2 = static_cast<const T*>(norm_x2); ms.ncp_partial = nullptr;
         return cp_update_launch<T>(grams, nmodes, mode, rank, static_cast<const T*>(weights), l2_reg, ms, m->rows,
                                    static_cast<T*>(out), out_ld, static_cast<T*>(gram_out), workspace, s);
     };

@@ -1080,6 +1080,16 @@ def test_fused_update_equals_unfused(shape, rank, dtype):
             e1 = host(tb._ops.cp_error_iprod(new_grams, w, ip, nx2))
             e2 = host(tb.cp_error(new_grams, w, m_out, f_new, nx2))
             assert abs(e1[2] - e2[2]) <= tol * abs(e2[2]) and abs(e1[1] - e2[1]) <= 10 * tol * abs(e2[1])
+            if mode == len(shape) - 1:
+                # the same launch can finish the error itself (last mode): identical inputs, same three scalars
+                part = tb._ops.mttkrp_partials(x, (None, fs), mode)
+                e3 = torch.zeros(3, dtype=x.dtype, device="cuda")
+                g3 = torch.empty_like(g_new)
+                ip3 = torch.zeros_like(ip)
+                tb._ops.cp_update_fused(grams, mode, w, part, gram_out=g3, iprod_out=ip3, norm_x2=nx2, err_out=e3)
+                e3 = host(e3)
+                assert abs(e3[1] - e1[1]) <= 1e-6 * abs(e1[1]) and abs(e3[2] - e1[2]) <= 1e-6 * abs(e1[2])
+                assert abs(e3[0] - e1[0]) <= 1e-5 * max(abs(e1[0]), 1e-3)
 
 
 def test_fused_sweep_same_trajectory_as_unfused(monkeypatch):
