@@ -270,6 +270,18 @@ int tlb200_cp_error(const void* const* grams, int nmodes, int64_t rank,
                     int64_t rows, const void* norm_x2, int dtype, void* err_out,
                     void* stream);
 
+/* Range hint for the fp16-split tensor-core engine.  The 3xTF32 engine needs only the data; its fp16 sibling (half
+ * the tensor-core instructions and operand traffic per tensor byte — what rank 33..64 is bound by under the power
+ * cap) computes on x * 2^k with max |x| mapped into fp16 range, so it needs max |x|.  tlb200_tensor_absmax writes it
+ * to a device float (fp32 tensors only; one HBM pass, no host sync); tlb200_hint_tensor_absmax registers that device
+ * scalar for the tensor whose base pointer is `x` (NULL withdraws the hint).  While a hint is registered,
+ * tlb200_mttkrp / tlb200_mttkrp_partials / tlb200_mode_dot calls on that pointer take the fp16 engine (same
+ * results to ~1e-6: every element keeps 22 significant bits relative to max |x|; elements below 2^-28 max |x| keep
+ * absolute accuracy 2^-50 max |x|).  The caller promises the scalar stays valid and >= max |x| for as long as the
+ * hint is registered (the ALS drivers: the tensor is constant over a decomposition).  No reference counterpart. */
+int tlb200_tensor_absmax(const void* x, int64_t n, int dtype, void* absmax_out, void* stream);
+int tlb200_hint_tensor_absmax(const void* x, const void* absmax_device);
+
 /* Sum of squares of a contiguous array (||X||^2) into a device scalar of `dtype`
  * (accumulated in double).  Replaces tl.norm(tensor, 2)**2 at _cp.py:350. */
 size_t tlb200_sumsq_workspace_bytes(int64_t n, int dtype);

@@ -111,6 +111,8 @@ SIGNATURES = {
                                        c_size_t, c_int, POINTER(Partials), c_void_p]),
     "tlb200_mttkrp_from_ttm_partials": (c_int, [c_void_p, _I64P, c_int, c_int, _VPP, _I64P, _I64P, c_int64, c_void_p, c_int,
                                                 c_void_p, c_size_t, POINTER(Partials), c_void_p]),
+    "tlb200_tensor_absmax": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "tlb200_hint_tensor_absmax": (c_int, [c_void_p, c_void_p]),
     "tlb200_cp_update_fused": (c_int, [_VPP, c_int, c_int, c_int64, c_void_p, c_double, POINTER(Partials), c_int, c_void_p,
                                        c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                        c_void_p]),

@@ -11,6 +11,7 @@ Inputs are borrowed and never mutated; results are new tensors.
 """
 from __future__ import annotations
 
+import os
 import warnings
 from typing import Iterable, Sequence
 
@@ -574,6 +575,58 @@ def sumsq(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         st = lib.tlb200_sumsq(xc.data_ptr(), xc.numel(), dt, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(x))
     _lib.check(st, "sumsq")
     return out
+
+
+def tensor_absmax(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """max |x| as a device float (fp32 tensors; one pass, no host sync) — the range hint of the fp16-split engine."""
+    _check_tensor(x, "x")
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise NotImplementedError("tensor_absmax takes contiguous float32 tensors")
+    if out is None:
+        out = torch.empty(1, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    with _Device(x):
+        st = lib.tlb200_tensor_absmax(x.data_ptr(), x.numel(), _DTYPES[x.dtype], out.data_ptr(), _stream(x))
+    _lib.check(st, "tensor_absmax")
+    return out
+
+
+class RangeHint:
+    """Registers max |x| of a tensor for as long as this object lives: MTTKRP / mode_dot calls on that tensor (same
+    base pointer) then run on the fp16-split tensor-core engine instead of 3xTF32 (include/tlb200.h,
+    tlb200_hint_tensor_absmax).  The owner promises not to change the tensor while the hint is registered — the
+    ALS drivers hold one for their (constant) input tensor.  `TLB200_DISABLE_HF=1` turns the engine off."""
+
+    _live: dict = {}            # base pointer -> id of the RangeHint that registered it last
+
+    def __init__(self, x: torch.Tensor):
+        self.ptr = None
+        self.absmax = tensor_absmax(x)
+        self._x = x                       # keeps the storage (and therefore the pointer's meaning) alive
+        _lib.check(_lib.load().tlb200_hint_tensor_absmax(x.data_ptr(), self.absmax.data_ptr()), "hint_tensor_absmax")
+        self.ptr = x.data_ptr()
+        RangeHint._live[self.ptr] = id(self)
+
+    @staticmethod
+    def applies(x: torch.Tensor, rank: int) -> bool:
+        """The hint pays where the tf32 engine is tensor-pipe / power bound: fp32, rank above 32 (measured)."""
+        lo = int(os.environ.get("TLB200_HF_MIN_RANK", "33"))
+        return (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and rank >= lo
+                and os.environ.get("TLB200_DISABLE_HF", "0") in ("", "0"))
+
+    def close(self) -> None:
+        if self.ptr is not None:
+            try:
+                if RangeHint._live.get(self.ptr) == id(self):      # a later hint for the same tensor stays
+                    del RangeHint._live[self.ptr]
+                    _lib.load().tlb200_hint_tensor_absmax(self.ptr, None)
+            except Exception:           # interpreter shutdown
+                pass
+            self.ptr = None
+            self._x = None
+
+    def __del__(self):
+        self.close()
 
 
 def gram(f: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:

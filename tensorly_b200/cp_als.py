@@ -79,6 +79,7 @@ class CudaOps:
     mttkrp_from_ttm_partials = staticmethod(_ops.mttkrp_from_ttm_partials)
     cp_update_fused = staticmethod(_ops.cp_update_fused)
     cp_error_iprod = staticmethod(_ops.cp_error_iprod)
+    range_hint = staticmethod(_ops.RangeHint)
     nncp_update = staticmethod(_ops.nncp_update)
     hals_update = staticmethod(_ops.hals_update)   # the whole HALS inner iteration of one mode in one kernel
     cp_error = staticmethod(_ops.cp_error)
@@ -233,6 +234,12 @@ class CPALS:
         self.iprod = torch.zeros(1, dtype=dt, device=dev)
         self._mbuf = {}
         self._iprod_fresh = False
+        # The tensor is constant over the decomposition (no mask): its max |x| is found once and registered, which lets
+        # the rank-33..64 tensor passes run on the fp16-split engine (half the tensor-core work per byte).
+        self._range_hint = None
+        if (self.mask is None and hasattr(self.ops, "range_hint") and tensor_local.is_cuda
+                and _ops.RangeHint.applies(tensor_local, self.rank)):
+            self._range_hint = self.ops.range_hint(tensor_local)
         self._want_error = True       # set per sweep: lets the last mode's solve finish the error in its own tail
         self._err_done = False
         self._fuse = (update == "ls" and hasattr(self.ops, "cp_update_fused") and tensor_local.is_cuda

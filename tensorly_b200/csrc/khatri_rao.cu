@@ -5,6 +5,7 @@
 // reassociated).  Output-bandwidth bound: each output element is written once, inputs
 // are tiny and L2-resident.
 #include "common.cuh"
+#include "hf_split.cuh"
 
 namespace tlb200 {
 namespace {
@@ -165,7 +166,73 @@ khatri_rao_t_kernel(KrArgs<T> a, int64_t total_rows, int64_t rows_padded, int64_
     }
 }
 
+// fp16-split variant for the tensor-core engine's fp16 sibling: one CTA per column c finds the column's own
+// power-of-two scale (pass 1: max |v|), then writes hi / lo halves (pass 2).  The products are formed twice — the
+// table is tiny next to the tensor pass it feeds.
+__global__ void __launch_bounds__(256)
+khatri_rao_t_f16_kernel(KrArgs<float> a, int64_t total_rows, int64_t rows_padded, int64_t rank,
+                        const float* __restrict__ weights, __half* __restrict__ hi, __half* __restrict__ lo,
+                        float* __restrict__ col_inv) {
+    const int64_t c = blockIdx.x;
+    auto value = [&](int64_t row) {
+        int64_t rem = row;
+        float v = 1.f;
+        bool first = true;
+        // factor 0 is the slowest index: peel from the last matrix; multiply in the reference's order (0, 1, ...)
+        int64_t idx[TLB200_MAX_NDIM];
+#pragma unroll
+        for (int i = TLB200_MAX_NDIM - 1; i >= 0; --i) {
+            if (i < a.nmats) {
+                const int64_t q = rem / a.rows[i];
+                idx[i] = rem - q * a.rows[i];
+                rem = q;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < TLB200_MAX_NDIM; ++i) {
+            if (i < a.nmats) {
+                const float f = a.mat[i][idx[i] * a.rs[i] + c * a.cs[i]];
+                if (first) { v = weights ? mul_rn(f, weights[c]) : f; first = false; }
+                else v = mul_rn(v, f);
+            }
+        }
+        return v;
+    };
+    unsigned mx = 0;
+    if (c < rank)
+        for (int64_t row = threadIdx.x; row < total_rows; row += 256) mx = max(mx, __float_as_uint(fabsf(value(row))));
+    float inv;
+    const float sc = hf_block_scale(mx, &inv);
+    if (threadIdx.x == 0) col_inv[c] = inv;
+    for (int64_t row = threadIdx.x; row < rows_padded; row += 256) {
+        const float v = (c < rank && row < total_rows) ? value(row) * sc : 0.f;
+        __half h, l;
+        hf_split1(v, h, l);
+        hi[c * rows_padded + row] = h;
+        lo[c * rows_padded + row] = l;
+    }
+}
+
 }  // namespace
+
+int launch_khatri_rao_t_f16(const float* const* mats, const int64_t* rows, const int64_t* row_stride,
+                            const int64_t* col_stride, int nmats, int64_t rank, const float* weights, __half* hi,
+                            __half* lo, int64_t rows_padded, int64_t pad_cols, float* col_inv, cudaStream_t stream) {
+    if (nmats < 1 || nmats > TLB200_MAX_NDIM || rank < 0 || pad_cols < rank) return TLB200_EINVAL;
+    KrArgs<float> a;
+    a.nmats = nmats;
+    int64_t total = 1;
+    for (int i = 0; i < nmats; ++i) {
+        a.mat[i] = mats[i]; a.rows[i] = rows[i]; a.rs[i] = row_stride[i]; a.cs[i] = col_stride[i];
+        total *= rows[i];
+    }
+    for (int i = nmats; i < TLB200_MAX_NDIM; ++i) { a.mat[i] = nullptr; a.rows[i] = 1; a.rs[i] = 0; a.cs[i] = 0; }
+    if (rows_padded < total) return TLB200_EINVAL;
+    if (rows_padded == 0 || pad_cols == 0) return TLB200_OK;
+    khatri_rao_t_f16_kernel<<<(unsigned)pad_cols, 256, 0, stream>>>(a, total, rows_padded, rank, weights, hi, lo, col_inv);
+    TLB_CHECK_LAUNCH();
+    return TLB200_OK;
+}
 
 template <typename T>
 int launch_khatri_rao_t(const T* const* mats, const int64_t* rows, const int64_t* row_stride, const int64_t* col_stride,

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "stream_gemm.cuh"
 #include "mttkrp_tc.cuh"
+#include "hf_split.cuh"
 
 namespace tlb200 {
 
@@ -146,7 +147,22 @@ static int run(const T* x, const int64_t* shape, int ndim, int mode, const T* co
             w = nullptr;  // weights go to the first non-skipped factor only
         }
     }
-    if (pl.path == TLB200_PATH_TCGEN05) {
+    // a registered range hint (tlb200_hint_tensor_absmax) selects the fp16-split engine
+    const float* x_absmax = nullptr;
+    if constexpr (sizeof(T) == 4) {
+        if (pl.path == TLB200_PATH_TCGEN05 && mttkrp_tc_hf_ok(pl)) x_absmax = tc_range_hint(x);
+    }
+    if (x_absmax != nullptr) {
+        // Q transposed as fp16 hi / lo tables [rank_padded][Bpad] with one power-of-two scale per column, then the
+        // inverse scales [rank_padded] — all inside the region sized for the fp32 tables
+        const int64_t bpad = ceil_div(pl.B, 64) * 64;
+        __half* qhi = reinterpret_cast<__half*>(Q);
+        float* col_inv = reinterpret_cast<float*>(Q) + pl.rank_padded * bpad;
+        st = launch_khatri_rao_t_f16(reinterpret_cast<const float* const*>(factors) + pl.q_first, shape + pl.q_first,
+                                     frs + pl.q_first, fcs + pl.q_first, pl.q_count, rank,
+                                     reinterpret_cast<const float*>(w), qhi, qhi + pl.rank_padded * bpad, bpad,
+                                     pl.rank_padded, col_inv, stream);
+    } else if (pl.path == TLB200_PATH_TCGEN05) {
         // the tensor-core engine takes Q transposed ([rank_padded][Bpad], K-major rows, zero padded) and already
         // split into tf32 hi / lo tables, which TMA streams straight into the B-operand ring
         const int64_t bpad = ceil_div(pl.B, 64) * 64;
@@ -162,10 +178,10 @@ static int run(const T* x, const int64_t* shape, int ndim, int mode, const T* co
     if (st) return st;
 
     if (pl.path == TLB200_PATH_TCGEN05) {
-        set_last_path("tcgen05");
+        set_last_path(x_absmax ? "tcgen05-f16" : "tcgen05");
         st = mttkrp_tc_launch(reinterpret_cast<const float*>(x), pl, rank, reinterpret_cast<const float*>(P),
                               reinterpret_cast<const float*>(Q), reinterpret_cast<float*>(partial),
-                              ws.base + ws.used(), stream);
+                              ws.base + ws.used(), stream, x_absmax);
         if (st) return st;
     } else {
         set_last_path("simt");

@@ -11,6 +11,8 @@
 #include "mttkrp_tc.cuh"
 #include "tc_stream.cuh"
 
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 
 namespace tlb200 {
@@ -30,6 +32,8 @@ bool mttkrp_tc_supported(const tlb200_mttkrp_plan_t& pl, int64_t rank, int dtype
     if (pl.A * ceil_div(pl.B, 64) < 8 || pl.J < 32) return false;
     return tc_available();
 }
+
+bool mttkrp_tc_hf_ok(const tlb200_mttkrp_plan_t& pl) { return layout_for(pl) != TC_X_KMAJOR_1; }
 
 // chunks of the inner Khatri-Rao table one work item keeps resident in shared memory
 static int block_chunks(const tlb200_mttkrp_plan_t& pl, int64_t rank_padded) {
@@ -73,9 +77,10 @@ void mttkrp_tc_fill_plan(tlb200_mttkrp_plan_t* pl, int64_t rank) {
 size_t mttkrp_tc_extra_workspace(const tlb200_mttkrp_plan_t&) { return 0; }
 
 int mttkrp_tc_launch(const float* x, const tlb200_mttkrp_plan_t& pl, int64_t /*rank*/, const float* P, const float* Q,
-                     float* partial, void* /*extra_ws*/, cudaStream_t stream) {
+                     float* partial, void* /*extra_ws*/, cudaStream_t stream, const float* x_absmax) {
     if (reinterpret_cast<uintptr_t>(x) % 16) return TLB200_EUNSUPPORTED;
     TcStreamLaunch l;
+    l.hf = x_absmax != nullptr;
     l.rp = (int)pl.rank_padded;
     l.x_layout = layout_for(pl);
     l.b_mode = TC_B_MAT;
@@ -100,8 +105,16 @@ int mttkrp_tc_launch(const float* x, const tlb200_mttkrp_plan_t& pl, int64_t /*r
         st = tc_encode_map(&l.x_map, x, 3, dims, strides, box, false);
     }
     if (st) return st;
-    {   // Q^T hi / lo tables [rank_padded][ldq]: one unit = box of 32 contraction elements x all rows, swizzled
-        const uint64_t ldq = (uint64_t)ceil_div(pl.B, 64) * 64;
+    const uint64_t ldq = (uint64_t)ceil_div(pl.B, 64) * 64;
+    if (l.hf) {   // fp16 tables: one slot = box of 64 contraction elements (128 bytes) x all rows
+        uint64_t qd[2] = {ldq, (uint64_t)pl.rank_padded}, qs[1] = {ldq * 2};
+        uint32_t qb[2] = {64, (uint32_t)pl.rank_padded};
+        const __half* qh = reinterpret_cast<const __half*>(Q);
+        st = tc_encode_map(&l.bhi_map, qh, 2, qd, qs, qb, true, true);
+        if (st) return st;
+        st = tc_encode_map(&l.blo_map, qh + pl.rank_padded * ldq, 2, qd, qs, qb, true, true);
+        if (st) return st;
+    } else {   // Q^T hi / lo tables [rank_padded][ldq]: one unit = box of 32 contraction elements x all rows, swizzled
         uint64_t qd[2] = {ldq, (uint64_t)pl.rank_padded}, qs[1] = {ldq * 4};
         uint32_t qb[2] = {32, (uint32_t)pl.rank_padded};
         st = tc_encode_map(&l.bhi_map, Q, 2, qd, qs, qb, true);
@@ -121,6 +134,8 @@ int mttkrp_tc_launch(const float* x, const tlb200_mttkrp_plan_t& pl, int64_t /*r
     p.a_per_range = ceil_div(pl.A, p.k_ranges);
     p.b_resident = 1;
     p.group_units = tc_group_units();
+    p.x_absmax = x_absmax;
+    p.col_inv = l.hf ? Q + pl.rank_padded * ldq : nullptr;
     p.P = P;     // outer Khatri-Rao table: applied per `a` by the epilogue
     p.out = partial;
     p.sOk = pl.J * pl.rank_padded; p.sOm = pl.rank_padded; p.sOn = 1;

@@ -49,6 +49,8 @@
 //                no Khatri-Rao tile is ever formed — not even in shared memory.
 #include "tc_stream.cuh"
 
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 
 namespace tlb200 {
@@ -131,6 +133,17 @@ __device__ __forceinline__ void mma_ts_tf32_acc(uint32_t d_tmem, uint32_t a_tmem
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
                  ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc) : "memory");
 }
+// kind::f16 (fp16 operands, fp32 accumulate), A from TMEM: K = 16 per instruction at the cost of a K = 8 tf32 one
+__device__ __forceinline__ void mma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_ts_f16_acc(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
@@ -160,6 +173,32 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f16 with fp16 A and B, fp32 accumulate
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// the power-of-two scale that maps |x| <= absmax into [2^14, 2^15) (fp16 range), and its inverse
+__device__ __forceinline__ float hf_scale(const float* __restrict__ absmax, float* inv) {
+    const int e = (int)((__float_as_uint(__ldg(absmax)) >> 23) & 0xFFu);
+    int se = 268 - e;                       // biased exponent of 2^(14 - (e - 127))
+    se = se < 1 ? 1 : (se > 253 ? 253 : se);
+    *inv = __uint_as_float((uint32_t)(254 - se) << 23);
+    return __uint_as_float((uint32_t)se << 23);
+}
+// fp16 split of two scaled values: hi = RN_fp16(x), lo = RN_fp16((x - hi) * 2^11); x0 goes to the low half (even k)
+__device__ __forceinline__ void hf_split2(float x0, float x1, uint32_t& hi2, uint32_t& lo2) {
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(x1), "f"(x0));
+    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
+    const float l0 = (x0 - h.x) * 2048.f, l1 = (x1 - h.y) * 2048.f;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(l1), "f"(l0));
+}
+
+#define TLB_TMEM_ST16(taddr, r)                                                                                          \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                                        \
+                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"                                             \
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),  \
+                 "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])                                \
+                 : "memory")
 #define TLB_TMEM_LD32(taddr, r)                                                                                          \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                             \
                  "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
@@ -216,15 +255,19 @@ __device__ __forceinline__ TcItem tc_item(const TcStreamParams& p, int64_t it) {
 }
 
 // ---- compile-time configuration per (RP, X layout) -------------------------------------
-template <int RP, int XL>
+// HF: the fp16-split engine (range hint present) — half the MMA instructions and TMEM/shared-memory operand traffic
+// of the tf32 one.  A units are [hi 16 | lo 16] columns of packed halves; a B slot holds 64 contraction elements
+// (one whole X tile) per 128-byte row, so the K-step arithmetic on the B descriptor is the tf32 engine's.
+template <int RP, int XL, bool HF>
 struct Cfg {
     static constexpr int KS = XL == TC_X_KMAJOR_1 ? 32 : 64;        // K extent of one X stage
     static constexpr int KO = KS / 32;                              // 32-element units per X stage
     static constexpr int X_STAGE = TM * KS * 4;
     static constexpr int XS = KS == 32 ? 8 : 4;                     // bytes in flight per SM hide HBM latency
     static constexpr int D_COLS = 2 * RP;                           // per accumulator set: [hi*hi (RP) | hi*lo + lo*hi (RP)]
-    static constexpr int A_COLS = 64;                               // TMEM columns per A unit: [hi 32 | lo 32]
-    static constexpr int AS = RP == 32 ? 6 : 4;
+    static constexpr int BKO = HF ? 1 : KO;                         // B slots per X tile
+    static constexpr int A_COLS = HF ? 32 : 64;                     // TMEM columns per A unit: [hi 32 | lo 32] (HF: packed halves)
+    static constexpr int AS = HF ? 8 : (RP == 32 ? 6 : 4);
     static constexpr int B_UNIT = 2 * RP * 128;                     // [hi RP rows | lo RP rows] x 128 B, K-major SW128
     static constexpr int BS = RP == 32 ? 8 : 6;                     // B-operand slots (32-element units): 64 / 96 KB, a ring
                                                                     // (streamed B) or one resident b block per item
@@ -239,17 +282,18 @@ struct Cfg {
     // the two convert sets take alternate tiles: with an even ring every stage always belongs to the same set,
     // so a set observes every phase of the barriers it waits on (an odd ring would alias phase parities)
     static_assert(XS % 2 == 0, "X ring must be even");
-    static_assert(BS % KO == 0, "B ring must hold whole tiles");
+    static_assert(BS % BKO == 0, "B ring must hold whole tiles");
+    static_assert(!HF || KS == 64, "the fp16 engine takes 64-element tiles only");
     static_assert(SMEM + 1024 <= 227 * 1024, "smem budget");
 };
 
-template <int RP, int XL, int BM>
+template <int RP, int XL, bool HF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap bhi_map,
                  const __grid_constant__ CUtensorMap blo_map, const TcStreamParams p) {
-    using C = Cfg<RP, XL>;
-    constexpr int KS = C::KS, KO = C::KO, XS = C::XS, AS = C::AS, BS = C::BS;
-    constexpr bool kUnitRelease = RP == 64 && KO == 2;     // A-ring slots are handed back unit by unit
+    using C = Cfg<RP, XL, HF>;
+    constexpr int KS = C::KS, KO = C::KO, XS = C::XS, AS = C::AS, BS = C::BS, BKO = C::BKO;
+    constexpr bool kUnitRelease = RP == 64 && KO == 2 && !HF;     // A-ring slots are handed back unit by unit
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* x_smem = smem + C::OFF_X;
@@ -329,8 +373,8 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             const int mw = warp == 1 ? 0 : 1;       // this issuer takes tiles with (global tile index & 1) == mw
             uint32_t gt = 0;                        // global tile index (per CTA)
             uint32_t own = 0;                       // tiles issued by this warp so far
-            constexpr uint32_t idesc1 = idesc_tf32(TM, 2 * RP);   // A_hi x [B_hi | B_lo] -> columns [0, 2RP)
-            constexpr uint32_t idesc2 = idesc_tf32(TM, RP);       // A_lo x B_hi          -> columns [RP, 2RP)
+            constexpr uint32_t idesc1 = HF ? idesc_f16(TM, 2 * RP) : idesc_tf32(TM, 2 * RP);   // A_hi x [B_hi | B_lo] -> columns [0, 2RP)
+            constexpr uint32_t idesc2 = HF ? idesc_f16(TM, RP) : idesc_tf32(TM, RP);           // A_lo x B_hi          -> columns [RP, 2RP)
             Ring ar, br;
             uint32_t G = 0;          // global accumulation-group counter
             // loop-invariant operand pieces: the issuing thread is a single latency-bound instruction
@@ -362,7 +406,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                     ar.idx += KO;
                     if (ar.idx == AS) { ar.idx = 0; ar.phase ^= 1u; }
                     const Ring bs0 = br;                                      // streamed B: ring position of unit 0
-                    br.idx += KO;
+                    br.idx += BKO;
                     if (br.idx == BS) { br.idx = 0; br.phase ^= 1u; }
                     if (((gt ^ (uint32_t)mw) & 1u) != 0) continue;            // the other issuer's tile
                     TLB_TRACE(1 + 2 * mw, tri, 4);
@@ -370,14 +414,14 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                     if (first && Gc >= 2) mbar_wait(&d_empty[dbuf], ((Gc >> 1) - 1) & 1u);
                     Ring b0 = bs0, b1 = bs0;
                     if (p.b_resident) {      // slot = position inside the item's b block, one phase per item
-                        b0.idx = j * KO; b0.phase = (bphase >> b0.idx) & 1u;
-                        b1.idx = j * KO + (KO - 1); b1.phase = (bphase >> b1.idx) & 1u;
-                    } else if constexpr (KO == 2) {
+                        b0.idx = j * BKO; b0.phase = (bphase >> b0.idx) & 1u;
+                        b1.idx = j * BKO + (BKO - 1); b1.phase = (bphase >> b1.idx) & 1u;
+                    } else if constexpr (BKO == 2) {
                         b1.idx = bs0.idx + 1;                                 // BS is even: a tile never wraps inside
                     }
                     TLB_TRACE(1 + 2 * mw, tri, 0);
                     // one overlapped wait per tile: the A tile and its B unit(s)
-                    if constexpr (KO == 2) mbar_wait3(&a_full[as0], aph, &b_full[b0.idx], b0.phase, &b_full[b1.idx], b1.phase);
+                    if constexpr (BKO == 2) mbar_wait3(&a_full[as0], aph, &b_full[b0.idx], b0.phase, &b_full[b1.idx], b1.phase);
                     else mbar_wait2(&a_full[as0], aph, &b_full[b0.idx], b0.phase);
                     // my turn: the other issuer has put its tile into the pipe (accumulate order within a group)
                     if (mw == 1) mbar_wait(&tok[1], own & 1u);
@@ -385,7 +429,23 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                     TLB_TRACE(1 + 2 * mw, tri, 2);
                     tc_fence_after();
                     if (elect_one_sync()) {
-                        if (!(p.debug & 2)) {
+                        if constexpr (HF) {
+                            if (!(p.debug & 2)) {
+                                const uint32_t d1 = d_base + dbuf * C::D_COLS;
+                                const uint32_t d2 = d1 + RP;
+                                const uint32_t blo = bdesc_lo0 + b0.idx * (C::B_UNIT >> 4);
+                                // 4 K steps of 16: step ks reads A unit ks / 2, halves [8 (ks & 1), +8) of its hi / lo
+                                // columns, and bytes [32 ks, +32) of the B rows
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    const uint32_t a_hi = a_base + (as0 + (ks >> 1)) * C::A_COLS + (ks & 1) * 8;
+                                    const uint64_t db = ((uint64_t)bdesc_hi << 32) | (blo + ks * 2);
+                                    if (ks == 0) mma_ts_f16(d1, a_hi, db, idesc1, first ? 0u : 1u);
+                                    else mma_ts_f16_acc(d1, a_hi, db, idesc1);
+                                    mma_ts_f16_acc(d2, a_hi + 16, db, idesc2);
+                                }
+                            }
+                        } else if (!(p.debug & 2)) {
 #pragma unroll
                             for (int u = 0; u < KO; ++u) {
                                 const uint32_t d1 = d_base + dbuf * C::D_COLS;
@@ -414,7 +474,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                         mbar_arrive(&tok[mw ^ 1]);
                         if (!p.b_resident || last_a) {     // a resident B slot is released by its last reader only
                             tc_commit(&b_empty[b0.idx]);
-                            if constexpr (KO == 2) tc_commit(&b_empty[b1.idx]);
+                            if constexpr (BKO == 2) tc_commit(&b_empty[b1.idx]);
                         }
                         if (kUnitRelease && (p.debug & 2)) tc_commit(&a_empty[as0]);      // perf triage: MMAs skipped
                         tc_commit(&a_empty[kUnitRelease ? as0 + KO - 1 : as0]);
@@ -424,7 +484,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                     TLB_TRACE(1 + 2 * mw, tri, 3); ++tri;
                     ++own;
                 }
-                bphase ^= (1u << (nbc * KO)) - 1u;
+                bphase ^= (1u << (nbc * BKO)) - 1u;
             }
         }
     } else if (warp < 10) {
@@ -436,6 +496,8 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         uint32_t cbase = 0;        // global index (per CTA) of the current item's first tile
         int pub_slot[2] = {0, 0};  // A slots stored but not yet published
         int unpublished = 0;       // A units whose tcgen05.st have been issued but not yet waited for
+        float hf_inv = 1.f;
+        const float hf_s = HF ? hf_scale(p.x_absmax, &hf_inv) : 1.f;
         for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
             const TcItem t = tc_item(p, it);
             const int n = max(0, t.a1 - t.a0) * max(0, t.bc1 - t.bc0);    // tiles of this item
@@ -527,7 +589,20 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                     }
                     if (warp == 2) TLB_TRACE(2, tri, 4 + u);
                     const uint32_t abase = lane_addr + a_col0 + as * C::A_COLS;
-                    if (!(p.debug & 4)) {
+                    if constexpr (HF) {
+                        if (!(p.debug & 4)) {
+                            // unit u of this row: ta for (u == 0) != flip, else tb; scaled into fp16 range, split, packed
+                            const bool first_line = (u == 0) != (flip != 0);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float x0 = __uint_as_float(first_line ? ta[2 * j] : tb[(2 * j) & (KS == 64 ? 31 : 0)]) * hf_s;
+                                const float x1 = __uint_as_float(first_line ? ta[2 * j + 1] : tb[(2 * j + 1) & (KS == 64 ? 31 : 0)]) * hf_s;
+                                hf_split2(x0, x1, h[j], h[16 + j]);
+                            }
+                            TLB_TMEM_ST16(abase, h);
+                            TLB_TMEM_ST16(abase + 16, (h + 16));
+                        }
+                    } else if (!(p.debug & 4)) {
                         if (KS == 32 || u == 0) {
 #pragma unroll
                             for (int k = 0; k < 32; ++k) h[k] = ((KS == 64 && flip) ? tb[k & (KS == 64 ? 31 : 0)] : ta[k]) & 0xFFFFE000u;
@@ -575,23 +650,23 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 if (t.a1 <= t.a0 || nbc <= 0) continue;
                 if (p.b_resident) {
                     // the item's b block is loaded once and stays in shared memory for all of its `a` rows
-                    for (int sl = 0; sl < nbc * KO; ++sl) {
+                    for (int sl = 0; sl < nbc * BKO; ++sl) {
                         mbar_wait(&b_empty[sl], ((bphase >> sl) & 1u) ^ 1u);
                         if (elect_one_sync()) {
                             mbar_expect_tx(&b_full[sl], C::B_UNIT);
                             unsigned char* dst = b_smem + sl * C::B_UNIT;
-                            tma_load_2d(dst, &bhi_map, &b_full[sl], t.bc0 * KS + sl * 32, 0);
-                            tma_load_2d(dst + RP * 128, &blo_map, &b_full[sl], t.bc0 * KS + sl * 32, 0);
+                            tma_load_2d(dst, &bhi_map, &b_full[sl], t.bc0 * KS + sl * (KS / BKO), 0);
+                            tma_load_2d(dst + RP * 128, &blo_map, &b_full[sl], t.bc0 * KS + sl * (KS / BKO), 0);
                         }
                         __syncwarp();
                     }
-                    bphase ^= (1u << (nbc * KO)) - 1u;
+                    bphase ^= (1u << (nbc * BKO)) - 1u;
                     continue;
                 }
                 for (int a = t.a0; a < t.a1; ++a)
                 for (int bc = t.bc0; bc < t.bc1; ++bc) {
 #pragma unroll
-                    for (int u = 0; u < KO; ++u) {
+                    for (int u = 0; u < BKO; ++u) {
                         mbar_wait(&b_empty[br.idx], br.phase ^ 1u);
                         if (elect_one_sync()) {
                             if ((p.debug & 8) && nb_loaded >= BS) {
@@ -599,8 +674,8 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                             } else {
                                 mbar_expect_tx(&b_full[br.idx], C::B_UNIT);
                                 unsigned char* dst = b_smem + br.idx * C::B_UNIT;
-                                tma_load_2d(dst, &bhi_map, &b_full[br.idx], bc * KS + u * 32, 0);
-                                tma_load_2d(dst + RP * 128, &blo_map, &b_full[br.idx], bc * KS + u * 32, 0);
+                                tma_load_2d(dst, &bhi_map, &b_full[br.idx], bc * KS + u * (KS / BKO), 0);
+                                tma_load_2d(dst + RP * 128, &blo_map, &b_full[br.idx], bc * KS + u * (KS / BKO), 0);
                             }
                         }
                         ++nb_loaded;
@@ -660,6 +735,11 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                         tc_fence_before();
                         mbar_arrive(&d_empty[buf]);
                     }
+                    if constexpr (HF) {
+                        // the cross-term block was formed from lo parts scaled by 2^11
+#pragma unroll
+                        for (int c = 0; c < CW; ++c) r1[c] = __float_as_uint(__uint_as_float(r1[c]) * (1.f / 2048.f));
+                    }
                     if (prow4 != nullptr) {
 #pragma unroll
                         for (int k = 0; k < CW / 4; ++k) {
@@ -679,6 +759,16 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 done += len;
                 bu += len;
                 if (bu >= units_per_a) { bu = 0; ++a; }
+            }
+            if constexpr (HF) {       // undo the power-of-two scales of the tensor and of the small operand's columns
+                float xinv;
+                hf_scale(p.x_absmax, &xinv);
+                const float4* ci = reinterpret_cast<const float4*>(p.col_inv);
+#pragma unroll
+                for (int c = 0; c < RP / 4; ++c) {
+                    const float4 v = __ldg(ci + c);
+                    acc[4 * c] *= v.x * xinv; acc[4 * c + 1] *= v.y * xinv; acc[4 * c + 2] *= v.z * xinv; acc[4 * c + 3] *= v.w * xinv;
+                }
             }
             const int64_t gm = (int64_t)mt * TM + row;
             if (gm < p.M) {
@@ -723,32 +813,36 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-template <int RP, int XL, int BM>
+template <int RP, int XL, bool HF>
 int launch_cfg(const TcStreamLaunch& l, cudaStream_t stream) {
-    using C = Cfg<RP, XL>;
+    using C = Cfg<RP, XL, HF>;
     const int smem = C::SMEM + 1024;
     static std::atomic<uint64_t> attr_done{0};        // per instantiation, one bit per device
-    if (ensure_dynamic_smem(tc_stream_kernel<RP, XL, BM>, smem, attr_done)) return TLB200_ECUDA;
+    if (ensure_dynamic_smem(tc_stream_kernel<RP, XL, HF>, smem, attr_done)) return TLB200_ECUDA;
     int64_t n_items = (int64_t)l.p.m_tiles * l.p.n_bblocks * l.p.k_ranges;
     if (n_items <= 0) return TLB200_OK;
     static int grid_cap = -1;
     if (grid_cap < 0) { const char* e = getenv("TLB200_TC_GRID"); grid_cap = e ? atoi(e) : kNumSMs; if (grid_cap < 1) grid_cap = kNumSMs; }
     const unsigned grid = (unsigned)(n_items < grid_cap ? n_items : grid_cap);
-    tc_stream_kernel<RP, XL, BM><<<grid, NUM_THREADS, smem, stream>>>(l.x_map, l.bhi_map, l.blo_map, l.p);
+    tc_stream_kernel<RP, XL, HF><<<grid, NUM_THREADS, smem, stream>>>(l.x_map, l.bhi_map, l.blo_map, l.p);
     TLB_CHECK_LAUNCH();
     return TLB200_OK;
 }
 
-template <int RP, int XL>
-int launch_bm(const TcStreamLaunch& l, cudaStream_t s) {
-    return launch_cfg<RP, XL, TC_B_MAT>(l, s);
-}
 template <int RP>
 int launch_xl(const TcStreamLaunch& l, cudaStream_t s) {
+    if (l.hf) {
+        if (!l.p.x_absmax || !l.p.col_inv) return TLB200_EINVAL;
+        switch (l.x_layout) {
+            case TC_X_KMAJOR_2: return launch_cfg<RP, TC_X_KMAJOR_2, true>(l, s);
+            case TC_X_MMAJOR: return launch_cfg<RP, TC_X_MMAJOR, true>(l, s);
+        }
+        return TLB200_EUNSUPPORTED;
+    }
     switch (l.x_layout) {
-        case TC_X_KMAJOR_1: return launch_bm<RP, TC_X_KMAJOR_1>(l, s);
-        case TC_X_KMAJOR_2: return launch_bm<RP, TC_X_KMAJOR_2>(l, s);
-        case TC_X_MMAJOR: return launch_bm<RP, TC_X_MMAJOR>(l, s);
+        case TC_X_KMAJOR_1: return launch_cfg<RP, TC_X_KMAJOR_1, false>(l, s);
+        case TC_X_KMAJOR_2: return launch_cfg<RP, TC_X_KMAJOR_2, false>(l, s);
+        case TC_X_MMAJOR: return launch_cfg<RP, TC_X_MMAJOR, false>(l, s);
     }
     return TLB200_EINVAL;
 }
@@ -757,15 +851,16 @@ int launch_xl(const TcStreamLaunch& l, cudaStream_t s) {
 
 bool tc_available() { return get_encode_fn() != nullptr && !getenv("TLB200_DISABLE_TC"); }
 
-int tc_encode_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box, bool swizzle128) {
+int tc_encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, bool swizzle128, bool half) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return TLB200_EUNSUPPORTED;
     cuuint64_t d[5], s[4];
     cuuint32_t b[5], e[5] = {1, 1, 1, 1, 1};
     for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; }
     for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), d, s, b, e,
+    CUresult r = enc(map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                     const_cast<void*>(base), d, s, b, e,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? TLB200_OK : TLB200_ECUDA;

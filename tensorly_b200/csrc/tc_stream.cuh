@@ -42,6 +42,10 @@ struct TcStreamParams {
     float* out;
     int64_t sOk, sOm, sOn;
     int n_valid;
+    // fp16-split engine only (TcStreamLaunch::hf): device scalar max |x| over the tensor (the range hint) and the
+    // inverse power-of-two column scales of the small operand [RP]
+    const float* x_absmax;
+    const float* col_inv;
     long long* trace;          // perf triage only: per-role clock64 timestamps of CTA 0 (null = off)
     int debug;                 // TLB200_TC_DEBUG bitmask (perf triage only): 1 skip KR math, 2 skip MMAs, 4 skip TMEM stores, 8 skip epilogue loads
 };
@@ -53,13 +57,14 @@ struct TcStreamLaunch {
     int rp;                    // 32 or 64
     int x_layout;              // TcXLayout
     int b_mode;                // TcBMode
+    int hf;                    // 1: fp16-split engine (64-element tiles only; B maps are fp16 [RP rows][Kpad], box {64, RP})
 };
 
 // true when cuTensorMapEncodeTiled could be resolved (a driver is present)
 bool tc_available();
 // encode helper (returns TLB200_ECUDA on failure)
-int tc_encode_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box, bool swizzle128);
+int tc_encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, bool swizzle128, bool half = false);
 int tc_stream_launch(const TcStreamLaunch& l, cudaStream_t stream);
 // K extent of one chunk for a layout
 inline int tc_chunk_k(int x_layout) { return x_layout == TC_X_KMAJOR_1 ? 32 : 64; }

@@ -10,6 +10,7 @@
 #include "ttm_tc.cuh"
 #include "tc_stream.cuh"
 #include "stream_gemm.cuh"
+#include "hf_split.cuh"
 
 namespace tlb200 {
 namespace {
@@ -88,7 +89,7 @@ bool ttm_tc_supported(int64_t L, int64_t J, int64_t T, int64_t I) {
 size_t ttm_tc_workspace(int64_t L, int64_t J, int64_t T, int64_t I) {
     TtmGeom g;
     if (!geom(L, J, T, I < kTtmRowBlock ? I : kTtmRowBlock, &g)) return 0;
-    size_t total = 2 * align_up((size_t)g.rp * g.kpad * 4, 256) + 256;
+    size_t total = 2 * align_up((size_t)g.rp * g.kpad * 4, 256) + 256 + 256;      // + the fp16 engine's column scales
     if (g.ksplit > 1) total += align_up((size_t)g.ksplit * g.M * g.rp * 4, 256);
     return total;
 }
@@ -103,7 +104,14 @@ static int ttm_tc_launch_block(const float* x, int64_t L, int64_t J, int64_t T, 
     float* bhi = ws.take<float>((size_t)g.rp * g.kpad);
     float* blo = ws.take<float>((size_t)g.rp * g.kpad);
     float* partial = g.ksplit > 1 ? ws.take<float>((size_t)g.ksplit * g.M * g.rp) : nullptr;
-    {
+    float* col_inv = ws.take<float>(64);
+    // a registered range hint for this tensor selects the fp16-split engine (64-element tiles only)
+    const float* x_absmax = g.ks == 64 ? tc_range_hint(x) : nullptr;
+    if (x_absmax != nullptr) {
+        const int st0 = launch_split_matrix_f16(m, I, J, mrs, mcs, g.rp, g.kpad, reinterpret_cast<__half*>(bhi),
+                                                reinterpret_cast<__half*>(blo), col_inv, stream);
+        if (st0) return st0;
+    } else {
         const int64_t total = (int64_t)g.rp * g.kpad;
         int64_t blocks = ceil_div(total, 256);
         if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
@@ -111,6 +119,7 @@ static int ttm_tc_launch_block(const float* x, int64_t L, int64_t J, int64_t T, 
         TLB_CHECK_LAUNCH();
     }
     TcStreamLaunch l;
+    l.hf = x_absmax != nullptr;
     l.rp = g.rp;
     l.x_layout = g.layout;
     l.b_mode = TC_B_MAT;
@@ -134,7 +143,14 @@ static int ttm_tc_launch_block(const float* x, int64_t L, int64_t J, int64_t T, 
         st = tc_encode_map(&l.x_map, x, 3, dims, strides, box, true);
     }
     if (st) return st;
-    {
+    if (l.hf) {
+        uint64_t bd[2] = {(uint64_t)g.kpad, (uint64_t)g.rp}, bs[1] = {(uint64_t)g.kpad * 2};
+        uint32_t bb[2] = {64, (uint32_t)g.rp};
+        st = tc_encode_map(&l.bhi_map, bhi, 2, bd, bs, bb, true, true);
+        if (st) return st;
+        st = tc_encode_map(&l.blo_map, blo, 2, bd, bs, bb, true, true);
+        if (st) return st;
+    } else {
         uint64_t bd[2] = {(uint64_t)g.kpad, (uint64_t)g.rp}, bs[1] = {(uint64_t)g.kpad * 4};
         uint32_t bb[2] = {32, (uint32_t)g.rp};
         st = tc_encode_map(&l.bhi_map, bhi, 2, bd, bs, bb, true);
@@ -152,6 +168,8 @@ static int ttm_tc_launch_block(const float* x, int64_t L, int64_t J, int64_t T, 
     p.b_resident = 0;                         // the matrix is streamed with the tiles (re-read from L2 per item)
     p.group_units = tc_group_units();
     p.P = nullptr;
+    p.x_absmax = x_absmax;
+    p.col_inv = l.hf ? col_inv : nullptr;
     p.out = out;
     if (g.layout == TC_X_MMAJOR) { p.sOk = I_total * T; p.sOm = 1; p.sOn = T; }
     else                         { p.sOk = 0; p.sOm = I_total; p.sOn = 1; }

@@ -8,6 +8,8 @@ dtype; ALS reconstruction error within 1e-4 (relative) after a fixed number of s
 """
 import itertools
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -1110,3 +1112,94 @@ def test_fused_sweep_same_trajectory_as_unfused(monkeypatch):
     assert max(abs(a - b) / b for a, b in zip(runs[0][0], runs[1][0])) <= 1e-5
     for a, b in zip(runs[0][1], runs[1][1]):
         assert float(torch.linalg.norm(a - b) / torch.linalg.norm(b)) <= 1e-3
+
+
+# ---- fp16-split tensor-core engine (range hint) ---------------------------------------------------------------
+def _kr_ref64(x, fs, mode):
+    """MTTKRP in fp64 on the device (einsum over the other modes)."""
+    xd = x.double()
+    letters = "abcde"[: x.dim()]
+    ops, subs = [xd], [letters]
+    for i, f in enumerate(fs):
+        if i != mode:
+            ops.append(f.double()); subs.append(letters[i] + "r")
+    return torch.einsum(",".join(subs) + "->" + letters[mode] + "r", *ops)
+
+
+@pytest.mark.parametrize("shape,rank", [((256, 192, 320), 64), ((256, 192, 320), 32), ((130, 96, 200), 48),
+                                        ((64, 48, 40, 64), 64)])
+@pytest.mark.parametrize("data", ["uniform", "zero_mean", "wide"])
+def test_fp16_engine_mttkrp_matches_fp64(shape, rank, data):
+    """With a registered range hint MTTKRP runs on the fp16-split engine; same 1e-5 gate as 3xTF32 — on uniform data,
+    zero-mean data, and data / factor columns spanning many orders of magnitude (per-tensor and per-column scales)."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.rand(shape, generator=g, device="cuda")
+    fs = [torch.rand(s, rank, generator=g, device="cuda") for s in shape]
+    if data != "uniform":
+        x = x - 0.5
+        fs = [f - 0.5 for f in fs]
+    if data == "wide":
+        x = x * 3.7e-10
+        fs = [f * torch.logspace(-6, 5, rank, device="cuda")[None, :] for f in fs]
+    x = x.contiguous()
+    hint = tb.RangeHint(x)
+    try:
+        assert float(hint.absmax) == float(x.abs().max())
+        for mode in range(len(shape)):
+            got = tb.unfolding_dot_khatri_rao(x, (None, fs), mode)
+            path = tb.last_kernel_path()
+            ref = _kr_ref64(x, fs, mode)
+            # column-wise: every rank-one component is held to the gate on its own (they differ by many orders of magnitude in "wide")
+            err = float(((got.double() - ref).norm(dim=0) / ref.norm(dim=0)).max())
+            assert err <= 1e-5, (mode, path, err)
+            if shape == (256, 192, 320):          # every mode of this shape streams 64-element tiles
+                assert path == "tcgen05-f16", (mode, path)
+    finally:
+        hint.close()
+    tb.unfolding_dot_khatri_rao(x, (None, fs), 0)
+    assert tb.last_kernel_path() != "tcgen05-f16"
+
+
+@pytest.mark.parametrize("shape,mode,rows", [((320, 256, 192), 2, 64), ((320, 256, 192), 0, 64), ((320, 256, 192), 1, 48),
+                                             ((96, 2048), 1, 64)])
+def test_fp16_engine_mode_dot_matches_fp64(shape, mode, rows):
+    g = torch.Generator(device="cuda").manual_seed(12)
+    x = (torch.rand(shape, generator=g, device="cuda") - 0.5).contiguous()
+    m = (torch.rand(rows, shape[mode], generator=g, device="cuda") - 0.5) * torch.logspace(-6, 6, rows, device="cuda")[:, None]
+    want = torch.tensordot(m.double(), x.double(), dims=([1], [mode])).movedim(0, mode)
+    base = tb.mode_dot(x, m, mode)
+    hint = tb.RangeHint(x)
+    try:
+        got = tb.mode_dot(x, m, mode)
+        path = tb.last_kernel_path()
+    finally:
+        hint.close()
+    sl = [slice(None)] * len(shape)
+    for i in (0, rows // 2, rows - 1):        # row-wise: the rows of m differ by 1e12 in scale
+        sl[mode] = i
+        e = float((got[tuple(sl)].double() - want[tuple(sl)]).norm() / want[tuple(sl)].norm())
+        e0 = float((base[tuple(sl)].double() - want[tuple(sl)]).norm() / want[tuple(sl)].norm())
+        assert e <= 1e-5, (i, path, e, e0)
+
+
+def test_fp16_engine_in_the_driver():
+    """CPALS registers the hint itself at rank > 32: same trajectory as the 3xTF32 sweeps."""
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = torch.rand((256, 224, 192), generator=g, device="cuda")
+    fs = [torch.rand(s, 64, generator=g, device="cuda") for s in x.shape]
+    w = torch.ones(64, device="cuda")
+    runs = []
+    for off in ("0", "1"):
+        os.environ["TLB200_HF_MIN_RANK"] = "33" if off == "0" else "1000"
+        try:
+            st = tb.CPALS(x, w, fs)
+            assert (st._range_hint is not None) == (off == "0")
+            errs = []
+            for _ in range(5):
+                st.sweep(True)
+                errs.append(float(st.err[0]))
+            runs.append(errs)
+            del st
+        finally:
+            os.environ.pop("TLB200_HF_MIN_RANK", None)
+    assert max(abs(a - b) / b for a, b in zip(*runs)) <= 1e-5, runs
