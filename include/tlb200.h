@@ -122,6 +122,10 @@ typedef struct {
     int     rank_passes;      /* passes over the tensor: 1, or ceil(rank/64) column blocks
                                  on the tcgen05 path when rank > 64 (the other fields then
                                  describe the first pass)                   */
+    int     f16;              /* 1: planned for the fp16-split engine (a range hint is registered
+                                 for the tensor, see tlb200_hint_tensor_absmax); the shape-only
+                                 tlb200_mttkrp_plan always reports the 3xTF32 plan (0) */
+    int     reserved_;
 } tlb200_mttkrp_plan_t;
 
 int tlb200_mttkrp_plan(const int64_t* shape, int ndim, int mode, int64_t rank,

@@ -10,6 +10,7 @@ g = torch.Generator(device="cuda").manual_seed(0)
 x = torch.rand(n, n, n, generator=g, device="cuda")
 fs = [torch.rand(n, R, generator=g, device="cuda") for _ in range(3)]
 w = torch.ones(R, device="cuda")
+hint = tb.RangeHint(x) if os.environ.get("TLB200_DISABLE_HF", "0") in ("", "0") else None     # the ALS drivers register it
 for _ in range(reps):
     for mode in range(3):
         tb.unfolding_dot_khatri_rao(x, (w, fs), mode)

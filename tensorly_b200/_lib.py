@@ -33,7 +33,7 @@ class MttkrpPlan(ctypes.Structure):
         ("p_first", c_int), ("p_count", c_int),
         ("q_first", c_int), ("q_count", c_int),
         ("rank_padded", c_int64), ("splits", c_int64),
-        ("path", c_int), ("rank_passes", c_int),
+        ("path", c_int), ("rank_passes", c_int), ("f16", c_int), ("reserved_", c_int),
     ]
 
 

@@ -45,7 +45,38 @@ def set_dimension_tree(flag: bool) -> None:
     _cache.entry = None
 
 
+# ---- automatic range hint behind the stateless tenalg API ------------------------------------------------------
+# The fp16-split engine (rank 33..64, include/tlb200.h: tlb200_hint_tensor_absmax) needs max |tensor|.  An ALS loop
+# passes the same tensor object every call, so the SECOND call that sees the same object at the same torch
+# `_version` pays one pass for max |x| and registers it; any other tensor, or an in-place edit, drops the hint
+# before the kernel runs (a one-off call never pays).  TLB200_BACKEND_AUTOHINT=0 turns this off.
+_autohint = {"on": os.environ.get("TLB200_BACKEND_AUTOHINT", "1") != "0"}
+
+
+def _track_range_hint(tensor, rank):
+    e = getattr(_cache, "hint", None)
+    if e is not None and e[0]() is tensor and e[1] == tensor._version:
+        if e[3] is None:
+            e[2] += 1
+            if e[2] >= 2:
+                e[3] = _ops.RangeHint(tensor, hold=False)    # withdrawn when the tensor object dies
+        return
+    if e is not None and e[3] is not None:
+        e[3].close()
+    _cache.hint = None
+    import torch
+    if torch.is_tensor(tensor) and _ops.RangeHint.applies(tensor, rank):
+        import weakref
+        _cache.hint = [weakref.ref(tensor), tensor._version, 1, None]
+
+
 def _unfolding_dot_khatri_rao(tensor, cp_tensor, mode):
+    if _autohint["on"]:
+        try:
+            rank = cp_tensor[1][0].shape[1]
+        except Exception:
+            rank = 0
+        _track_range_hint(tensor, rank)
     if not _dimtree["on"]:
         return _ops.unfolding_dot_khatri_rao(tensor, cp_tensor, mode)
     import torch

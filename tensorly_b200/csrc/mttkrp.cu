@@ -21,7 +21,7 @@
 namespace tlb200 {
 
 static int make_plan_one(const int64_t* shape, int ndim, int mode, int64_t rank, int dtype, int path,
-                         tlb200_mttkrp_plan_t* pl) {
+                         tlb200_mttkrp_plan_t* pl, bool f16 = false) {
     if (!shape || !pl || ndim < 2 || ndim > TLB200_MAX_NDIM || mode < 0 || mode >= ndim || rank < 1 ||
         !dtype_valid(dtype) || path < TLB200_PATH_AUTO || path > TLB200_PATH_TCGEN05)
         return TLB200_EINVAL;
@@ -73,8 +73,11 @@ static int make_plan_one(const int64_t* shape, int ndim, int mode, int64_t rank,
     if (path == TLB200_PATH_TCGEN05 && resolved != TLB200_PATH_TCGEN05) return TLB200_EUNSUPPORTED;
     pl->path = resolved;
     pl->rank_passes = 1;
+    pl->f16 = 0;
+    pl->reserved_ = 0;
 
     if (resolved == TLB200_PATH_TCGEN05) {
+        pl->f16 = f16 && mttkrp_tc_hf_ok(*pl) ? 1 : 0;
         mttkrp_tc_fill_plan(pl, rank);
     } else {
         const int TR = stream_gemm_tr_for(rank, dtype);
@@ -99,18 +102,21 @@ constexpr int64_t kTcRankChunk = 64;      // widest column block the tcgen05 eng
 // columns (factor column slices are pointer offsets).  Two to four passes at ~5 TB/s still beat the SIMT kernel,
 // which is FMA-bound at such ranks (0.25 TB/s at rank 100).  The returned plan describes the first pass.
 static int make_plan(const int64_t* shape, int ndim, int mode, int64_t rank, int dtype, int path,
-                     tlb200_mttkrp_plan_t* pl) {
+                     tlb200_mttkrp_plan_t* pl, bool f16 = false) {
     if (rank > kTcRankChunk && dtype == TLB200_F32 && path != TLB200_PATH_SIMT) {
         tlb200_mttkrp_plan_t chunk;
-        const int st = make_plan_one(shape, ndim, mode, kTcRankChunk, dtype, path, &chunk);
+        const int st = make_plan_one(shape, ndim, mode, kTcRankChunk, dtype, path, &chunk, f16);
         if (st == TLB200_OK && chunk.path == TLB200_PATH_TCGEN05) {
             *pl = chunk;
             pl->rank_passes = (int)ceil_div(rank, kTcRankChunk);
             return TLB200_OK;
         }
     }
-    return make_plan_one(shape, ndim, mode, rank, dtype, path, pl);
+    return make_plan_one(shape, ndim, mode, rank, dtype, path, pl, f16);
 }
+
+// a registered range hint (tlb200_hint_tensor_absmax) selects the fp16-split engine for this tensor
+static bool wants_f16(const void* x, int dtype) { return dtype == TLB200_F32 && x != nullptr && tc_range_hint(x) != nullptr; }
 
 static size_t workspace_for(const tlb200_mttkrp_plan_t& pl, int dtype) {
     const size_t es = dtype_size(dtype);
@@ -147,10 +153,10 @@ static int run(const T* x, const int64_t* shape, int ndim, int mode, const T* co
             w = nullptr;  // weights go to the first non-skipped factor only
         }
     }
-    // a registered range hint (tlb200_hint_tensor_absmax) selects the fp16-split engine
     const float* x_absmax = nullptr;
-    if constexpr (sizeof(T) == 4) {
-        if (pl.path == TLB200_PATH_TCGEN05 && mttkrp_tc_hf_ok(pl)) x_absmax = tc_range_hint(x);
+    if (pl.f16) {
+        x_absmax = tc_range_hint(x);
+        if (x_absmax == nullptr) return TLB200_EINVAL;       // the hint was withdrawn between planning and launch
     }
     if (x_absmax != nullptr) {
         // Q transposed as fp16 hi / lo tables [rank_padded][Bpad] with one power-of-two scale per column, then the
@@ -246,6 +252,13 @@ extern "C" size_t tlb200_mttkrp_workspace_bytes(const int64_t* shape, int ndim, 
     tlb200_mttkrp_plan_t pl;
     if (make_plan(shape, ndim, mode, rank, dtype, path, &pl)) return 0;
     size_t need = workspace_for(pl, dtype);
+    if (pl.path == TLB200_PATH_TCGEN05) {                  // the fp16-split engine blocks the contraction differently
+        tlb200_mttkrp_plan_t hf;
+        if (!make_plan(shape, ndim, mode, rank, dtype, path, &hf, true)) {
+            const size_t h = workspace_for(hf, dtype);
+            if (h > need) need = h;
+        }
+    }
     if (pl.rank_passes > 1 && rank % kTcRankChunk) {       // the last, narrower pass may plan differently
         tlb200_mttkrp_plan_t tail;
         if (!make_plan_one(shape, ndim, mode, rank % kTcRankChunk, dtype, path, &tail)) {
@@ -270,7 +283,8 @@ extern "C" int tlb200_mttkrp(const void* x, const int64_t* shape, int ndim, int 
                              const void* weights, int dtype, void* out, int64_t out_ld, void* workspace,
                              size_t workspace_bytes, int path, void* stream) {
     tlb200_mttkrp_plan_t pl;
-    int st = make_plan(shape, ndim, mode, rank, dtype, path, &pl);
+    const bool f16 = wants_f16(x, dtype);
+    int st = make_plan(shape, ndim, mode, rank, dtype, path, &pl, f16);
     if (st) return st;
     if (!x || !factors || !f_row_stride || !f_col_stride || !out || out_ld < rank || !workspace) return TLB200_EINVAL;
     for (int i = 0; i < ndim; ++i)
@@ -289,7 +303,7 @@ extern "C" int tlb200_mttkrp(const void* x, const int64_t* shape, int ndim, int 
         for (int64_t c0 = 0; c0 < rank; c0 += kTcRankChunk) {
             const int64_t rc = rank - c0 < kTcRankChunk ? rank - c0 : kTcRankChunk;
             tlb200_mttkrp_plan_t cpl;
-            st = make_plan_one(shape, ndim, mode, rc, dtype, path, &cpl);
+            st = make_plan_one(shape, ndim, mode, rc, dtype, path, &cpl, f16);
             if (st) return st;
             if (workspace_bytes < workspace_for(cpl, dtype)) return TLB200_EWORKSPACE;
             for (int i = 0; i < ndim; ++i)
@@ -313,7 +327,7 @@ extern "C" int tlb200_mttkrp_partials(const void* x, const int64_t* shape, int n
                                       tlb200_partials_t* partials, void* stream) {
     tlb200_mttkrp_plan_t pl;
     if (!partials) return TLB200_EINVAL;
-    int st = make_plan(shape, ndim, mode, rank, dtype, path, &pl);
+    int st = make_plan(shape, ndim, mode, rank, dtype, path, &pl, wants_f16(x, dtype));
     if (st) return st;
     if (pl.rank_passes > 1) return TLB200_EUNSUPPORTED;
     if (!x || !factors || !f_row_stride || !f_col_stride || !workspace) return TLB200_EINVAL;

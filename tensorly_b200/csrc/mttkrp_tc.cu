@@ -38,6 +38,23 @@ bool mttkrp_tc_hf_ok(const tlb200_mttkrp_plan_t& pl) { return layout_for(pl) != 
 // chunks of the inner Khatri-Rao table one work item keeps resident in shared memory
 static int block_chunks(const tlb200_mttkrp_plan_t& pl, int64_t rank_padded) {
     const int ks = tc_chunk_k(layout_for(pl));
+    if (pl.f16) {
+        // fp16 engine: every slot holds a whole 64-element tile of the table, so twice the block fits — and the
+        // accumulation groups (cut at every `a` boundary) are twice as long: half the drains per tile
+        const int cap = tc_b_slots((int)rank_padded);
+        if (const char* e = getenv("TLB200_TC_NB_F16")) { const int v = atoi(e); if (v >= 1 && v <= cap) return v; }
+        // equal blocks: the largest size in [cap / 2, cap] that wastes the fewest chunk slots over the b range
+        // (2048 / 64 = 32 chunks: 8 x 4 rather than 5 x 6 + 2)
+        const int64_t cpa = ceil_div(pl.B, ks);
+        if (cpa <= cap) return (int)cpa;
+        int best = cap;
+        int64_t best_waste = -1;
+        for (int nb = cap; nb >= (cap + 1) / 2; --nb) {
+            const int64_t waste = ceil_div(cpa, nb) * nb - cpa;
+            if (best_waste < 0 || waste < best_waste) { best = nb; best_waste = waste; }
+        }
+        return best;
+    }
     // as many chunks as fit in shared memory: a shorter block would mean shorter accumulation groups, i.e. more
     // epilogue drains per tile (measured: equal blocks of 2 chunks lose to blocks of 3 + 1 at B = 256, rank 64)
     return tc_b_slots((int)rank_padded) * 32 / ks;
@@ -133,7 +150,7 @@ int mttkrp_tc_launch(const float* x, const tlb200_mttkrp_plan_t& pl, int64_t /*r
     if (p.k_ranges < 1 || p.k_ranges * p.n_bblocks != pl.splits) return TLB200_EINVAL;
     p.a_per_range = ceil_div(pl.A, p.k_ranges);
     p.b_resident = 1;
-    p.group_units = tc_group_units();
+    p.group_units = tc_group_units(l.hf != 0);
     p.x_absmax = x_absmax;
     p.col_inv = l.hf ? Q + pl.rank_padded * ldq : nullptr;
     p.P = P;     // outer Khatri-Rao table: applied per `a` by the epilogue

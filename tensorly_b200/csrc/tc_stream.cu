@@ -269,7 +269,7 @@ struct Cfg {
     static constexpr int A_COLS = HF ? 32 : 64;                     // TMEM columns per A unit: [hi 32 | lo 32] (HF: packed halves)
     static constexpr int AS = HF ? 8 : (RP == 32 ? 6 : 4);
     static constexpr int B_UNIT = 2 * RP * 128;                     // [hi RP rows | lo RP rows] x 128 B, K-major SW128
-    static constexpr int BS = RP == 32 ? 8 : 6;                     // B-operand slots (32-element units): 64 / 96 KB, a ring
+    static constexpr int BS = RP == 32 ? 8 : 6;                     // B-operand slots (32-element units; HF: 64): 64 / 96 KB, a ring
                                                                     // (streamed B) or one resident b block per item
     static constexpr int OFF_X = 0;
     static constexpr int OFF_B = OFF_X + XS * X_STAGE;
@@ -866,17 +866,22 @@ int tc_encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* 
     return r == CUDA_SUCCESS ? TLB200_OK : TLB200_ECUDA;
 }
 
-int tc_group_units() {
+int tc_group_units(bool hf) {
     // accumulation-group length in 32-element K units.  Only the hi*hi products carry a significant
     // round-toward-zero loss (4 MMAs per unit, ~6e-8 each, measured): 8 units keep MTTKRP/TTM near 2e-6.
-    static int units = -1;
+    // The fp16 engine issues 2 hi*hi MMAs per unit: 16 units are the same number of roundings.
+    static int units = -1, units_hf = -1;
     if (units < 0) {
         const char* e = getenv("TLB200_TC_FLUSH");
         units = e ? atoi(e) : 8;
         if (units < 2) units = 2;
         units &= ~1;          // whole tiles (2 units) per group
+        const char* h = getenv("TLB200_TC_FLUSH_F16");
+        units_hf = h ? atoi(h) : 16;
+        if (units_hf < 2) units_hf = 2;
+        units_hf &= ~1;
     }
-    return units;
+    return hf ? units_hf : units;
 }
 
 static long long* g_trace = nullptr;

@@ -68,7 +68,7 @@ int tc_encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* 
 int tc_stream_launch(const TcStreamLaunch& l, cudaStream_t stream);
 // K extent of one chunk for a layout
 inline int tc_chunk_k(int x_layout) { return x_layout == TC_X_KMAJOR_1 ? 32 : 64; }
-int tc_group_units();
+int tc_group_units(bool hf = false);
 // shared-memory slots (32-element units) for the small operand
 inline int tc_b_slots(int rp) { return rp == 32 ? 8 : 6; }
 

@@ -166,7 +166,7 @@ static int ttm_tc_launch_block(const float* x, int64_t L, int64_t J, int64_t T, 
     p.a_per_range = 1;
     p.nb = g.nb; p.n_bblocks = g.ksplit;
     p.b_resident = 0;                         // the matrix is streamed with the tiles (re-read from L2 per item)
-    p.group_units = tc_group_units();
+    p.group_units = tc_group_units(l.hf != 0);
     p.P = nullptr;
     p.x_absmax = x_absmax;
     p.col_inv = l.hf ? col_inv : nullptr;

@@ -64,6 +64,7 @@ class CudaOps:
     subspace_iterate = staticmethod(_ops.subspace_iterate)
     sumsq = staticmethod(_ops.sumsq)
     supports_graphs = True
+    range_hint = staticmethod(_ops.RangeHint)
 
     @staticmethod
     def eigh_top(g, p):
@@ -116,6 +117,11 @@ class HOOI:
             # orthonormal), exactly like the reference loop (_tucker.py:194-196)
             self.factors.append(f.to(self.x.dtype).contiguous())
         self.norm_x2 = ops.sumsq(self.x)
+        # the first product of every chain reads the (constant) input tensor: with its max |x| registered, projections
+        # onto more than 32 columns run on the fp16-split engine (tensorly_b200._ops.RangeHint)
+        self._range_hint = None
+        if self.x.is_cuda and hasattr(ops, "range_hint") and _ops.RangeHint.applies(self.x, max(int(r) for r in rank)):
+            self._range_hint = ops.range_hint(self.x)
         self.core: Optional[torch.Tensor] = None
         self.err = torch.zeros(1, dtype=self.x.dtype, device=self.x.device)
         self._graph = None

@@ -1190,7 +1190,7 @@ def test_fp16_engine_in_the_driver():
     w = torch.ones(64, device="cuda")
     runs = []
     for off in ("0", "1"):
-        os.environ["TLB200_HF_MIN_RANK"] = "33" if off == "0" else "1000"
+        os.environ["TLB200_HF_MIN_RANK"] = "1" if off == "0" else "1000"
         try:
             st = tb.CPALS(x, w, fs)
             assert (st._range_hint is not None) == (off == "0")
