@@ -7,10 +7,13 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 R = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 g = torch.Generator(device="cuda").manual_seed(0)
-x = torch.rand(n, n, n, generator=g, device="cuda")
-fs = [torch.rand(n, R, generator=g, device="cuda") for _ in range(3)]
-w = torch.ones(R, device="cuda")
-hint = tb.RangeHint(x) if os.environ.get("TLB200_DISABLE_HF", "0") in ("", "0") else None     # the ALS drivers register it
+dt = torch.float64 if os.environ.get("DTYPE", "f32") == "f64" else torch.float32
+x = torch.rand(n, n, n, generator=g, device="cuda", dtype=dt)
+fs = [torch.rand(n, R, generator=g, device="cuda", dtype=dt) for _ in range(3)]
+w = torch.ones(R, device="cuda", dtype=dt)
+hint = None
+if dt == torch.float32 and os.environ.get("TLB200_DISABLE_HF", "0") in ("", "0"):
+    hint = tb.RangeHint(x)      # the ALS drivers register it
 for _ in range(reps):
     for mode in range(3):
         tb.unfolding_dot_khatri_rao(x, (w, fs), mode)

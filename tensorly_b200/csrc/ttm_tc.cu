@@ -107,6 +107,7 @@ static int ttm_tc_launch_block(const float* x, int64_t L, int64_t J, int64_t T, 
     float* col_inv = ws.take<float>(64);
     // a registered range hint for this tensor selects the fp16-split engine (64-element tiles only)
     const float* x_absmax = g.ks == 64 ? tc_range_hint(x) : nullptr;
+    set_last_path(x_absmax ? "tcgen05-f16" : "tcgen05");
     if (x_absmax != nullptr) {
         const int st0 = launch_split_matrix_f16(m, I, J, mrs, mcs, g.rp, g.kpad, reinterpret_cast<__half*>(bhi),
                                                 reinterpret_cast<__half*>(blo), col_inv, stream);
