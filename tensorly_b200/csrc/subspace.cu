@@ -186,6 +186,15 @@ __device__ __forceinline__ double fast_rsqrt(double d) {
     r = r * (1.5 - 0.5 * d * r * r);
     return r;
 }
+// One Newton step on the 22-bit float seed: 2^-43 relative.  Enough for the power steps (their orthonormalisation
+// only stabilises the iteration — the shift already leaves a 1e-13 defect, and a final two-pass
+// tlb200_orthonormalize makes the basis exact); it takes ~100 clk off every pivot's dependency chain.
+__device__ __forceinline__ double fast_rsqrt1(double d) {
+    if (!(d > 1e-30 && d < 1e30)) return rsqrt(d);
+    const double r = (double)rsqrtf((float)d);
+    const double e = fma(-d * r, r, 1.0);
+    return fma(0.5 * r, e, r);
+}
 
 __device__ void chol_upper_64(double (*S)[OR_MAX + 1], double* __restrict__ Rm, double* __restrict__ invd, int R,
                               int* bad_out) {
@@ -224,14 +233,13 @@ __device__ void chol_upper_64(double (*S)[OR_MAX + 1], double* __restrict__ Rm, 
             const double* rk = rowk[k & 1];
             double d = rk[k];
             if (!(d > shift)) { d = shift > 0.0 ? shift : 1e-300; bad = 1; }
-            const double rs = fast_rsqrt(d);
-            const double id = rs * rs;
+            const double rs = fast_rsqrt1(d);
             // row k of R goes out (threads 0..63, one column each)
             if (tid >= k && tid < R) Rm[k * R + tid] = tid == k ? d * rs : rk[tid] * rs;
             if (tid == k) invd[k] = rs;
             double ri[4], rj[4];
 #pragma unroll
-            for (int x = 0; x < 4; ++x) { ri[x] = rk[ti + 16 * x] * id; rj[x] = rk[tj + 16 * x]; }
+            for (int x = 0; x < 4; ++x) { ri[x] = rk[ti + 16 * x] * rs; rj[x] = rk[tj + 16 * x] * rs; }      // rows of R itself
 #pragma unroll
             for (int x = 0; x < 4; ++x)
 #pragma unroll
@@ -272,6 +280,18 @@ power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const
     const int r = tid >> 4, cl = (tid & 15) * 2, ch = 32 + cl;
     const int64_t row0 = (int64_t)blockIdx.x * PS_ROWS;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    // pipelined path: warps 0-3 take the even k, warps 4-7 the odd k; thread = rows {2 rp, 2 rp + 1} x the same four
+    // columns, two accumulator sets alternating along k.  (One row x 4 columns over all k was a chain of 512
+    // dependent DFMAs per accumulator with 8 independent ones per scheduler — latency-bound at 40 % of the pipe —
+    // and needed 5 shared-memory wavefronts per 4 DFMAs; this is 6 per 8, with 32 independent DFMAs per scheduler.)
+    const int khalf = tid >> 7, rp = (tid & 127) >> 4;
+    double acc2[2][2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) acc2[i][j][t] = 0.0;
     const long long t_start = clock64();
     double* stage0 = reinterpret_cast<double*>(ps_smem);
     const int nchunks = (int)((n + PS_KC - 1) / PS_KC);
@@ -305,17 +325,45 @@ power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const
             __syncthreads();                       // chunk c has landed for everyone; chunk c - 1 is fully consumed
             if (c + PS_STAGES - 1 < nchunks) issue(c + PS_STAGES - 1); else asm volatile("cp.async.commit_group;" ::: "memory");
             const double* us = stage0 + (c % PS_STAGES) * PS_STAGE_DOUBLES;
-            const double* gs = us + PS_KC * OR_MAX + r * PS_GLD;
-#pragma unroll 8
-            for (int kk = 0; kk < PS_KC; ++kk) {
-                const double g = gs[kk];
-                const double2 u0 = *reinterpret_cast<const double2*>(us + kk * OR_MAX + cl);
-                const double2 u1 = *reinterpret_cast<const double2*>(us + kk * OR_MAX + ch);
-                acc[0] = fma(g, u0.x, acc[0]); acc[1] = fma(g, u0.y, acc[1]);
-                acc[2] = fma(g, u1.x, acc[2]); acc[3] = fma(g, u1.y, acc[3]);
+            const double* g0 = us + PS_KC * OR_MAX + (2 * rp) * PS_GLD;
+            const double* g1 = g0 + PS_GLD;
+#pragma unroll 4
+            for (int k4 = 0; k4 < PS_KC; k4 += 4) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int kk = k4 + 2 * i + khalf;
+                    const double ga = g0[kk], gb = g1[kk];
+                    const double2 u0 = *reinterpret_cast<const double2*>(us + kk * OR_MAX + cl);
+                    const double2 u1 = *reinterpret_cast<const double2*>(us + kk * OR_MAX + ch);
+                    acc2[i][0][0] = fma(ga, u0.x, acc2[i][0][0]); acc2[i][0][1] = fma(ga, u0.y, acc2[i][0][1]);
+                    acc2[i][0][2] = fma(ga, u1.x, acc2[i][0][2]); acc2[i][0][3] = fma(ga, u1.y, acc2[i][0][3]);
+                    acc2[i][1][0] = fma(gb, u0.x, acc2[i][1][0]); acc2[i][1][1] = fma(gb, u0.y, acc2[i][1][1]);
+                    acc2[i][1][2] = fma(gb, u1.x, acc2[i][1][2]); acc2[i][1][3] = fma(gb, u1.y, acc2[i][1][3]);
+                }
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+        // fold the two accumulator sets, then the two k halves (through shared memory, over the consumed stages)
+        __syncthreads();
+        double* fold = stage0 + PS_ROWS * OR_MAX;                    // behind the Zs tile written below
+        if (khalf == 1) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) fold[((tid & 127) * 2 + j) * 4 + t] = acc2[0][j][t] + acc2[1][j][t];
+        }
+        __syncthreads();
+        if (khalf == 0) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const double v = (acc2[0][j][t] + acc2[1][j][t]) + fold[((tid & 127) * 2 + j) * 4 + t];
+                    const int rr = 2 * rp + j, c = (t < 2 ? cl : ch) + (t & 1);
+                    stage0[rr * OR_MAX + c] = v;                     // the Zs tile (nobody reads the stages any more)
+                    if (row0 + rr < n && c < p) Z[(row0 + rr) * p + c] = v;
+                }
+        }
     } else {
         double* Us0 = stage0;                                        // [PS_KC][64]
         double* Gs0 = Us0 + PS_KC * OR_MAX;                          // [PS_ROWS][PS_GLD]
@@ -344,11 +392,13 @@ power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const
     __syncthreads();
     // the Z block: to global, and into shared memory (over the U tile) for its Gram partial
     double* Zs = Us;                                                 // [PS_ROWS][64]
+    if (!pipelined) {
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const int c = (t < 2 ? cl : ch) + (t & 1);
-        Zs[r * OR_MAX + c] = acc[t];
-        if (row0 + r < n && c < p) Z[(row0 + r) * p + c] = acc[t];
+        for (int t = 0; t < 4; ++t) {
+            const int c = (t < 2 ? cl : ch) + (t & 1);
+            Zs[r * OR_MAX + c] = acc[t];
+            if (row0 + r < n && c < p) Z[(row0 + r) * p + c] = acc[t];
+        }
     }
     __syncthreads();
     {

@@ -176,7 +176,7 @@ def test_mttkrp_vs_oracle(shape, rank, dtype, path):
         out = host(tb.unfolding_dot_khatri_rao(xd, (wd, fd), mode))
         err = rel_fro(out, ref)
         assert err <= TOL[np.dtype(dtype)], (shape, rank, mode, tb.last_kernel_path(), err)
-        assert tb.last_kernel_path() in ("simt", "tcgen05")
+        assert tb.last_kernel_path() in ("simt", "dmma", "tcgen05", "tcgen05-f16")
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
@@ -684,7 +684,7 @@ def test_reference_parafac_runs_unmodified_on_backend(tl_b200, golden):
         ref = g[f"{tag}/errors"]
         got = np.array([float(e) for e in errs])
         assert np.max(np.abs(got - ref) / ref) <= 1e-4
-        assert tb.last_kernel_path() in ("simt", "tcgen05")
+        assert tb.last_kernel_path() in ("simt", "dmma", "tcgen05", "tcgen05-f16")
 
 
 def test_reference_parafac_on_backend_with_dimension_tree_cache(tl_b200, golden):
@@ -735,7 +735,7 @@ def test_reference_nn_parafac_and_tucker_run_unmodified_on_backend(tl_b200, gold
     assert abs(float(torch.linalg.norm(core)) - float(g["tucker/core_norm"])) <= 1e-6 * float(g["tucker/core_norm"])
     (core2, factors2), errs2 = partial_tucker(dev(x), ranks[:2], modes=[0, 1], n_iter_max=3, init="svd", tol=0)
     assert tuple(core2.shape) == (ranks[0], ranks[1], x.shape[2])
-    assert tb.last_kernel_path() in ("simt", "tcgen05")
+    assert tb.last_kernel_path() in ("simt", "dmma", "tcgen05", "tcgen05-f16")
 
 
 def test_reference_tucker_with_gram_svd_plugin(tl_b200, golden):
