@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q -k "tucker or orthonormalize or hals or smoke" > gpurun_out/tests12.txt 2>&1; echo "tests rc=$?" >> gpurun_out/tests12.txt
 python scripts/ps_trace.py > gpurun_out/ps_trace3.txt 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:power_step_a -s 20 -c 1 -o gpurun_out/prof_ps_a python scripts/ps_trace.py > gpurun_out/ncu_ps.log 2>&1; echo "ncu rc=$?"
+echo skip ncu
 timeout 900 python bench.py --workload small --no-e2e --no-cpu --no-fp64 --no-refdriver --no-c2 > gpurun_out/bench12.json 2> gpurun_out/bench12.err; echo "bench rc=$?"
 grep -v "^$" gpurun_out/tests12.txt | tail -n 6; cat gpurun_out/ps_trace3.txt; tail -n 3 gpurun_out/bench12.err
 python - <<'P'

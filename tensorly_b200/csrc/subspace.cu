@@ -195,6 +195,65 @@ __device__ __forceinline__ double fast_rsqrt1(double d) {
     const double e = fma(-d * r, r, 1.0);
     return fma(0.5 * r, e, r);
 }
+// 1 / sqrt(d) and 1 / d from the hardware's double-precision seeds (MUFU.RSQ64H / RCP64H, ~2^-20) + one Newton step
+// each (~2^-40), as two INDEPENDENT chains: the trailing update needs only 1 / d, which is two dependent fp64 operations
+// after its seed, while the scaled row (which needs 1 / sqrt) leaves the critical path.  fp64 operations have a long
+// latency here, and the pivot loop of the Cholesky is one dependency chain.
+__device__ __forceinline__ void pivot_scales(double d, double& rs, double& id) {
+    if (!(d > 1e-280 && d < 1e280)) { rs = rsqrt(d); id = rs * rs; return; }
+    double r0, i0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(i0) : "d"(d));
+    id = fma(i0, fma(-d, i0, 1.0), i0);
+    rs = fma(0.5 * r0, fma(-d * r0, r0, 1.0), r0);
+}
+
+// pivots 16 KB .. 16 KB + 15.  KB is static, so everything a pivot of this block cannot touch is pruned at compile
+// time: register rows x < KB are finished, pairs with y < x lie below the diagonal (10 / 6 / 3 / 1 live pairs for
+// KB = 0..3 instead of 16 predicated ones — the loop was ~200 instructions per pivot and issue-bound).
+template <int KB>
+__device__ __forceinline__ void chol_block(double (&a)[4][4], double (*rowk)[OR_MAX], double* __restrict__ Rm,
+                                           double* __restrict__ invd, int R, double shift, int& bad, int ti, int tj, int tid) {
+#pragma unroll 1
+    for (int kl = 0; kl < 16; ++kl) {
+        const int k = 16 * KB + kl;
+        if (k >= R) break;
+        const double* rk = rowk[k & 1];
+        double d = rk[k];
+        if (!(d > shift)) { d = shift > 0.0 ? shift : 1e-300; bad = 1; }
+        double rs, id;
+        pivot_scales(d, rs, id);
+        // row k of R goes out (threads 0..63, one column each)
+        if (tid >= k && tid < R) Rm[k * R + tid] = tid == k ? d * rs : rk[tid] * rs;
+        if (tid == k) invd[k] = rs;
+        double ri[4], rj[4];
+#pragma unroll
+        for (int x = KB; x < 4; ++x) { ri[x] = rk[ti + 16 * x]; rj[x] = rk[tj + 16 * x]; }
+#pragma unroll
+        for (int x = KB; x < 4; ++x)
+#pragma unroll
+            for (int y = x; y < 4; ++y) {
+                const bool on = (x > KB || ti > kl) && (y > x || tj >= ti);
+                // the products do not wait for the pivot's reciprocal
+                if (on) a[x][y] = fma(-(ri[x] * rj[y]), id, a[x][y]);
+            }
+        // publish row k + 1 into the other buffer: its owners are the 16 threads with ti == (k + 1) % 16
+        if (k + 1 < R) {
+            if (kl < 15) {
+                if (ti == kl + 1) {
+#pragma unroll
+                    for (int y = KB; y < 4; ++y) rowk[(k + 1) & 1][tj + 16 * y] = a[KB][y];
+                }
+            } else if (KB < 3) {
+                if (ti == 0) {
+#pragma unroll
+                    for (int y = KB + 1; y < 4; ++y) rowk[(k + 1) & 1][tj + 16 * y] = a[KB < 3 ? KB + 1 : 3][y];
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
 
 __device__ void chol_upper_64(double (*S)[OR_MAX + 1], double* __restrict__ Rm, double* __restrict__ invd, int R,
                               int* bad_out) {
@@ -224,43 +283,10 @@ __device__ void chol_upper_64(double (*S)[OR_MAX + 1], double* __restrict__ Rm, 
         for (int y = 0; y < 4; ++y) rowk[0][tj + 16 * y] = a[0][y];
     }
     __syncthreads();
-#pragma unroll 1
-    for (int kb = 0; kb < 4; ++kb) {                 // k = 16 kb + kl: the register index kb is static inside the body
-#pragma unroll 1
-        for (int kl = 0; kl < 16; ++kl) {
-            const int k = 16 * kb + kl;
-            if (k >= R) break;
-            const double* rk = rowk[k & 1];
-            double d = rk[k];
-            if (!(d > shift)) { d = shift > 0.0 ? shift : 1e-300; bad = 1; }
-            const double rs = fast_rsqrt1(d);
-            // row k of R goes out (threads 0..63, one column each)
-            if (tid >= k && tid < R) Rm[k * R + tid] = tid == k ? d * rs : rk[tid] * rs;
-            if (tid == k) invd[k] = rs;
-            double ri[4], rj[4];
-#pragma unroll
-            for (int x = 0; x < 4; ++x) { ri[x] = rk[ti + 16 * x] * rs; rj[x] = rk[tj + 16 * x] * rs; }      // rows of R itself
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) {
-                    const int i = ti + 16 * x, j = tj + 16 * y;
-                    if (i > k && j >= i) a[x][y] = fma(-ri[x], rj[y], a[x][y]);
-                }
-            // publish row k + 1 (owners: ti == (k + 1) % 16, register row (k + 1) / 16) into the other buffer
-            const int kn = k + 1;
-            if (kn < R && ti == (kn & 15)) {
-                const int xn = kn >> 4;
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-                    if (x == xn) {
-#pragma unroll
-                        for (int y = 0; y < 4; ++y) rowk[kn & 1][tj + 16 * y] = a[x][y];
-                    }
-            }
-            __syncthreads();
-        }
-    }
+    chol_block<0>(a, rowk, Rm, invd, R, shift, bad, ti, tj, tid);
+    if (R > 16) chol_block<1>(a, rowk, Rm, invd, R, shift, bad, ti, tj, tid);
+    if (R > 32) chol_block<2>(a, rowk, Rm, invd, R, shift, bad, ti, tj, tid);
+    if (R > 48) chol_block<3>(a, rowk, Rm, invd, R, shift, bad, ti, tj, tid);
     if (tid == 0 && bad_out) *bad_out = bad;
 }
 
@@ -404,14 +430,28 @@ power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const
     {
         double* mine = partial + (size_t)blockIdx.x * p * p;
         const int a0 = tid >> 4, b0 = tid & 15;                      // outputs (a0 + 16 x, b0 + 16 y)
+        // 16 independent accumulators per thread (the 16-deep chains one after the other cost more than the GEMM)
+        double sacc[4][4];
+#pragma unroll
         for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) sacc[x][y] = 0.0;
+#pragma unroll 4
+        for (int i = 0; i < PS_ROWS; ++i) {
+            double za[4], zb[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) { za[x] = Zs[i * OR_MAX + a0 + 16 * x]; zb[x] = Zs[i * OR_MAX + b0 + 16 * x]; }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) sacc[x][y] = fma(za[x], zb[y], sacc[x][y]);
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
             for (int y = 0; y < 4; ++y) {
                 const int a = a0 + 16 * x, b = b0 + 16 * y;
-                if (a >= p || b >= p) continue;
-                double sacc = 0.0;
-#pragma unroll
-                for (int i = 0; i < PS_ROWS; ++i) sacc = fma(Zs[i * OR_MAX + a], Zs[i * OR_MAX + b], sacc);
-                mine[a * p + b] = sacc;
+                if (a < p && b < p) mine[a * p + b] = sacc[x][y];
             }
     }
     __threadfence();
