@@ -162,9 +162,12 @@ orth_apply_kernel(const T* __restrict__ z, int64_t rows, int R, int64_t rs, int6
 // launches instead of the five (TTM prep + TTM + 2 orth kernels + copies) the generic entry points would take.
 constexpr int PS_ROWS = 16;
 constexpr int PS_KC = 64;
-constexpr int PS_GLD = 66;                                          // G tile row stride: 528 bytes, 16-byte aligned
+// tile row strides of 68 doubles (544 bytes, 16-byte aligned): 136 words = 8 mod 32, so the 16 fragment loads of a
+// half-warp (4 k x 4 rows / columns) hit 32 distinct banks
+constexpr int PS_GLD = 68;
+constexpr int PS_ULD = 68;
 constexpr int PS_STAGES = 3;
-constexpr int PS_STAGE_DOUBLES = PS_KC * OR_MAX + PS_ROWS * PS_GLD;  // 5152 doubles = 41 216 bytes
+constexpr int PS_STAGE_DOUBLES = PS_KC * PS_ULD + PS_ROWS * PS_GLD;  // 5440 doubles = 43 520 bytes
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
     const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -290,6 +293,11 @@ __device__ void chol_upper_64(double (*S)[OR_MAX + 1], double* __restrict__ Rm, 
     if (tid == 0 && bad_out) *bad_out = bad;
 }
 
+__device__ __forceinline__ void ps_dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
 __global__ void __launch_bounds__(256)
 power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const double* __restrict__ U, int p,
                     int64_t u_ld, double* __restrict__ Z, double* __restrict__ partial, double* __restrict__ ssum,
@@ -306,19 +314,10 @@ power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const
     const int r = tid >> 4, cl = (tid & 15) * 2, ch = 32 + cl;
     const int64_t row0 = (int64_t)blockIdx.x * PS_ROWS;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    // pipelined path: warps 0-3 take the even k, warps 4-7 the odd k; thread = rows {2 rp, 2 rp + 1} x the same four
-    // columns, two accumulator sets alternating along k.  (One row x 4 columns over all k was a chain of 512
-    // dependent DFMAs per accumulator with 8 independent ones per scheduler — latency-bound at 40 % of the pipe —
-    // and needed 5 shared-memory wavefronts per 4 DFMAs; this is 6 per 8, with 32 independent DFMAs per scheduler.)
-    const int khalf = tid >> 7, rp = (tid & 127) >> 4;
-    double acc2[2][2][4];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-            for (int t = 0; t < 4; ++t) acc2[i][j][t] = 0.0;
+    const int lane = tid & 31, warp = tid >> 5, g8 = lane >> 2, q4 = lane & 3;      // DMMA fragment coordinates
+    double cacc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};     // [k4 parity][row tile][2]
     const long long t_start = clock64();
+    long long t_loop = t_start, t_z = t_start;
     double* stage0 = reinterpret_cast<double*>(ps_smem);
     const int nchunks = (int)((n + PS_KC - 1) / PS_KC);
     if (pipelined) {
@@ -329,12 +328,12 @@ power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const
         __syncthreads();
         auto issue = [&](int chunk) {
             double* us = stage0 + (chunk % PS_STAGES) * PS_STAGE_DOUBLES;
-            double* gs = us + PS_KC * OR_MAX;
+            double* gs = us + PS_KC * PS_ULD;
             const int64_t k0 = (int64_t)chunk * PS_KC;
             for (int e = tid; e < PS_KC * pc; e += 256) {
                 const int kk = e / pc, c2 = e - kk * pc;
                 const bool ok = k0 + kk < n;
-                cp_async16(us + kk * OR_MAX + 2 * c2, U + (ok ? (k0 + kk) * u_ld + 2 * c2 : 0), ok);
+                cp_async16(us + kk * PS_ULD + 2 * c2, U + (ok ? (k0 + kk) * u_ld + 2 * c2 : 0), ok);
             }
             for (int e = tid; e < PS_ROWS * (PS_KC / 2); e += 256) {
                 const int rr = e / (PS_KC / 2), k2 = e - rr * (PS_KC / 2);
@@ -349,47 +348,34 @@ power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const
         for (int c = 0; c < nchunks; ++c) {
             asm volatile("cp.async.wait_group %0;" ::"n"(PS_STAGES - 2) : "memory");
             __syncthreads();                       // chunk c has landed for everyone; chunk c - 1 is fully consumed
-            if (c + PS_STAGES - 1 < nchunks) issue(c + PS_STAGES - 1); else asm volatile("cp.async.commit_group;" ::: "memory");
+            if (c + PS_STAGES - 1 < nchunks && pipelined != 2) issue(c + PS_STAGES - 1); else asm volatile("cp.async.commit_group;" ::: "memory");
+            if (pipelined == 3) continue;
             const double* us = stage0 + (c % PS_STAGES) * PS_STAGE_DOUBLES;
-            const double* g0 = us + PS_KC * OR_MAX + (2 * rp) * PS_GLD;
-            const double* g1 = g0 + PS_GLD;
+            const double* gs = us + PS_KC * PS_ULD;
+            // warp w: columns [8 w, 8 w + 8) of both 8-row tiles, all of k — DMMA.8x8x4 fragments straight from the
+            // tiles (3 LDS.64 per 512 FMAs; the FMA version needed 12 shared-memory wavefronts per 256 and was bound
+            // by them: 27 of the 35 kclk of this loop)
 #pragma unroll 4
-            for (int k4 = 0; k4 < PS_KC; k4 += 4) {
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int kk = k4 + 2 * i + khalf;
-                    const double ga = g0[kk], gb = g1[kk];
-                    const double2 u0 = *reinterpret_cast<const double2*>(us + kk * OR_MAX + cl);
-                    const double2 u1 = *reinterpret_cast<const double2*>(us + kk * OR_MAX + ch);
-                    acc2[i][0][0] = fma(ga, u0.x, acc2[i][0][0]); acc2[i][0][1] = fma(ga, u0.y, acc2[i][0][1]);
-                    acc2[i][0][2] = fma(ga, u1.x, acc2[i][0][2]); acc2[i][0][3] = fma(ga, u1.y, acc2[i][0][3]);
-                    acc2[i][1][0] = fma(gb, u0.x, acc2[i][1][0]); acc2[i][1][1] = fma(gb, u0.y, acc2[i][1][1]);
-                    acc2[i][1][2] = fma(gb, u1.x, acc2[i][1][2]); acc2[i][1][3] = fma(gb, u1.y, acc2[i][1][3]);
-                }
+            for (int k4 = 0; k4 < PS_KC / 4; ++k4) {
+                const int kk = k4 * 4 + q4;
+                const double b = us[kk * PS_ULD + warp * 8 + g8];
+                const double a0 = gs[g8 * PS_GLD + kk], a1 = gs[(8 + g8) * PS_GLD + kk];
+                ps_dmma(cacc[k4 & 1][0][0], cacc[k4 & 1][0][1], a0, b);
+                ps_dmma(cacc[k4 & 1][1][0], cacc[k4 & 1][1][1], a1, b);
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        // fold the two accumulator sets, then the two k halves (through shared memory, over the consumed stages)
-        __syncthreads();
-        double* fold = stage0 + PS_ROWS * OR_MAX;                    // behind the Zs tile written below
-        if (khalf == 1) {
+        t_loop = clock64();
+        __syncthreads();                       // nobody reads the stages any more: the Z tile goes over stage 0
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                for (int t = 0; t < 4; ++t) fold[((tid & 127) * 2 + j) * 4 + t] = acc2[0][j][t] + acc2[1][j][t];
-        }
-        __syncthreads();
-        if (khalf == 0) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const double v = (acc2[0][j][t] + acc2[1][j][t]) + fold[((tid & 127) * 2 + j) * 4 + t];
-                    const int rr = 2 * rp + j, c = (t < 2 ? cl : ch) + (t & 1);
-                    stage0[rr * OR_MAX + c] = v;                     // the Zs tile (nobody reads the stages any more)
-                    if (row0 + rr < n && c < p) Z[(row0 + rr) * p + c] = v;
-                }
-        }
+            for (int h = 0; h < 2; ++h) {
+                const double v = cacc[0][mt][h] + cacc[1][mt][h];
+                const int rr = mt * 8 + g8, c = warp * 8 + 2 * q4 + h;
+                stage0[rr * OR_MAX + c] = v;
+                if (row0 + rr < n && c < p) Z[(row0 + rr) * p + c] = v;
+            }
     } else {
         double* Us0 = stage0;                                        // [PS_KC][64]
         double* Gs0 = Us0 + PS_KC * OR_MAX;                          // [PS_ROWS][PS_GLD]
@@ -417,6 +403,7 @@ power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const
     double* Us = stage0;
     __syncthreads();
     // the Z block: to global, and into shared memory (over the U tile) for its Gram partial
+    t_z = clock64();
     double* Zs = Us;                                                 // [PS_ROWS][64]
     if (!pipelined) {
 #pragma unroll
@@ -493,7 +480,7 @@ power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const
         if (tid == 0) *counter = 0u;
     }
     __syncthreads();
-    if (tid == 0) { g_ps_trace[0] = t_start; g_ps_trace[1] = t_gemm; }
+    if (tid == 0) { g_ps_trace[0] = t_start; g_ps_trace[1] = t_gemm; g_ps_trace[6] = t_loop; g_ps_trace[7] = t_z; }
     PS_TRACE(2);
     chol_upper_64(S, rinv, rinv + (size_t)p * p, p, status);          // rinv buffer: [R factor, p x p][1 / diagonal, p]
     PS_TRACE(3);
@@ -714,8 +701,13 @@ extern "C" int tlb200_subspace_iterate(const void* g, int64_t n, int64_t g_ld, v
     constexpr int smem_a = PS_STAGES * PS_STAGE_DOUBLES * (int)sizeof(double);    // 123 648 bytes: 3 GEMM stages
     static_assert(smem_a >= 2 * OR_MAX * (OR_MAX + 1) * (int)sizeof(double), "the factoring phase reuses the stages");
     // cp.async moves 16-byte pieces: rows of G and U must start 16-byte aligned
-    const int pipelined = g_ld % 2 == 0 && u_ld % 2 == 0 && reinterpret_cast<uintptr_t>(g) % 16 == 0 &&
-                          reinterpret_cast<uintptr_t>(u) % 16 == 0;
+    int pipelined = g_ld % 2 == 0 && u_ld % 2 == 0 && reinterpret_cast<uintptr_t>(g) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(u) % 16 == 0;
+    if (pipelined) {     // perf triage: 2 = load only the first stages (compute-only timing), 3 = loads only
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("TLB200_PS_DEBUG"); dbg = e ? atoi(e) : 0; }
+        if (dbg == 2 || dbg == 3) pipelined = dbg;
+    }
     static std::atomic<uint64_t> attr_done{0};
     if (ensure_dynamic_smem(power_step_a_kernel, smem_a, attr_done)) return TLB200_ECUDA;
     const int nblk = (int)ceil_div(n, PS_ROWS);
