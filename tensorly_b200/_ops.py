@@ -598,7 +598,7 @@ class RangeHint:
     tlb200_hint_tensor_absmax).  The owner promises not to change the tensor while the hint is registered — the
     ALS drivers hold one for their (constant) input tensor.  `TLB200_DISABLE_HF=1` turns the engine off."""
 
-    _live: dict = {}            # base pointer -> id of the RangeHint that registered it last
+    _live: dict = {}            # base pointer -> [(id of hint, absmax tensor), ...] in registration order
 
     def __init__(self, x: torch.Tensor, hold: bool = True):
         self.ptr = None
@@ -608,16 +608,25 @@ class RangeHint:
         self._x = x if hold else None
         _lib.check(_lib.load().tlb200_hint_tensor_absmax(x.data_ptr(), self.absmax.data_ptr()), "hint_tensor_absmax")
         self.ptr = x.data_ptr()
-        RangeHint._live[self.ptr] = id(self)
+        RangeHint._live.setdefault(self.ptr, []).append((id(self), self.absmax))
         if not hold:
             weakref.finalize(x, RangeHint._withdraw, self.ptr, id(self))
 
     @staticmethod
     def _withdraw(ptr, owner):
+        """Several owners may hold a hint for the same tensor (two drivers on one input): the registration survives
+        until the last of them lets go, and always points at a live scalar."""
         try:
-            if RangeHint._live.get(ptr) == owner:
+            entries = RangeHint._live.get(ptr)
+            if not entries:
+                return
+            entries[:] = [e for e in entries if e[0] != owner]
+            lib = _lib.load()
+            if entries:
+                lib.tlb200_hint_tensor_absmax(ptr, entries[-1][1].data_ptr())
+            else:
                 del RangeHint._live[ptr]
-                _lib.load().tlb200_hint_tensor_absmax(ptr, None)
+                lib.tlb200_hint_tensor_absmax(ptr, None)
         except Exception:               # interpreter shutdown
             pass
 

@@ -1203,3 +1203,22 @@ def test_fp16_engine_in_the_driver():
         finally:
             os.environ.pop("TLB200_HF_MIN_RANK", None)
     assert max(abs(a - b) / b for a, b in zip(*runs)) <= 1e-5, runs
+
+
+def test_range_hint_survives_a_second_owner():
+    """Two drivers on one tensor: the hint stays registered until the last of them lets go."""
+    g = torch.Generator(device="cuda").manual_seed(14)
+    x = torch.rand((256, 192, 320), generator=g, device="cuda")
+    fs = [torch.rand(s, 64, generator=g, device="cuda") for s in x.shape]
+    a = tb.RangeHint(x)
+    b = tb.RangeHint(x)
+    b.close()
+    tb.unfolding_dot_khatri_rao(x, (None, fs), 1)
+    assert tb.last_kernel_path() == "tcgen05-f16"
+    c = tb.RangeHint(x)
+    a.close()
+    tb.unfolding_dot_khatri_rao(x, (None, fs), 1)
+    assert tb.last_kernel_path() == "tcgen05-f16"
+    c.close()
+    tb.unfolding_dot_khatri_rao(x, (None, fs), 1)
+    assert tb.last_kernel_path() == "tcgen05"
