@@ -631,6 +631,63 @@ def fp64_leg(env):
     return res
 
 
+def n4_leg(env):
+    """SURVEY 8(f) n4 kernels on a C2-like problem (512 x 1024 x 1024 fp32, rank 32): reconstruction (writes the tensor
+    once: HBM-write bound up to R ~ 16, FMA-bound above on the CUDA cores), the fused masked-ALS imputation pass (reads
+    tensor + mask, writes tensor), one masked sweep of the own driver, and one HALS mode update."""
+    import torch
+    import tensorly_b200 as tb
+    shape, R = (512, 1024, 1024), 32
+    g = torch.Generator(device=env.device).manual_seed(9)
+    x = torch.rand(shape, generator=g, device=env.device)
+    fs = [torch.rand((s, R), generator=g, device=env.device) for s in shape]
+    w = torch.ones(R, device=env.device)
+    res = {"shape": list(shape), "rank": R}
+
+    def timeit(fn, reps=5):
+        for _ in range(2):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+    n = x.numel()
+    peak, _ = measured_peak_hbm()
+    out = torch.empty_like(x)
+    ms = timeit(lambda: tb.cp_to_tensor((w, fs), out=out))
+    res["cp_to_tensor"] = {"ms": ms, "gbs_written": 4.0 * n / (ms * 1e-3) / 1e9, "tflops": 2.0 * R * n / (ms * 1e-3) / 1e12,
+                           "frac_of_hbm_peak": 4.0 * n / (ms * 1e-3) / 1e9 / peak,
+                           "bound": "fp32 FMA issue on the CUDA cores at this rank (2R flop per 4 bytes written)"}
+    mask = (torch.rand(shape, generator=g, device=env.device) > 0.1).to(torch.float32)
+    xi = x.clone()
+    ms = timeit(lambda: tb.cp_impute(xi, mask, (w, fs), out=xi))
+    res["cp_impute"] = {"ms": ms, "gbs": 12.0 * n / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": 12.0 * n / (ms * 1e-3) / 1e9 / peak,
+                        "what": "x*mask + rec*(1-mask) in place + both norms: 12 B per element, rec never materialised"}
+    st = tb.CPALS(x, w, fs, mask=mask)
+    for _ in range(2):
+        st.sweep(True)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(5):
+        st.sweep(True)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 5
+    res["masked_sweep"] = {"ms": ms, "sweeps_per_s": 1e3 / ms, "what": "own driver with mask=: dimension-tree sweep + one imputation pass"}
+    del st
+    grams = [tb.gram(f) for f in fs]
+    m = tb.unfolding_dot_khatri_rao(x, (None, fs), 0)
+    f0 = fs[0].clone()
+    ms = timeit(lambda: tb.hals_update(grams, 0, w, m, f0, n_iter_max=100, tol=1e-8), reps=3)
+    res["hals_update"] = {"ms": ms, "rows": shape[0], "what": "one kernel = the whole hals_nnls call of a mode update (<= 100 passes over the rank)"}
+    return res
+
+
 def tucker_leg(env, steps):
     """C3 (BASELINE configs[2]): tucker HOOI rank [64,64,64] on random 512^3 fp32 — the TTM tensor-core path.
     Own driver (TTM chains + Gram + subspace iteration on the hand-written kernels) and, beside it, the unmodified
@@ -875,6 +932,12 @@ def run_ours(args):
         del r2
         torch.cuda.empty_cache()
     fp64 = fp64_leg(env) if (env.rank == 0 and env.world == 1 and not args.no_fp64) else None
+    n4 = None
+    if env.rank == 0 and env.world == 1 and not args.no_n4:
+        try:
+            n4 = n4_leg(env)
+        except Exception as exc:          # a secondary block must never cost the headline line
+            n4 = {"unavailable": f"{type(exc).__name__}: {str(exc)[:160]}"}
     c3 = tucker_leg(env, args.steps) if (env.rank == 0 and env.world == 1 and not args.no_c3) else None
     clocks = env.sampler.stop() if env.sampler else None
 
@@ -922,6 +985,7 @@ def run_ours(args):
             "c2": c2,
             "c3": c3,
             "fp64": fp64,
+            "n4": n4,
         }
         print(json.dumps(line), flush=True)
     if env.world > 1:
@@ -952,6 +1016,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-c2", action="store_true")
     ap.add_argument("--no-fp64", action="store_true")
+    ap.add_argument("--no-n4", action="store_true", help="skip the reconstruction / imputation / HALS block")
     ap.add_argument("--no-c3", action="store_true")
     ap.add_argument("--no-sustained", action="store_true")
     ap.add_argument("--no-refdriver", action="store_true")

@@ -12,9 +12,10 @@ import tensorly_b200 as tb
 
 torch.manual_seed(0)
 paths = set()
-for shape in [(128, 64, 96), (64, 36, 100)]:
+for shape, hinted in [((128, 64, 96), False), ((64, 36, 100), False), ((128, 64, 96), True), ((96, 64, 128), True)]:
     for R in (32, 64):
         x = torch.randn(shape, device="cuda")
+        hint = tb.RangeHint(x) if hinted else None        # the fp16-split engine (64-element tiles: inner extent % 32 == 0)
         fs = [torch.randn(s, R, device="cuda") for s in shape]
         w = torch.rand(R, device="cuda") + 0.5
         letters = "ijk"
@@ -37,6 +38,27 @@ for shape in [(128, 64, 96), (64, 36, 100)]:
             a = tb.mttkrp_from_ttm(t, (w, fs), mode)
             b = tb.unfolding_dot_khatri_rao(x, (w, fs), mode)
             assert float(torch.linalg.norm(a - b) / torch.linalg.norm(b)) < 1e-5
+        if hint is not None:
+            hint.close()
+# fp64 on DMMA (cp.async and register-staged variants: even / odd strides)
+for shape in [(64, 48, 96), (33, 47, 51)]:
+    x = torch.randn(shape, device="cuda", dtype=torch.float64)
+    fs = [torch.randn(s, 32, device="cuda", dtype=torch.float64) for s in shape]
+    for mode in range(3):
+        got = tb.unfolding_dot_khatri_rao(x, (None, fs), mode)
+        paths.add(tb.last_kernel_path())
+        ops = [fs[m] for m in range(3) if m != mode]
+        sub = ",".join(f"{'ijk'[m]}r" for m in range(3) if m != mode)
+        ref = torch.einsum(f"ijk,{sub}->{'ijk'[mode]}r", x, *ops)
+        assert float(torch.linalg.norm(got - ref) / torch.linalg.norm(ref)) < 1e-12
+# HOOI power step (cp.async + DMMA + register Cholesky) and the own Tucker driver
+y = torch.rand(96, 512, device="cuda", dtype=torch.float64)
+u = tb.subspace_iterate(y @ y.T, tb.orthonormalize(torch.rand(96, 16, device="cuda", dtype=torch.float64)), 3)
+# one-pass Cholesky QR: the defect is cond(Z)^2 x eps (1e-9..1e-8 here); the drivers finish with a two-pass orthonormalize
+assert float(torch.linalg.norm(u.T @ u - torch.eye(16, device="cuda", dtype=torch.float64))) < 1e-6
+u = tb.orthonormalize(u)
+assert float(torch.linalg.norm(u.T @ u - torch.eye(16, device="cuda", dtype=torch.float64))) < 1e-10
+tb.tucker(torch.rand((48, 40, 56), device="cuda"), [8, 8, 8], n_iter_max=2, init="random", random_state=1, tol=0)
 x = torch.rand((128, 96, 160), device="cuda")
 fs = [torch.rand(s, 32, device="cuda") for s in x.shape]
 cp, errs = tb.parafac(x, 32, n_iter_max=4, init=(None, fs), tol=0, return_errors=True)
