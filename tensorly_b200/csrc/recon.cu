@@ -10,12 +10,13 @@
 //       mask, forms rec in registers, writes the imputed tensor and accumulates both norms; rec never
 //       exists in memory.
 //
-// Kernel: out viewed as a matrix [I_0][C], C = prod_{n>=1} I_n (contiguous), computed as a rank-R outer-product
-// GEMM with 128 x 128 tiles, 8 x 8 register micro-tiles, operands in shared memory ([r][row] / [r][col], rank
-// chunks of 32).  Arithmetic intensity is 2R flop per 4 (plain) or 12 (impute) bytes: the plain reconstruction
-// is FMA-bound on the CUDA cores at R >= 16 (the tcgen05 variant is future work), the imputation pass is
-// HBM-bound up to R ~ 32.
+// Kernel (this file: fp64, rank > 64, small problems): out viewed as a matrix [I_0][C], C = prod_{n>=1} I_n
+// (contiguous), computed as a rank-R outer-product GEMM with 128 x 128 tiles, 8 x 8 register micro-tiles, operands in
+// shared memory ([r][row] / [r][col], rank chunks of 32).  Arithmetic intensity is 2R flop per 4 (plain) or 12
+// (impute) bytes: FMA-bound on the CUDA cores at R >= 16 — large fp32 problems of rank <= 64 therefore take the
+// tensor-core kernel of recon_tc.cu (3.2x / 2.2x this one at 512 x 1024 x 1024, rank 32).
 #include "common.cuh"
+#include "recon_tc.cuh"
 
 namespace tlb200 {
 namespace {
@@ -269,8 +270,13 @@ extern "C" int tlb200_cp_to_tensor(const void* const* factors, const int64_t* sh
     if (!dtype_valid(dtype) || !out) return TLB200_EINVAL;
     int st = make_geom(factors, shape, f_row_stride, f_col_stride, ndim, rank, &g);
     if (st) return st;
-    set_last_path("simt");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (recon_tc_supported(shape, ndim, rank, dtype)) {
+        set_last_path("tcgen05");
+        return recon_tc_launch(factors, shape, f_row_stride, f_col_stride, ndim, rank, (const float*)weights, nullptr,
+                               (const float*)mask, (float*)out, nullptr, s);
+    }
+    set_last_path("simt");
     if (dtype == TLB200_F32)
         return launch<float>(g, rank, (const float*)weights, nullptr, (const float*)mask, (float*)out, nullptr, nullptr, s);
     return launch<double>(g, rank, (const double*)weights, nullptr, (const double*)mask, (double*)out, nullptr, nullptr, s);
@@ -292,9 +298,18 @@ extern "C" int tlb200_cp_impute(const void* x, const void* mask, const void* con
     int st = make_geom(factors, shape, f_row_stride, f_col_stride, ndim, rank, &g);
     if (st) return st;
     if (workspace_bytes < tlb200_cp_impute_workspace_bytes(shape, ndim)) return TLB200_EWORKSPACE;
-    set_last_path("simt");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     double* partial = static_cast<double*>(workspace);
+    if (recon_tc_supported(shape, ndim, rank, dtype)) {
+        set_last_path("tcgen05");
+        st = recon_tc_launch(factors, shape, f_row_stride, f_col_stride, ndim, rank, (const float*)weights,
+                             (const float*)x, (const float*)mask, (float*)out, partial, s);
+        if (st) return st;
+        impute_finish_kernel<float><<<1, 256, 0, s>>>(partial, (int64_t)recon_tc_grid(shape, ndim), (float*)stats);
+        TLB_CHECK_LAUNCH();
+        return TLB200_OK;
+    }
+    set_last_path("simt");
     if (dtype == TLB200_F32)
         return launch<float>(g, rank, (const float*)weights, (const float*)x, (const float*)mask, (float*)out, partial,
                              (float*)stats, s);

@@ -826,7 +826,11 @@ def test_cp_to_tensor_golden(golden):
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("shape,rank", [((96, 80, 112), 16), ((130, 70, 45), 10), ((40, 24, 20, 12), 33), ((300, 200), 64),
-                                        ((257, 129), 100)])
+                                        ((257, 129), 100),
+                                        # large enough for the tcgen05 variant (fp32, rank <= 64): aligned, ragged rows,
+                                        # odd column count (scalar stores), 4-way, 2-way
+                                        ((256, 96, 80), 32), ((200, 130, 52), 20), ((300, 77, 61), 64),
+                                        ((64, 32, 24, 40), 48), ((2000, 1100), 7)])
 def test_cp_to_tensor_and_impute_vs_oracle(shape, rank, dtype):
     rng = np.random.RandomState(17)
     fs = [(rng.random_sample((s, rank)) - 0.4).astype(dtype) for s in shape]
@@ -834,6 +838,17 @@ def test_cp_to_tensor_and_impute_vs_oracle(shape, rank, dtype):
     ref = O.cp_to_tensor((w, fs))
     out = tb.cp_to_tensor((dev(w), [dev(f) for f in fs]))
     assert rel_fro(host(out), ref) <= TOL[np.dtype(dtype)]
+    big = shape[0] >= 64 and np.prod(shape[1:]) >= 1024 and np.prod(shape) >= 2 ** 20
+    assert tb.last_kernel_path() == ("tcgen05" if (big and dtype == np.float32 and rank <= 64) else "simt")
+    if big:
+        # every row of the tensor on its own (a wrong tile or swizzle shows up as a few bad rows, not in the norm)
+        got = host(out).reshape(shape[0], -1).astype(np.float64)
+        want = ref.reshape(shape[0], -1).astype(np.float64)
+        rows = np.linalg.norm(got - want, axis=1) / np.maximum(np.linalg.norm(want, axis=1), 1e-30)
+        assert rows.max() <= 10 * TOL[np.dtype(dtype)], int(rows.argmax())
+        mask2 = (rng.random_sample(shape) > 0.5).astype(dtype)
+        got2 = tb.cp_to_tensor((dev(w), [dev(f) for f in fs]), mask=dev(mask2))
+        assert rel_fro(host(got2), ref * mask2) <= TOL[np.dtype(dtype)]
     x = rng.standard_normal(shape).astype(dtype)
     mask = (rng.random_sample(shape) > 0.3).astype(dtype)
     new_ref, nrm, unnorm = O.cp_impute(x, mask, (w, fs))
