@@ -668,6 +668,14 @@ def n4_leg(env):
     ms = timeit(lambda: tb.cp_impute(xi, mask, (w, fs), out=xi))
     res["cp_impute"] = {"ms": ms, "gbs": 12.0 * n / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": 12.0 * n / (ms * 1e-3) / 1e9 / peak,
                         "what": "x*mask + rec*(1-mask) in place + both norms: 12 B per element, rec never materialised"}
+    # the same two passes at rank 64 (two 32-wide contraction chunks, one Khatri-Rao stage)
+    fs64 = [torch.rand((s, 64), generator=g, device=env.device) for s in shape]
+    w64 = torch.ones(64, device=env.device)
+    ms = timeit(lambda: tb.cp_to_tensor((w64, fs64), out=out))
+    res["cp_to_tensor_rank64"] = {"ms": ms, "gbs_written": 4.0 * n / (ms * 1e-3) / 1e9}
+    ms = timeit(lambda: tb.cp_impute(xi, mask, (w64, fs64), out=xi))
+    res["cp_impute_rank64"] = {"ms": ms, "gbs": 12.0 * n / (ms * 1e-3) / 1e9}
+    del fs64
     st = tb.CPALS(x, w, fs, mask=mask)
     for _ in range(2):
         st.sweep(True)

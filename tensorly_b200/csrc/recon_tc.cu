@@ -7,15 +7,15 @@
 // Why: the SIMT kernel (recon.cu) is bound by fp32 FMA issue from rank 16 up — 1.2 TB/s of output at rank 32, and the
 // imputation pass it feeds was 80 % of a masked ALS sweep.  The product is a GEMM with a tiny contraction (K = R) and
 // a streaming output, so here the OUTPUT streams: a persistent CTA per SM walks 128 x 128 output tiles,
-//   warps 1-4  form the operand tiles in shared memory — the mode-0 factor tile (once per row block) and the
+//   warps 1-8  form the operand tiles in shared memory — the mode-0 factor tile (once per row block) and the
 //              Khatri-Rao tile of the tile's 128 columns (never materialised in memory), each split exactly into
 //              tf32 hi + lo and stored in the canonical K-major SWIZZLE_128B layout,
 //   warp 0     issues D[:, 0:256] = A_hi [K_hi | K_lo] and D[:, 128:256] += A_lo K_hi per 8-wide K step (3xTF32 with
 //              two instructions per step, like tc_stream.cu) into one of two TMEM accumulator sets,
-//   warps 5-8  drain the other set 32 columns at a time: hi*hi + cross columns, the epilogue variant, and the result
+//   warps 9-12 drain the other set 32 columns at a time: hi*hi + cross columns, the epilogue variant, and the result
 //              into a swizzled shared-memory slot that one thread hands to TMA (cp.async.bulk.tensor store): no
 //              global access is issued by a lane, so nothing waits on HBM latency and edges are clipped by TMA,
-//   warp 9     (imputation / masked variants) TMA-loads the x and mask boxes of the slots ahead of the epilogue.
+//   warp 13    (imputation / masked variants) TMA-loads the x and mask boxes of the slots ahead of the epilogue.
 // Bound: HBM (4 bytes written per element; 12 bytes moved for the imputation pass).
 #include "recon_tc.cuh"
 #include "tc_stream.cuh"
@@ -27,7 +27,7 @@ namespace tlb200 {
 namespace {
 
 constexpr int RT_M = 128, RT_N = 128;
-constexpr int RT_THREADS = 10 * 32;
+constexpr int RT_THREADS = 14 * 32;     // warp 0 MMA, 1-8 producers, 9-12 epilogue (one per TMEM lane quarter), 13 TMA loader
 constexpr int RT_SC = 32;             // columns staged per step
 constexpr int RT_SLD = RT_SC + 4;     // staging row pitch in floats (conflict-free 128-bit row writes)
 constexpr uint32_t RT_SPIN_LIMIT = 1u << 22;
@@ -70,6 +70,15 @@ __device__ __forceinline__ void rt_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 __device__ __forceinline__ void rt_tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(rt_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(rt_smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void rt_tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(rt_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(rt_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void rt_tma_store_3d(const void* src, const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(rt_smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void rt_tma_store_2d(const void* src, const CUtensorMap* map, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -114,13 +123,17 @@ struct ReconTcParams {
 // MODE 0: out = rec.   MODE 1: out = x*mask + rec*(1-mask) + the two norms.   MODE 2: out = rec * mask.
 // shared-memory plan per (CHUNKS, MODE): rank <= 32 double-buffers the Khatri-Rao tile; rank 33..64 needs twice the
 // operand bytes and keeps one stage (producer + MMA of a tile take less than the tile's HBM time)
-template <int CHUNKS, int MODE>
+// W = 128-byte lines per row and TMA box (1 or 2): rows of the tensor lie megabytes apart, and DRAM serves two adjacent
+// lines per row markedly better than one (measured for the tensor stream of tc_stream.cu: 6.8 against 4.5 TB/s)
+template <int CHUNKS, int MODE, int W>
 struct RtCfg {
     static constexpr int A_BYTES = CHUNKS * 16384;          // per part (hi or lo): [chunk][128 rows][128 B]
     static constexpr int B_STAGE = CHUNKS * 32768;          // [chunk][hi 128 rows | lo 128 rows][128 B]
     static constexpr int NB = CHUNKS == 1 ? 2 : 1;
-    static constexpr int SLOT = MODE == 0 ? 16384 : 32768;  // [out / x box: 128 rows x 128 B][mask box]
-    static constexpr int NS = (MODE == 0 || CHUNKS == 1) ? 4 : 3;
+    static constexpr int BOX = 16384 * W;                   // one box: [128 rows][W lines][128 B]
+    static constexpr int SLOT = MODE == 0 ? BOX : 2 * BOX;  // [out / x box][mask box]
+    static constexpr int NS = CHUNKS == 1 ? (128 * 1024) / SLOT > 4 ? 4 : (128 * 1024) / SLOT : (96 * 1024) / SLOT;
+    static_assert(NS >= 2, "at least two slots");
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = 2 * A_BYTES;
     static constexpr int OFF_SLOT = OFF_B + NB * B_STAGE;
@@ -130,12 +143,13 @@ struct RtCfg {
     static_assert(SMEM <= 227 * 1024, "smem budget");
 };
 
-template <int CHUNKS, int MODE>
+template <int CHUNKS, int MODE, int W>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_constant__ CUtensorMap x_map,
                 const __grid_constant__ CUtensorMap mask_map, const ReconTcParams p) {
-    using Cfg = RtCfg<CHUNKS, MODE>;
-    constexpr int A_BYTES = Cfg::A_BYTES, B_STAGE = Cfg::B_STAGE, NB = Cfg::NB, NS = Cfg::NS, SLOT = Cfg::SLOT;
+    using Cfg = RtCfg<CHUNKS, MODE, W>;
+    constexpr int A_BYTES = Cfg::A_BYTES, B_STAGE = Cfg::B_STAGE, NB = Cfg::NB, NS = Cfg::NS, SLOT = Cfg::SLOT, BOX = Cfg::BOX;
+    constexpr int PC = 32 * W;                  // columns per epilogue part (TMA path)
     constexpr int OFF_A = Cfg::OFF_A, OFF_B = Cfg::OFF_B, OFF_STG = Cfg::OFF_SLOT, OFF_BAR = Cfg::OFF_BAR;
     extern __shared__ unsigned char rt_smem_raw[];
     unsigned char* smem = rt_smem_raw + ((1024u - (rt_smem_u32(rt_smem_raw) & 1023u)) & 1023u);
@@ -157,9 +171,9 @@ recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_consta
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0 && lane == 0) {
-        rt_mbar_init(a_full, 128); rt_mbar_init(a_empty, 1);
+        rt_mbar_init(a_full, 256); rt_mbar_init(a_empty, 1);
         for (int i = 0; i < 2; ++i) {
-            rt_mbar_init(&b_full[i], 128); rt_mbar_init(&b_empty[i], 1);
+            rt_mbar_init(&b_full[i], 256); rt_mbar_init(&b_empty[i], 1);
             rt_mbar_init(&d_full[i], 1); rt_mbar_init(&d_empty[i], 128);
         }
         for (int i = 0; i < 4; ++i) { rt_mbar_init(&slot_full[i], 1); rt_mbar_init(&slot_free[i], 1); }
@@ -215,9 +229,9 @@ recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_consta
             __syncwarp();
             if (last_of_row) ++a_gen;
         }
-    } else if (warp <= 4) {
-        // ================= operand producers (128 threads) =================
-        // thread (rr, c): rows rr + 16 i of a tile, 16-byte chunk c (4 rank entries) — 8 threads read one 128-byte
+    } else if (warp <= 8) {
+        // ================= operand producers (256 threads: two warps per scheduler hide each other's latencies) =========
+        // thread (rr, c): rows rr + 32 i of a tile, 16-byte chunk c (4 rank entries) — 8 threads read one 128-byte
         // factor row together (coalesced), and the chunk goes to its swizzled place with one store (one thread per
         // row of 32 entries made every warp-level load touch 32 cache lines: the kernel was LSU-bound at 0.3 TB/s).
         const int pt = tid - 32, rr = pt >> 3, c = pt & 7;
@@ -259,8 +273,8 @@ recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_consta
                         wv.z = r0 + 2 < p.R ? __ldg(p.w + r0 + 2) : 0.f; wv.w = r0 + 3 < p.R ? __ldg(p.w + r0 + 3) : 0.f;
                     }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int row = rr + 16 * i;
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = rr + 32 * i;
                         const int64_t gi = rt * RT_M + row;
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (gi < p.I) {
@@ -279,44 +293,44 @@ recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_consta
             if (n >= NB) rt_mbar_wait(&b_empty[s], ((n / NB) - 1) & 1u);
             unsigned char* stage = b_smem + s * B_STAGE;
             if (p.ndim <= 3) {
-                // 2- and 3-way tensors: the 8 columns of this thread are 16 apart — one division per tile, then an
-                // odometer; all 16 factor-row loads are issued before the first product (two columns at a time was a
+                // 2- and 3-way tensors: the 4 columns of this thread are 32 apart — one division per tile, then an
+                // odometer; all 8 factor-row loads are issued before the first product (two columns at a time was a
                 // chain of exposed L2 round trips: the producers, not HBM, set the pace)
                 const bool three = p.ndim == 3;
                 const int64_t I2 = three ? p.shape[2] : 1;
                 const int64_t gc0 = ct * RT_N + rr;
                 int64_t j = three ? gc0 / I2 : gc0;
                 int64_t k = three ? gc0 - j * I2 : 0;
-                const float* r1[8];
-                const float* r2[8];
-                bool ok[8];
+                const float* r1[4];
+                const float* r2[4];
+                bool ok[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < 4; ++i) {
                     ok[i] = j < p.shape[1];
                     r1[i] = p.f[1] + (ok[i] ? j : 0) * p.rs[1];
                     r2[i] = three ? p.f[2] + k * p.rs[2] : p.f[1];
-                    if (three) { k += 16; while (k >= I2) { k -= I2; ++j; } } else j += 16;
+                    if (three) { k += 32; while (k >= I2) { k -= I2; ++j; } } else j += 32;
                 }
 #pragma unroll
                 for (int ch = 0; ch < CHUNKS; ++ch) {
                     const int r0 = ch * 32 + 4 * c;
-                    float4 u1[8], u2[8];
+                    float4 u1[4], u2[4];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < 4; ++i) {
                         u1[i] = ok[i] ? load4(r1[i], p.cs[1], r0, unit_cs) : make_float4(0.f, 0.f, 0.f, 0.f);
                         if (three) u2[i] = load4(r2[i], p.cs[2], r0, unit_cs);
                     }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < 4; ++i) {
                         float4 v = u1[i];
                         if (three) { v.x *= u2[i].x; v.y *= u2[i].y; v.z *= u2[i].z; v.w *= u2[i].w; }
-                        store_chunk(stage + ch * 32768, stage + ch * 32768 + 16384, rr + 16 * i, v);
+                        store_chunk(stage + ch * 32768, stage + ch * 32768 + 16384, rr + 32 * i, v);
                     }
                 }
             } else {
 #pragma unroll 2
-            for (int i = 0; i < 8; ++i) {
-                const int col = rr + 16 * i;
+            for (int i = 0; i < 4; ++i) {
+                const int col = rr + 32 * i;
                 const int64_t gc = ct * RT_N + col;
                 // factor rows of this column (last mode fastest)
                 const float* kp1 = nullptr;
@@ -354,21 +368,26 @@ recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_consta
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             rt_mbar_arrive(&b_full[s]);
         }
-    } else if (warp == 9) {
+    } else if (warp == 13) {
         // ================= TMA loader of the x / mask boxes (imputation / masked variants, TMA epilogue only) ==========
         if (MODE != 0 && p.use_tma) {
             uint32_t g = 0;                                   // global part counter of this CTA
             for (int64_t t = t_begin; t < t_end; ++t) {
                 const int64_t rt = t / p.col_tiles, ct = t - rt * p.col_tiles;
-                for (int part = 0; part < RT_N / RT_SC; ++part, ++g) {
+                for (int part = 0; part < RT_N / PC; ++part, ++g) {
                     const uint32_t k = g % NS;
                     if (g >= (uint32_t)NS) rt_mbar_wait(&slot_free[k], ((g / NS) - 1) & 1u);
                     if (rt_elect_one()) {
                         unsigned char* slot = slots + k * SLOT;
-                        rt_mbar_expect_tx(&slot_full[k], MODE == 1 ? 32768 : 16384);
-                        const int cx = (int)(ct * RT_N + part * RT_SC), cy = (int)(rt * RT_M);
-                        if (MODE == 1) rt_tma_load_2d(slot, &x_map, &slot_full[k], cx, cy);
-                        rt_tma_load_2d(slot + 16384, &mask_map, &slot_full[k], cx, cy);
+                        rt_mbar_expect_tx(&slot_full[k], MODE == 1 ? 2 * BOX : BOX);
+                        const int cx = (int)(ct * RT_N + part * PC), cy = (int)(rt * RT_M);
+                        if constexpr (W == 1) {
+                            if (MODE == 1) rt_tma_load_2d(slot, &x_map, &slot_full[k], cx, cy);
+                            rt_tma_load_2d(slot + BOX, &mask_map, &slot_full[k], cx, cy);
+                        } else {
+                            if (MODE == 1) rt_tma_load_3d(slot, &x_map, &slot_full[k], 0, cx / 32, cy);
+                            rt_tma_load_3d(slot + BOX, &mask_map, &slot_full[k], 0, cx / 32, cy);
+                        }
                     }
                     __syncwarp();
                 }
@@ -390,82 +409,70 @@ recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_consta
             const uint32_t s = n & 1u;
             rt_mbar_wait(&d_full[s], (n >> 1) & 1u);
             rt_fence_after();
+            const int64_t gi = rt * RT_M + row;
 #pragma unroll 1
-            for (int part = 0; part < RT_N / RT_SC; ++part, ++g) {
+            for (int part = 0; part < RT_N / PC; ++part, ++g) {
                 const uint32_t k = g % NS;
                 unsigned char* slot = slots + k * SLOT;
-                uint32_t r0[32], r1[32];
-                RT_TMEM_LD16(lane_addr + s * 256 + part * RT_SC, r0);                    // hi*hi
-                RT_TMEM_LD16(lane_addr + s * 256 + part * RT_SC + 16, (r0 + 16));
-                RT_TMEM_LD16(lane_addr + s * 256 + RT_N + part * RT_SC, r1);             // hi*lo + lo*hi
-                RT_TMEM_LD16(lane_addr + s * 256 + RT_N + part * RT_SC + 16, (r1 + 16));
                 if (MODE != 0) rt_mbar_wait(&slot_full[k], (g / NS) & 1u);               // x / mask boxes have landed
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (part == RT_N / RT_SC - 1) {                   // every column of the set has been read
-                    rt_fence_before();
-                    rt_mbar_arrive(&d_empty[s]);
-                }
-                float po[4] = {0.f, 0.f, 0.f, 0.f}, pr[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint32_t off = (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4);
-                    float v[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r0[4 * c + j]) + __uint_as_float(r1[4 * c + j]);
-                    if constexpr (MODE == 1) {
-                        const float4 xv = *reinterpret_cast<const float4*>(slot + off);
-                        const float4 mv = *reinterpret_cast<const float4*>(slot + 16384 + off);
-                        const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ms[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float rec = v[j];
-                            const float o = xs[j] * ms[j] + rec * (1.f - ms[j]);       // the reference's expression
-                            const float d = o - rec;
-                            po[j] = fmaf(o, o, po[j]);
-                            pr[j] = fmaf(d, d, pr[j]);
-                            v[j] = o;
-                        }
-                    } else if constexpr (MODE == 2) {
-                        const float4 mv = *reinterpret_cast<const float4*>(slot + 16384 + off);
-                        v[0] *= mv.x; v[1] *= mv.y; v[2] *= mv.z; v[3] *= mv.w;
+                for (int ko = 0; ko < W; ++ko) {                  // the W lines of this row: 32 columns each
+                    const int col0 = part * PC + ko * 32;
+                    uint32_t r0[32], r1[32];
+                    RT_TMEM_LD16(lane_addr + s * 256 + col0, r0);                        // hi*hi
+                    RT_TMEM_LD16(lane_addr + s * 256 + col0 + 16, (r0 + 16));
+                    RT_TMEM_LD16(lane_addr + s * 256 + RT_N + col0, r1);                 // hi*lo + lo*hi
+                    RT_TMEM_LD16(lane_addr + s * 256 + RT_N + col0 + 16, (r1 + 16));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (col0 + 32 == RT_N) {                      // every column of the set has been read
+                        rt_fence_before();
+                        rt_mbar_arrive(&d_empty[s]);
                     }
-                    *reinterpret_cast<float4*>(slot + off) = make_float4(v[0], v[1], v[2], v[3]);
-                }
-                if constexpr (MODE == 1) {
-                    // rows / columns beyond the tensor were zero-filled by TMA (x = mask = 0): they would add rec^2
-                    const int64_t gi = rt * RT_M + row;
-                    if (gi < p.I) {
-                        const int64_t gc = ct * RT_N + part * RT_SC;
-                        if (gc + RT_SC <= p.C) {
-                            s_out += (double)((po[0] + po[1]) + (po[2] + po[3]));
-                            s_res += (double)((pr[0] + pr[1]) + (pr[2] + pr[3]));
-                        } else {
-                            // ragged last part: redo the sums over the valid columns only (C % 4 == 0: whole chunks)
-                            float so = 0.f, sr = 0.f;
-                            for (int c = 0; c < 8; ++c) {
-                                if (gc + 4 * c >= p.C) break;
-                                const uint32_t off = (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4);
-                                const float4 ov = *reinterpret_cast<const float4*>(slot + off);
-                                const float o4[4] = {ov.x, ov.y, ov.z, ov.w};
-                                for (int j = 0; j < 4; ++j) {
-                                    const float rec = __uint_as_float(r0[4 * c + j]) + __uint_as_float(r1[4 * c + j]);
-                                    so = fmaf(o4[j], o4[j], so);
-                                    sr = fmaf(o4[j] - rec, o4[j] - rec, sr);
-                                }
+                    const int line = W * row + ko;                // [128 rows][W lines][128 B], chunk c at c ^ (line & 7)
+                    float po[4] = {0.f, 0.f, 0.f, 0.f}, pr[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint32_t off = (uint32_t)line * 128u + (uint32_t)((c ^ (line & 7)) << 4);
+                        float v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r0[4 * c + j]) + __uint_as_float(r1[4 * c + j]);
+                        if constexpr (MODE == 1) {
+                            const float4 xv = *reinterpret_cast<const float4*>(slot + off);
+                            const float4 mv = *reinterpret_cast<const float4*>(slot + BOX + off);
+                            const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ms[4] = {mv.x, mv.y, mv.z, mv.w};
+                            // chunks beyond the tensor were zero-filled by TMA (x = mask = 0) and are clipped on the
+                            // way out; they must not reach the norms (C % 4 == 0: whole chunks)
+                            const bool live = gi < p.I && ct * RT_N + col0 + 4 * c < p.C;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float rec = v[j];
+                                const float o = xs[j] * ms[j] + rec * (1.f - ms[j]);       // the reference's expression
+                                const float d = o - rec;
+                                if (live) { po[j] = fmaf(o, o, po[j]); pr[j] = fmaf(d, d, pr[j]); }
+                                v[j] = o;
                             }
-                            s_out += (double)so;
-                            s_res += (double)sr;
+                        } else if constexpr (MODE == 2) {
+                            const float4 mv = *reinterpret_cast<const float4*>(slot + BOX + off);
+                            v[0] *= mv.x; v[1] *= mv.y; v[2] *= mv.z; v[3] *= mv.w;
                         }
+                        *reinterpret_cast<float4*>(slot + off) = make_float4(v[0], v[1], v[2], v[3]);
+                    }
+                    if constexpr (MODE == 1) {
+                        // fp32 partial sums over 32 elements (4 independent chains), folded into doubles per line
+                        s_out += (double)((po[0] + po[1]) + (po[2] + po[3]));
+                        s_res += (double)((pr[0] + pr[1]) + (pr[2] + pr[3]));
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the slot is read by the async proxy next
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (storer) {
-                    rt_tma_store_2d(slot, &out_map, (int)(ct * RT_N + part * RT_SC), (int)(rt * RT_M));
+                    const int cx = (int)(ct * RT_N + part * PC), cy = (int)(rt * RT_M);
+                    if constexpr (W == 1) rt_tma_store_2d(slot, &out_map, cx, cy);
+                    else rt_tma_store_3d(slot, &out_map, 0, cx / 32, cy);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    // every store but this one has finished reading its slot: part g - 1's slot is free again
-                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    if (MODE != 0 && g >= 1) rt_mbar_arrive(&slot_free[(g - 1) % NS]);
+                    // the slot is free again as soon as the store has READ it (not when the data has landed)
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    if (MODE != 0) rt_mbar_arrive(&slot_free[k]);
                 }
             }
         }
@@ -605,14 +612,14 @@ recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_consta
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
-template <int CHUNKS, int MODE>
+template <int CHUNKS, int MODE, int W>
 int launch_one(const ReconTcParams& p, const CUtensorMap* maps, int grid, cudaStream_t stream) {
     // at least 120 KB: two of these CTAs must never share an SM (each allocates all 512 TMEM columns)
-    constexpr int need = RtCfg<CHUNKS, MODE>::SMEM;
+    constexpr int need = RtCfg<CHUNKS, MODE, W>::SMEM;
     constexpr int smem = need > 120 * 1024 ? need : 120 * 1024;
     static std::atomic<uint64_t> attr_done{0};
-    if (ensure_dynamic_smem(recon_tc_kernel<CHUNKS, MODE>, smem, attr_done)) return TLB200_ECUDA;
-    recon_tc_kernel<CHUNKS, MODE><<<grid, RT_THREADS, smem, stream>>>(maps[0], maps[1], maps[2], p);
+    if (ensure_dynamic_smem(recon_tc_kernel<CHUNKS, MODE, W>, smem, attr_done)) return TLB200_ECUDA;
+    recon_tc_kernel<CHUNKS, MODE, W><<<grid, RT_THREADS, smem, stream>>>(maps[0], maps[1], maps[2], p);
     TLB_CHECK_LAUNCH();
     return TLB200_OK;
 }
@@ -662,22 +669,42 @@ int recon_tc_launch(const void* const* factors, const int64_t* shape, const int6
     p.use_tma = tc_available() && p.C % 4 == 0 && p.C < (1LL << 31) && p.I < (1LL << 31) &&
                 reinterpret_cast<uintptr_t>(out) % 16 == 0 && (!x || reinterpret_cast<uintptr_t>(x) % 16 == 0) &&
                 (!mask || reinterpret_cast<uintptr_t>(mask) % 16 == 0) && !getenv("TLB200_RECON_NO_TMA");
+    // two lines per row and box where the extents allow it (C % 32 == 0) and shared memory holds the slots
+    // (rank <= 32, or the plain reconstruction whose slots carry no x / mask boxes)
+    static int w_cap = -1;
+    if (w_cap < 0) { const char* e = getenv("TLB200_RECON_LINES"); w_cap = e ? atoi(e) : 2; }
+    const int W = (p.use_tma && p.C % 32 == 0 && (rank <= 32 || mode == 0) && w_cap >= 2) ? 2 : 1;
     if (p.use_tma) {
-        const uint64_t dims[2] = {(uint64_t)p.C, (uint64_t)p.I}, strides[1] = {(uint64_t)p.C * 4};
-        const uint32_t box[2] = {32, 128};
-        int st = tc_encode_map(&maps[0], out, 2, dims, strides, box, true);
-        if (!st && x) st = tc_encode_map(&maps[1], x, 2, dims, strides, box, true);
-        if (!st && mask) st = tc_encode_map(&maps[2], mask, 2, dims, strides, box, true);
-        if (st) p.use_tma = 0;
+        int st;
+        const void* bases[3] = {out, x, mask};
+        for (int i = 0; i < 3; ++i) {
+            if (!bases[i]) continue;
+            if (W == 1) {
+                const uint64_t dims[2] = {(uint64_t)p.C, (uint64_t)p.I}, strides[1] = {(uint64_t)p.C * 4};
+                const uint32_t box[2] = {32, 128};
+                st = tc_encode_map(&maps[i], bases[i], 2, dims, strides, box, true);
+            } else {
+                const uint64_t dims[3] = {32, (uint64_t)p.C / 32, (uint64_t)p.I}, strides[2] = {128, (uint64_t)p.C * 4};
+                const uint32_t box[3] = {32, 2, 128};
+                st = tc_encode_map(&maps[i], bases[i], 3, dims, strides, box, true);
+            }
+            if (st) { p.use_tma = 0; break; }
+        }
     }
+    const int Wk = p.use_tma ? W : 1;
     if (rank <= 32) {
-        if (mode == 0) return launch_one<1, 0>(p, maps, grid, stream);
-        if (mode == 1) return launch_one<1, 1>(p, maps, grid, stream);
-        return launch_one<1, 2>(p, maps, grid, stream);
+        if (Wk == 2) {
+            if (mode == 0) return launch_one<1, 0, 2>(p, maps, grid, stream);
+            if (mode == 1) return launch_one<1, 1, 2>(p, maps, grid, stream);
+            return launch_one<1, 2, 2>(p, maps, grid, stream);
+        }
+        if (mode == 0) return launch_one<1, 0, 1>(p, maps, grid, stream);
+        if (mode == 1) return launch_one<1, 1, 1>(p, maps, grid, stream);
+        return launch_one<1, 2, 1>(p, maps, grid, stream);
     }
-    if (mode == 0) return launch_one<2, 0>(p, maps, grid, stream);
-    if (mode == 1) return launch_one<2, 1>(p, maps, grid, stream);
-    return launch_one<2, 2>(p, maps, grid, stream);
+    if (mode == 0) return Wk == 2 ? launch_one<2, 0, 2>(p, maps, grid, stream) : launch_one<2, 0, 1>(p, maps, grid, stream);
+    if (mode == 1) return launch_one<2, 1, 1>(p, maps, grid, stream);
+    return launch_one<2, 2, 1>(p, maps, grid, stream);
 }
 
 }  // namespace tlb200
