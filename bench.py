@@ -697,6 +697,50 @@ def n4_leg(env):
     return res
 
 
+def c4_leg(env, steps):
+    """C4 (BASELINE configs[3]): non_negative_parafac (multiplicative updates) rank 64 on a random 256^4 fp32 tensor
+    (17.2 GB): every mode's MTTKRP streams the tensor in place (mode 0 / middle / last views of a 4-way array; the
+    reference would materialise a 4.3 GB Khatri-Rao matrix and a 17 GB permuted copy per mode)."""
+    import torch
+    import tensorly_b200 as tb
+    shape, R = (256, 256, 256, 256), 64
+    x = device_slab(shape, 0, shape[0], torch.float32, env.device, seed=4)
+    g = torch.Generator(device=env.device).manual_seed(6)
+    fs = [torch.rand((s, R), generator=g, device=env.device) for s in shape]
+    w = torch.ones(R, device=env.device)
+    out = {"workload": "C4: non_negative_parafac rank 64 on random 256x256x256x256 fp32", "unit": UNIT}
+    st = tb.CPALS(x, w, fs, update="mu")
+    for _ in range(3):
+        st.sweep(True)
+    n = max(5, min(steps, 20))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(n):
+        st.sweep(True)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / n
+    out.update({"value": 1e3 / ms, "ms_per_step": ms, "steps": n, "final_rel_error": float(st.err[0])})
+    alg = 4.0 * (x.numel() + R * sum(shape))
+    per_mode = []
+    for mode in range(4):
+        for _ in range(2):
+            tb.unfolding_dot_khatri_rao(x, (None, st.factors), mode)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(3):
+            tb.unfolding_dot_khatri_rao(x, (None, st.factors), mode)
+        b.record()
+        torch.cuda.synchronize()
+        per_mode.append(alg / (a.elapsed_time(b) / 3 * 1e-3) / 1e9)
+    peak, src = measured_peak_hbm()
+    out["roofline"] = {"bound": "hbm", "achieved": statistics.mean(per_mode), "peak": peak, "unit": "GB/s",
+                       "frac": statistics.mean(per_mode) / peak, "per_mode_gbs": per_mode, "kernel": f"MTTKRP ({tb.last_kernel_path()})",
+                       "algorithmic_bytes_per_launch": alg, "peak_source": src}
+    return out
+
+
 def tucker_leg(env, steps):
     """C3 (BASELINE configs[2]): tucker HOOI rank [64,64,64] on random 512^3 fp32 — the TTM tensor-core path.
     Own driver (TTM chains + Gram + subspace iteration on the hand-written kernels) and, beside it, the unmodified
@@ -948,6 +992,12 @@ def run_ours(args):
         except Exception as exc:          # a secondary block must never cost the headline line
             n4 = {"unavailable": f"{type(exc).__name__}: {str(exc)[:160]}"}
     c3 = tucker_leg(env, args.steps) if (env.rank == 0 and env.world == 1 and not args.no_c3) else None
+    c4 = None
+    if env.rank == 0 and env.world == 1 and not args.no_c4:
+        try:
+            c4 = c4_leg(env, args.steps)
+        except Exception as exc:          # a secondary block must never cost the headline line
+            c4 = {"unavailable": f"{type(exc).__name__}: {str(exc)[:160]}"}
     clocks = env.sampler.stop() if env.sampler else None
 
     # ---- CPU baselines on the host cores (rank 0, N=1 only), bounded samples ---------------
@@ -993,6 +1043,7 @@ def run_ours(args):
             "reference_driver_on_b200": ref_driver,
             "c2": c2,
             "c3": c3,
+            "c4": c4,
             "fp64": fp64,
             "n4": n4,
         }
@@ -1024,6 +1075,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-c2", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the 256^4 non-negative CP block")
     ap.add_argument("--no-fp64", action="store_true")
     ap.add_argument("--no-n4", action="store_true", help="skip the reconstruction / imputation / HALS block")
     ap.add_argument("--no-c3", action="store_true")

@@ -7,7 +7,7 @@ echo "== bench (driver command) =="; date +%s > gpurun_out/r2_bench_t0; timeout 
 date +%s > gpurun_out/r2_bench_t1; echo "bench wall: $(( $(cat gpurun_out/r2_bench_t1) - $(cat gpurun_out/r2_bench_t0) )) s"
 echo "== bench reference arm =="; timeout 900 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2_bench_reference_n1.json 2> gpurun_out/r2_bench_reference_n1.err; echo "exit $?"; cut -c1-400 gpurun_out/r2_bench_reference_n1.json
 echo "== launch list =="
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r2_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-refdriver --no-c3 --no-fp64 --no-sustained > gpurun_out/r2_ncu_bench.log 2>&1; echo "exit $?"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r2_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-refdriver --no-c3 --no-c4 --no-n4 --no-fp64 --no-sustained > gpurun_out/r2_ncu_bench.log 2>&1; echo "exit $?"
 python scripts/launch_summary.py gpurun_out/r2_launches_bench.csv > gpurun_out/r2_launches_summary.txt 2>&1; head -n 12 gpurun_out/r2_launches_summary.txt
 echo "== ncu full: MTTKRP C5 rank 64 =="
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_stream -s 3 -c 2 -o gpurun_out/r2_prof_tc_c5 python scripts/prof_mttkrp.py 2048 64 2 > gpurun_out/r2_ncu_tc.log 2>&1; echo "exit $?"
