@@ -122,18 +122,22 @@ def test_c2_als_three_sweeps_vs_oracle():
 
 
 # --------------------------------------------------------------------------- C5 / C4 against fp64 on the device
+@pytest.mark.parametrize("engine", ["tcgen05", "tcgen05-f16"])
 @pytest.mark.parametrize("zero_mean", [False, True])
-def test_full_size_c5_properties(zero_mean):
-    """C5 (2048^3 fp32, rank 64, 34.4 GB) with random data: every mode's MTTKRP (rank-64 tcgen05 engine), the
-    dimension-tree route, and additivity over the 8 mode-0 slabs of the multi-GPU partition, against fp64."""
+def test_full_size_c5_properties(zero_mean, engine):
+    """C5 (2048^3 fp32, rank 64, 34.4 GB) with random data: every mode's MTTKRP on both tensor-core engines (3xTF32,
+    and the fp16 split the drivers use once max |x| is registered), the dimension-tree route, and additivity over the
+    8 mode-0 slabs of the multi-GPU partition, against fp64."""
     _need(60)
     n, R = 2048, 64
     x, w, fs = _random_problem((n, n, n), R, zero_mean, seed=31 + zero_mean)
+    hint = tb.RangeHint(x) if engine == "tcgen05-f16" else None
     t = tb.mode_dot(x, fs[2], 2, transpose=True)
+    assert tb.last_kernel_path() == engine
     for mode in range(3):
         truth = mttkrp_fp64_on_device(x, w, fs, mode)
         got = tb.unfolding_dot_khatri_rao(x, (w, fs), mode)
-        assert tb.last_kernel_path() == "tcgen05"
+        assert tb.last_kernel_path() == engine
         err = _rel(got, truth)
         assert err <= 1e-5, (mode, zero_mean, err)
         if mode < 2:
@@ -179,17 +183,20 @@ def test_full_size_c5_als_sweeps_match_n_pass_and_fp64_error():
     assert abs(errs[0][-1] - explicit) / explicit <= 1e-4, (errs[0][-1], explicit)
 
 
+@pytest.mark.parametrize("engine", ["tcgen05", "tcgen05-f16"])
 @pytest.mark.parametrize("zero_mean", [False, True])
-def test_full_size_c4_random_data(zero_mean):
-    """C4 (256^4 fp32, rank 64, 17 GB) with random data, all four modes, direct and from the dimension tree."""
+def test_full_size_c4_random_data(zero_mean, engine):
+    """C4 (256^4 fp32, rank 64, 17 GB) with random data, all four modes, direct and from the dimension tree, on both
+    tensor-core engines."""
     _need(45)
     n, R = 256, 64
     x, w, fs = _random_problem((n, n, n, n), R, zero_mean, seed=41 + zero_mean)
+    hint = tb.RangeHint(x) if engine == "tcgen05-f16" else None
     t = tb.mode_dot(x, fs[3], 3, transpose=True)
     for mode in range(4):
         truth = mttkrp_fp64_on_device(x, w, fs, mode)
         got = tb.unfolding_dot_khatri_rao(x, (w, fs), mode)
-        assert tb.last_kernel_path() == "tcgen05"
+        assert tb.last_kernel_path() == engine
         err = _rel(got, truth)
         assert err <= 1e-5, (mode, zero_mean, err)
         if mode < 3:
