@@ -470,9 +470,18 @@ recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_consta
                     if constexpr (W == 1) rt_tma_store_2d(slot, &out_map, cx, cy);
                     else rt_tma_store_3d(slot, &out_map, 0, cx / 32, cy);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    // the slot is free again as soon as the store has READ it (not when the data has landed)
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    if (MODE != 0) rt_mbar_arrive(&slot_free[k]);
+                    // A slot is free again as soon as its store has READ it (not when the data has landed).  With two
+                    // slots the loader needs this one back at once, so the storer waits for the read; with three or
+                    // more it only makes sure the PREVIOUS store has been read (it almost always has) and the slot
+                    // being rewritten next — last used three or more parts ago — is then known free at the barrier.
+                    if constexpr (MODE != 0 && NS == 2) {
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        rt_mbar_arrive(&slot_free[k]);
+                    } else {
+                        static_assert(MODE != 0 ? NS >= 2 : NS >= 3, "slot reuse distance");
+                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        if (MODE != 0 && g >= 1) rt_mbar_arrive(&slot_free[(g - 1) % NS]);
+                    }
                 }
             }
         }

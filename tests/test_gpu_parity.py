@@ -830,7 +830,9 @@ def test_cp_to_tensor_golden(golden):
                                         # large enough for the tcgen05 variant (fp32, rank <= 64): aligned, ragged rows,
                                         # odd column count (scalar stores), 4-way, 2-way
                                         ((256, 96, 80), 32), ((200, 130, 52), 20), ((300, 77, 61), 64),
-                                        ((64, 32, 24, 40), 48), ((2000, 1100), 7)])
+                                        ((64, 32, 24, 40), 48), ((2000, 1100), 7),
+                                        # two contraction chunks through the TMA epilogue (one / two lines per box)
+                                        ((256, 64, 128), 64), ((192, 80, 96), 48), ((100, 90, 124), 40)])
 def test_cp_to_tensor_and_impute_vs_oracle(shape, rank, dtype):
     rng = np.random.RandomState(17)
     fs = [(rng.random_sample((s, rank)) - 0.4).astype(dtype) for s in shape]
