@@ -129,10 +129,14 @@ template <int CHUNKS, int MODE, int W>
 struct RtCfg {
     static constexpr int A_BYTES = CHUNKS * 16384;          // per part (hi or lo): [chunk][128 rows][128 B]
     static constexpr int B_STAGE = CHUNKS * 32768;          // [chunk][hi 128 rows | lo 128 rows][128 B]
-    static constexpr int NB = CHUNKS == 1 ? 2 : 1;
+    // Khatri-Rao stages: two wherever they fit.  At rank 33..64 the operands take twice the bytes: the plain
+    // reconstruction (4 bytes per element: its tile time is the shortest) keeps two stages and one-line boxes, the
+    // imputation variants (12 bytes per element) one stage and more slot bytes.
+    static constexpr int NB = (CHUNKS == 1 || MODE == 0) ? 2 : 1;
     static constexpr int BOX = 16384 * W;                   // one box: [128 rows][W lines][128 B]
     static constexpr int SLOT = MODE == 0 ? BOX : 2 * BOX;  // [out / x box][mask box]
-    static constexpr int NS = CHUNKS == 1 ? (128 * 1024) / SLOT > 4 ? 4 : (128 * 1024) / SLOT : (96 * 1024) / SLOT;
+    static constexpr int SLOT_BYTES = CHUNKS == 1 ? 128 * 1024 : (MODE == 0 ? 32 * 1024 : 96 * 1024);
+    static constexpr int NS = SLOT_BYTES / SLOT > 4 ? 4 : SLOT_BYTES / SLOT;
     static_assert(NS >= 2, "at least two slots");
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = 2 * A_BYTES;
@@ -474,11 +478,11 @@ recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_consta
                     // slots the loader needs this one back at once, so the storer waits for the read; with three or
                     // more it only makes sure the PREVIOUS store has been read (it almost always has) and the slot
                     // being rewritten next — last used three or more parts ago — is then known free at the barrier.
-                    if constexpr (MODE != 0 && NS == 2) {
+                    if constexpr (NS == 2) {
                         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        rt_mbar_arrive(&slot_free[k]);
+                        if (MODE != 0) rt_mbar_arrive(&slot_free[k]);
                     } else {
-                        static_assert(MODE != 0 ? NS >= 2 : NS >= 3, "slot reuse distance");
+                        static_assert(NS >= 3, "slot reuse distance");
                         asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                         if (MODE != 0 && g >= 1) rt_mbar_arrive(&slot_free[(g - 1) % NS]);
                     }
@@ -678,11 +682,10 @@ int recon_tc_launch(const void* const* factors, const int64_t* shape, const int6
     p.use_tma = tc_available() && p.C % 4 == 0 && p.C < (1LL << 31) && p.I < (1LL << 31) &&
                 reinterpret_cast<uintptr_t>(out) % 16 == 0 && (!x || reinterpret_cast<uintptr_t>(x) % 16 == 0) &&
                 (!mask || reinterpret_cast<uintptr_t>(mask) % 16 == 0) && !getenv("TLB200_RECON_NO_TMA");
-    // two lines per row and box where the extents allow it (C % 32 == 0) and shared memory holds the slots
-    // (rank <= 32, or the plain reconstruction whose slots carry no x / mask boxes)
+    // two lines per row and box where the extents allow it (C % 32 == 0) and shared memory holds the slots (rank <= 32)
     static int w_cap = -1;
     if (w_cap < 0) { const char* e = getenv("TLB200_RECON_LINES"); w_cap = e ? atoi(e) : 2; }
-    const int W = (p.use_tma && p.C % 32 == 0 && (rank <= 32 || mode == 0) && w_cap >= 2) ? 2 : 1;
+    const int W = (p.use_tma && p.C % 32 == 0 && rank <= 32 && w_cap >= 2) ? 2 : 1;
     if (p.use_tma) {
         int st;
         const void* bases[3] = {out, x, mask};
@@ -711,7 +714,7 @@ int recon_tc_launch(const void* const* factors, const int64_t* shape, const int6
         if (mode == 1) return launch_one<1, 1, 1>(p, maps, grid, stream);
         return launch_one<1, 2, 1>(p, maps, grid, stream);
     }
-    if (mode == 0) return Wk == 2 ? launch_one<2, 0, 2>(p, maps, grid, stream) : launch_one<2, 0, 1>(p, maps, grid, stream);
+    if (mode == 0) return launch_one<2, 0, 1>(p, maps, grid, stream);
     if (mode == 1) return launch_one<2, 1, 1>(p, maps, grid, stream);
     return launch_one<2, 2, 1>(p, maps, grid, stream);
 }
