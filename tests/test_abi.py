@@ -104,6 +104,22 @@ def test_c_abi_validates_before_launching():
     assert st == _lib.TLB200_EINVAL
 
 
+def test_range_hint_entry_points_validate_and_the_shape_only_plan_stays_tf32():
+    """tlb200_hint_tensor_absmax is host-only bookkeeping (a pointer table): it validates its arguments, accepts a
+    withdrawal of something never registered, and the shape-only plan never reports the fp16-split engine."""
+    import ctypes
+    import tensorly_b200 as tb
+    lib = _lib.load()
+    assert lib.tlb200_hint_tensor_absmax(None, None) == _lib.TLB200_EINVAL
+    assert lib.tlb200_hint_tensor_absmax(ctypes.c_void_p(0x1000), None) == 0          # nothing registered: a no-op
+    assert lib.tlb200_tensor_absmax(None, 10, _lib.F32, None, None) == _lib.TLB200_EINVAL
+    assert lib.tlb200_tensor_absmax(ctypes.c_void_p(0x1000), 10, _lib.F64, ctypes.c_void_p(0x2000), None) != 0   # fp32 only
+    assert tb.mttkrp_plan((256, 192, 320), 1, 64).f16 == 0
+    # the fp16 engine blocks the contraction differently: the workspace query covers both plans
+    shape = _lib.i64_array((256, 192, 320))
+    assert lib.tlb200_mttkrp_workspace_bytes(shape, 3, 1, 64, _lib.F32, _lib.PATH_AUTO) > 0
+
+
 def test_plan_reports_column_block_passes_field():
     """rank_passes is part of the plan struct: 1 on the SIMT path (all a GPU-less box can plan), ceil(rank / 64)
     column blocks when the tcgen05 engine is available."""
