@@ -19,6 +19,6 @@ lib = _lib.load()
 lib.tlb200_debug_subspace_trace.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
 lib.tlb200_debug_subspace_trace(out)
 t = list(out)
-names = ["gemm+gram", "rendezvous+sum+load S", "cholesky", "inverse", "write rinv"]
-print("phase clocks:", {n: t[i + 1] - t[i] for i, n in enumerate(names)})
+names = ["gemm+gram", "rendezvous+sum+load S", "cholesky"]
+print("phase clocks (factoring CTA):", {n: t[i + 1] - t[i] for i, n in enumerate(names)})
 print("inside gemm+gram:", {"k loop": t[6] - t[0], "fold + Z out": t[7] - t[6], "gram partial + fence": t[1] - t[7]})

@@ -299,12 +299,16 @@ __device__ __forceinline__ void ps_dmma(double& c0, double& c1, double a, double
 }
 
 __global__ void __launch_bounds__(256)
-power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const double* __restrict__ U, int p,
+power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const double* U, int p,
                     int64_t u_ld, double* __restrict__ Z, double* __restrict__ partial, double* __restrict__ ssum,
                     unsigned* __restrict__ counter, double* __restrict__ rinv, int* __restrict__ status, int parallel,
-                    int pipelined) {
+                    int pipelined, double* __restrict__ U_out) {
     extern __shared__ __align__(16) unsigned char ps_smem[];
     typedef double Row[OR_MAX + 1];
+    // fused solve (parallel mode): the epoch word is advanced by the factoring CTA once R is in global memory; every
+    // CTA reads it before the rendezvous (nobody can advance it before all have passed it)
+    __shared__ unsigned s_epoch;
+    if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile unsigned*>(counter + 8);
     // GEMM phase: PS_STAGES stages of [Us: PS_KC x 64][Gs: 16 x PS_GLD]; later, in the factoring CTA only:
     // [S: 64 x 65][Ri: 64 x 65]
     __shared__ int s_last;
@@ -466,10 +470,75 @@ power_step_a_kernel(const double* __restrict__ G, int64_t n, int64_t g_ld, const
         __syncthreads();
         if (tid == 0) s_last = atomicAdd(counter + 2, 1u) == gridDim.x - 1;
         __syncthreads();
-        if (!s_last) return;
-        __threadfence();
-        for (int e = tid; e < p * p; e += 256) S[e / p][e % p] = __ldcg(ssum + e);
-        if (tid == 0) { counter[0] = 0u; counter[2] = 0u; }
+        if (s_last) {
+            __threadfence();
+            for (int e = tid; e < p * p; e += 256) S[e / p][e % p] = __ldcg(ssum + e);
+            if (tid == 0) { counter[0] = 0u; counter[2] = 0u; }
+            __syncthreads();
+            if (tid == 0) { g_ps_trace[0] = t_start; g_ps_trace[1] = t_gemm; g_ps_trace[6] = t_loop; g_ps_trace[7] = t_z; }
+            PS_TRACE(2);
+            chol_upper_64(S, rinv, rinv + (size_t)p * p, p, status);
+            PS_TRACE(3);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                unsigned next = s_epoch + 1u;
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(counter + 8), "r"(next) : "memory");
+            }
+        } else if (tid == 0) {
+            // wait for the factor (bounded: trap instead of hanging)
+            const unsigned want = s_epoch + 1u;
+            unsigned seen = 0, spins = 0;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter + 8) : "memory");
+                if (++spins > (1u << 26)) asm volatile("trap;");
+            } while (seen != want);
+        }
+        __syncthreads();
+        // U = Z R^{-1} for this CTA's 16 rows, here instead of in a second launch: 16 lanes per row, axpy form (see
+        // power_step_b_kernel).  The Z block is still in shared memory — except in the factoring CTA, whose tile was
+        // overwritten by S: it reads its rows back from global memory.
+        {
+            double* Rs = stage0 + 9216;                       // [64][64]: R[k][i] for i > k, else 0 (past S / R^-1 scratch)
+            double* idg = Rs + OR_MAX * OR_MAX;
+            for (int e = tid; e < OR_MAX * OR_MAX; e += 256) {
+                const int k = e >> 6, i = e & 63;
+                Rs[e] = (k < p && i < p && i > k) ? __ldcg(rinv + k * p + i) : 0.0;
+            }
+            if (tid < OR_MAX) idg[tid] = tid < p ? __ldcg(rinv + (size_t)p * p + tid) : 0.0;
+            const int lr = tid >> 4, l16 = tid & 15;
+            const int64_t grow = row0 + lr;
+            double b[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int i = t * 16 + l16;
+                if (s_last) b[t] = (grow < n && i < p) ? __ldcg(Z + grow * p + i) : 0.0;
+                else b[t] = stage0[lr * OR_MAX + i];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl) {
+#pragma unroll 4
+                for (int kk = 0; kk < 16; ++kk) {
+                    const int k = sl * 16 + kk;
+                    if (k >= p) break;
+                    const double qk = __shfl_sync(0xffffffffu, b[sl] * idg[k], kk, 16);
+                    if (l16 == kk) b[sl] = qk;
+                    const double* c = Rs + k * OR_MAX + l16;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) b[t] = fma(-c[t * 16], qk, b[t]);
+                }
+            }
+            if (grow < n)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int i = t * 16 + l16;
+                    if (i < p) U_out[grow * u_ld + i] = b[t];
+                }
+        }
+        PS_TRACE(4);
+        PS_TRACE(5);
+        return;
     } else {
         if (tid == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
         __syncthreads();
@@ -712,11 +781,14 @@ extern "C" int tlb200_subspace_iterate(const void* g, int64_t n, int64_t g_ld, v
     if (ensure_dynamic_smem(power_step_a_kernel, smem_a, attr_done)) return TLB200_ECUDA;
     const int nblk = (int)ceil_div(n, PS_ROWS);
     for (int it = 0; it < steps; ++it) {
+        const int parallel = nblk > 1 && nblk <= kNumSMs;
         power_step_a_kernel<<<nblk, 256, smem_a, s>>>((const double*)g, n, g_ld, (const double*)u, (int)p, u_ld, z, partial,
-                                                      ssum, counter, rinv, status, nblk > 1 && nblk <= kNumSMs, pipelined);
+                                                      ssum, counter, rinv, status, parallel, pipelined, (double*)u);
         TLB_CHECK_LAUNCH();
-        power_step_b_kernel<<<nblk, 256, 0, s>>>(z, n, (int)p, rinv, (double*)u, u_ld);
-        TLB_CHECK_LAUNCH();
+        if (!parallel) {           // (parallel: every CTA solved its own rows after the factoring CTA published R)
+            power_step_b_kernel<<<nblk, 256, 0, s>>>(z, n, (int)p, rinv, (double*)u, u_ld);
+            TLB_CHECK_LAUNCH();
+        }
     }
     return TLB200_OK;
 }
