@@ -955,6 +955,13 @@ def run_ours(args):
     if env.sampler:
         env.sampler.start()
 
+    def guarded(fn, *a):
+        """Rank-0-only secondary blocks must never cost the headline line."""
+        try:
+            return fn(*a)
+        except Exception as exc:
+            return {"unavailable": f"{type(exc).__name__}: {str(exc)[:200]}"}
+
     key = args.workload
     res = bench_workload(env, key, args, headline=True)
     state = res["state"]
@@ -962,7 +969,7 @@ def run_ours(args):
     parity = parity_leg(env)
     ref_driver = None
     if env.rank == 0 and env.world == 1 and not args.no_refdriver:
-        ref_driver = reference_driver_leg(env, key, res)
+        ref_driver = guarded(reference_driver_leg, env, key, res)
     e2e = None if args.no_e2e else e2e_leg(env, res, args)
     shape, R = WORKLOADS[key]["shape"], WORKLOADS[key]["rank"]
     dimtree = state.dimtree
@@ -980,32 +987,23 @@ def run_ours(args):
               "final_rel_error": r2["rel_err"], "launches_per_sweep": r2["launches_per_sweep"],
               "clocks": env.sampler.summary(*r2["clock_marks"]) if env.sampler else None}
         if env.rank == 0 and env.world == 1 and not args.no_refdriver:
-            c2["reference_driver_on_b200"] = reference_driver_leg(env, "c2", r2)
+            c2["reference_driver_on_b200"] = guarded(reference_driver_leg, env, "c2", r2)
         r2["state"]._graph = None
         del r2
         torch.cuda.empty_cache()
-    fp64 = fp64_leg(env) if (env.rank == 0 and env.world == 1 and not args.no_fp64) else None
-    n4 = None
-    if env.rank == 0 and env.world == 1 and not args.no_n4:
-        try:
-            n4 = n4_leg(env)
-        except Exception as exc:          # a secondary block must never cost the headline line
-            n4 = {"unavailable": f"{type(exc).__name__}: {str(exc)[:160]}"}
-    c3 = tucker_leg(env, args.steps) if (env.rank == 0 and env.world == 1 and not args.no_c3) else None
-    c4 = None
-    if env.rank == 0 and env.world == 1 and not args.no_c4:
-        try:
-            c4 = c4_leg(env, args.steps)
-        except Exception as exc:          # a secondary block must never cost the headline line
-            c4 = {"unavailable": f"{type(exc).__name__}: {str(exc)[:160]}"}
+    solo = env.rank == 0 and env.world == 1
+    fp64 = guarded(fp64_leg, env) if (solo and not args.no_fp64) else None
+    n4 = guarded(n4_leg, env) if (solo and not args.no_n4) else None
+    c3 = guarded(tucker_leg, env, args.steps) if (solo and not args.no_c3) else None
+    c4 = guarded(c4_leg, env, args.steps) if (solo and not args.no_c4) else None
     clocks = env.sampler.stop() if env.sampler else None
 
     # ---- CPU baselines on the host cores (rank 0, N=1 only), bounded samples ---------------
     cpu = None
     if env.rank == 0 and env.world == 1 and not args.no_cpu:
-        cpu = cpu_baseline_leg(key, args.cpu_budget_s)
+        cpu = guarded(cpu_baseline_leg, key, args.cpu_budget_s)
         if c2 is not None:
-            c2["cpu_baseline"] = cpu_baseline_leg("c2", args.cpu_budget_s)
+            c2["cpu_baseline"] = guarded(cpu_baseline_leg, "c2", args.cpu_budget_s)
 
     if env.rank == 0:
         wl = WORKLOADS[key]
