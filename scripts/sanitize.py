@@ -51,6 +51,23 @@ for shape in [(64, 48, 96), (33, 47, 51)]:
         sub = ",".join(f"{'ijk'[m]}r" for m in range(3) if m != mode)
         ref = torch.einsum(f"ijk,{sub}->{'ijk'[mode]}r", x, *ops)
         assert float(torch.linalg.norm(got - ref) / torch.linalg.norm(ref)) < 1e-12
+# reconstruction / imputation on the tensor cores: TMA epilogue with two-line and one-line boxes, two contraction chunks,
+# and the transposing epilogue for extents TMA cannot describe
+for shape, R in [((256, 64, 64), 32), ((256, 66, 62), 24), ((192, 64, 96), 48), ((192, 75, 73), 20)]:
+    fs = [torch.randn(s, R, device="cuda") for s in shape]
+    w = torch.rand(R, device="cuda") + 0.5
+    ref = torch.einsum("ir,jr,kr->ijk", fs[0].double() * w.double(), fs[1].double(), fs[2].double())
+    rec = tb.cp_to_tensor((w, fs))
+    paths.add("recon-" + tb.last_kernel_path())
+    assert float(torch.linalg.norm(rec.double() - ref) / torch.linalg.norm(ref)) < 1e-5, shape
+    x = torch.randn(shape, device="cuda")
+    mask = (torch.rand(shape, device="cuda") > 0.3).float()
+    new, stats = tb.cp_impute(x, mask, (w, fs))
+    want = x.double() * mask.double() + ref * (1 - mask.double())
+    assert float(torch.linalg.norm(new.double() - want) / torch.linalg.norm(want)) < 1e-5, shape
+    assert abs(float(stats[1]) - float((want ** 2).sum())) <= 1e-4 * float((want ** 2).sum())
+    got = tb.cp_to_tensor((w, fs), mask=mask)
+    assert float(torch.linalg.norm(got.double() - ref * mask.double()) / torch.linalg.norm(ref * mask.double())) < 1e-5
 # HOOI power step (cp.async + DMMA + register Cholesky) and the own Tucker driver
 y = torch.rand(96, 512, device="cuda", dtype=torch.float64)
 u = tb.subspace_iterate(y @ y.T, tb.orthonormalize(torch.rand(96, 16, device="cuda", dtype=torch.float64)), 3)
