@@ -58,7 +58,18 @@ namespace {
 
 constexpr int TM = 128;
 constexpr int NUM_THREADS = 512;
-constexpr uint32_t SPIN_LIMIT = 1u << 22;   // x ~1 us per try_wait: seconds, then trap (never hang the GPU)
+// A wait gives up (trap) after ~20 s of wall time — never hang the GPU.  The clock is only consulted every 1024 polls:
+// a poll may return at once or, with the suspend-time hint (100 us) honoured, sleep that long.  (The hint takes the
+// spin loops from ~38 % of all issued warp instructions to a few percent — same-box A/B: SM clock up ~100 MHz under the
+// power cap at the same 4.85-4.9 TB/s: the sustained rate is set by the energy of the data path, not by issue slots.)
+constexpr uint64_t WAIT_LIMIT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ void wait_watchdog(uint32_t& spins, uint64_t& t0) {
+    if ((++spins & 0x3FFu) != 0) return;
+    uint64_t now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > WAIT_LIMIT_NS) asm volatile("trap;");
+}
 
 // ---- PTX wrappers ---------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -73,12 +84,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0, spins = 0;
+    uint64_t t0 = 0;
     const uint32_t addr = smem_u32(bar);
     while (true) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x186A0;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
         if (done) break;
-        if (++spins > SPIN_LIMIT) asm volatile("trap;");
+        wait_watchdog(spins, t0);
     }
 }
 // One elected lane of a fully converged warp (the operands of tcgen05/TMA instructions must live in uniform
@@ -92,29 +104,31 @@ __device__ __forceinline__ uint32_t elect_one_sync() {
 // wait for two barriers at once: the two try_wait round trips overlap instead of adding up
 __device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t parity_a, uint64_t* bar_b, uint32_t parity_b) {
     uint32_t da = 0, db = 0, spins = 0;
+    uint64_t t0 = 0;
     const uint32_t aa = smem_u32(bar_a), ab = smem_u32(bar_b);
     while (true) {
-        if (!da) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        if (!da) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x186A0;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                               : "=r"(da) : "r"(aa), "r"(parity_a) : "memory");
-        if (!db) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        if (!db) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x186A0;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                               : "=r"(db) : "r"(ab), "r"(parity_b) : "memory");
         if (da && db) break;
-        if (++spins > SPIN_LIMIT) asm volatile("trap;");
+        wait_watchdog(spins, t0);
     }
 }
 // three barriers at once (A tile + both B units of a tile)
 __device__ __forceinline__ void mbar_wait3(uint64_t* bar_a, uint32_t pa, uint64_t* bar_b, uint32_t pb, uint64_t* bar_c, uint32_t pc) {
     uint32_t da = 0, db = 0, dc = 0, spins = 0;
+    uint64_t t0 = 0;
     const uint32_t aa = smem_u32(bar_a), ab = smem_u32(bar_b), ac = smem_u32(bar_c);
     while (true) {
-        if (!da) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        if (!da) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x186A0;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                               : "=r"(da) : "r"(aa), "r"(pa) : "memory");
-        if (!db) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        if (!db) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x186A0;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                               : "=r"(db) : "r"(ab), "r"(pb) : "memory");
-        if (!dc) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        if (!dc) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x186A0;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                               : "=r"(dc) : "r"(ac), "r"(pc) : "memory");
         if (da && db && dc) break;
-        if (++spins > SPIN_LIMIT) asm volatile("trap;");
+        wait_watchdog(spins, t0);
     }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
