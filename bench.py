@@ -102,7 +102,7 @@ class ClockSampler:
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,clocks.mem,temperature.gpu")
 
     def __init__(self, index: int):
         self.rows = []
@@ -127,7 +127,7 @@ class ClockSampler:
         return len(self.rows)
 
     def summary(self, start=0, end=None):
-        sm, smax, reasons, power = [], [], set(), []
+        sm, smax, reasons, power, mem, temp = [], [], set(), [], [], []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows[start:end]:
             parts = [p.strip() for p in r.split(",")]
@@ -140,12 +140,17 @@ class ClockSampler:
             for n, v in zip(names, parts[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
+            try:
+                mem.append(float(parts[7])); temp.append(float(parts[8]))
+            except (IndexError, ValueError):
+                pass
         if sm:
             # "under load": samples in the upper half of the observed power range
             thr = (max(power) + min(power)) / 2 if power else 0
             loaded = [s for s, p in zip(sm, power) if p >= thr] or sm
             return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
-                    "samples": len(sm), "power_w_max": max(power) if power else None}
+                    "samples": len(sm), "power_w_max": max(power) if power else None,
+                    "mem_mhz": statistics.median(mem) if mem else None, "temp_c_max": max(temp) if temp else None}
         return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "samples": 0}
 
     def stop(self):

@@ -41,7 +41,7 @@ for mode in range(3):
     s = cs.summary(m0, cs.mark())
     print(f"HFoff={os.environ.get('TLB200_DISABLE_HF', '0')} debug={os.environ.get('TLB200_TC_DEBUG', '0')} R={rank} mode {mode} "
           f"[{tb.last_kernel_path()}]: {x.numel() * 4 / ms / 1e6:7.0f} GB/s  {ms * 1e3:7.1f} us  sm {s['sm_mhz']} MHz  "
-          f"power max {s['power_w_max']} W  {s['reasons']}", flush=True)
+          f"mem {s.get('mem_mhz')} MHz  {s.get('temp_c_max')} C  power max {s['power_w_max']} W  {s['reasons']}", flush=True)
 # the ceiling under the same power cap: a read-only pass over the same tensor (max |x|), sustained
 for name, fn in (("tensor_absmax (read-only pass)", lambda: tb.tensor_absmax(x)), ("sumsq (read-only pass)", lambda: tb.sumsq(x))):
     for _ in range(5):
@@ -61,6 +61,6 @@ for name, fn in (("tensor_absmax (read-only pass)", lambda: tb.tensor_absmax(x))
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     s = cs.summary(m0, cs.mark())
-    print(f"ceiling {name}: {x.numel() * 4 / ms / 1e6:7.0f} GB/s  {ms * 1e3:7.1f} us  sm {s['sm_mhz']} MHz  power max {s['power_w_max']} W  "
+    print(f"ceiling {name}: {x.numel() * 4 / ms / 1e6:7.0f} GB/s  {ms * 1e3:7.1f} us  sm {s['sm_mhz']} MHz  mem {s.get('mem_mhz')} MHz  {s.get('temp_c_max')} C  power max {s['power_w_max']} W  "
           f"{s['reasons']}", flush=True)
 cs.stop()
