@@ -52,6 +52,7 @@ WORKLOADS = {
     "small": dict(shape=(256, 256, 256), rank=32, dtype="float32", name="small: parafac rank 32 on 256^3 fp32"),
     # one rank's share of C5 at N = 8 as a single-GPU problem (profiling aid: same kernels, no exchange)
     "c5slab": dict(shape=(256, 2048, 2048), rank=64, dtype="float32", name="C5 slab: 256x2048x2048 rank 64 (1/8 of C5)"),
+    "c2slab": dict(shape=(128, 1024, 1024), rank=32, dtype="float32", name="C2 slab: 128x1024x1024 rank 32 (1/8 of C2)"),
 }
 METRIC = "CP-ALS sweeps/s (MTTKRP HBM GB/s in roofline)"
 UNIT = "sweeps/s"
