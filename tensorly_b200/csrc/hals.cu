@@ -60,8 +60,10 @@ template <typename T, int RM>
 __global__ void __launch_bounds__(HT)
 hals_kernel(const HalsParams<T> p) {
     extern __shared__ __align__(16) unsigned char hals_smem[];
-    T* Urot = reinterpret_cast<T*>(hals_smem);          // [RM][RM]: Urot[k][j] = UtU[(k + j) % RM][k]
-    T* vs = Urot + RM * RM;                             // [RM][HT]: v_k of this thread's column at vs[k * HT + tid]
+    // UtU is kept in DOUBLE in shared memory: the gradient update reads R entries of it per coordinate and thread, and
+    // converting them from fp32 every time (F2F.F64.F32 issues at a quarter of the DFMA rate) cost more than the FMAs
+    double* Urot = reinterpret_cast<double*>(hals_smem);   // [RM][RM]: Urot[k][j] = UtU[(k + j) % RM][k]
+    T* vs = reinterpret_cast<T*>(Urot + RM * RM);          // [RM][HT]: v_k of this thread's column at vs[k * HT + tid]
     __shared__ T diag[RM];
     __shared__ double red[HT / 32];
     __shared__ double s_total;
@@ -85,7 +87,7 @@ hals_kernel(const HalsParams<T> p) {
                 if (p.w) v = (p.w[l] * v) * p.w[k];
             }
         }
-        Urot[e] = v;
+        Urot[e] = (double)v;
         if (j == 0) diag[k] = v;
     }
     // this column of V, its running sums, and the gradient g = UtM - UtU v (rotation 0: g[j] <-> coordinate j)
@@ -105,9 +107,9 @@ hals_kernel(const HalsParams<T> p) {
     for (int j = 0; j < RM; ++j) g[j] = (live && j < R) ? (double)p.m[col * p.m_rs + j * p.m_cs] : 0.0;
     for (int k = 0; k < R; ++k) {          // g[j] -= UtU[j][k] * v_k, with UtU[j][k] = Urot[k][(j - k) mod RM]
         const double vk = (double)vs[k * HT + tid];
-        const T* c = Urot + k * RM;
+        const double* c = Urot + k * RM;
 #pragma unroll
-        for (int j = 0; j < RM; ++j) g[j] -= (double)c[(j - k) & (RM - 1)] * vk;
+        for (int j = 0; j < RM; ++j) g[j] -= c[(j - k) & (RM - 1)] * vk;
     }
 
     const double Rd = (double)R;
@@ -136,10 +138,10 @@ hals_kernel(const HalsParams<T> p) {
                 vs[k * HT + tid] = nv;
             }
             // g <- rotate_left(g - delta * UtU[:, k]): coordinate k + 1 moves to register 0
-            const T* c = Urot + k * RM;
-            const double g0 = g[0] - delta * (double)c[0];
+            const double* c = Urot + k * RM;
+            const double g0 = g[0] - delta * c[0];
 #pragma unroll
-            for (int j = 1; j < RM; ++j) g[j - 1] = g[j] - delta * (double)c[j];
+            for (int j = 1; j < RM; ++j) g[j - 1] = g[j] - delta * c[j];
             g[RM - 1] = g0;
         }
         // global stopping statistic, fixed summation order
@@ -173,7 +175,7 @@ hals_kernel(const HalsParams<T> p) {
 
 template <typename T, int RM>
 int launch_rm(const HalsParams<T>& p, cudaStream_t stream) {
-    const int smem = (int)sizeof(T) * (RM * RM + RM * HT);
+    const int smem = (int)sizeof(double) * RM * RM + (int)sizeof(T) * RM * HT;
     static std::atomic<uint64_t> attr_done{0};
     if (ensure_dynamic_smem(hals_kernel<T, RM>, smem, attr_done)) return TLB200_ECUDA;
     const int64_t nblk = ceil_div(p.n, HT);
