@@ -121,21 +121,24 @@ struct ReconTcParams {
 };
 
 // MODE 0: out = rec.   MODE 1: out = x*mask + rec*(1-mask) + the two norms.   MODE 2: out = rec * mask.
-// shared-memory plan per (CHUNKS, MODE): rank <= 32 double-buffers the Khatri-Rao tile; rank 33..64 needs twice the
-// operand bytes and keeps one stage (producer + MMA of a tile take less than the tile's HBM time)
+// shared-memory plan per (CHUNKS, MODE, W): see the notes on NB below
 // W = 128-byte lines per row and TMA box (1 or 2): rows of the tensor lie megabytes apart, and DRAM serves two adjacent
 // lines per row markedly better than one (measured for the tensor stream of tc_stream.cu: 6.8 against 4.5 TB/s)
 template <int CHUNKS, int MODE, int W>
 struct RtCfg {
     static constexpr int A_BYTES = CHUNKS * 16384;          // per part (hi or lo): [chunk][128 rows][128 B]
-    static constexpr int B_STAGE = CHUNKS * 32768;          // [chunk][hi 128 rows | lo 128 rows][128 B]
-    // Khatri-Rao stages: two wherever they fit.  At rank 33..64 the operands take twice the bytes: the plain
-    // reconstruction (4 bytes per element: its tile time is the shortest) keeps two stages and one-line boxes, the
-    // imputation variants (12 bytes per element) one stage and more slot bytes.
-    static constexpr int NB = (CHUNKS == 1 || MODE == 0) ? 2 : 1;
+    static constexpr int B_STAGE = 32768;                   // ONE 32-wide chunk of the tile: [hi 128 rows | lo 128 rows][128 B]
+    // Khatri-Rao stages (one chunk each; a rank 33..64 tile takes two steps through them).  Rank <= 32: two.  Rank
+    // 33..64: the plain reconstruction (4 bytes per element, the shortest tile time) keeps two whole tiles = four
+    // stages and one-line boxes (3.5 TB/s; two stages + two-line boxes: 2.9); the imputation variants (12 bytes per
+    // element: producer + MMA of both chunks still take less than the tile's HBM time) keep ONE so that their slots
+    // can hold two-line boxes (4.8 TB/s; one-line boxes: 4.2).
+    static constexpr int NB = CHUNKS == 1 ? 2 : (MODE == 0 ? 4 : 1);
+    static constexpr int CPS = (CHUNKS == 2 && MODE == 0) ? 2 : 1;      // chunks handed over per barrier step
+    static constexpr int NST = NB / CPS;                                // step-stages
     static constexpr int BOX = 16384 * W;                   // one box: [128 rows][W lines][128 B]
     static constexpr int SLOT = MODE == 0 ? BOX : 2 * BOX;  // [out / x box][mask box]
-    static constexpr int SLOT_BYTES = CHUNKS == 1 ? 128 * 1024 : (MODE == 0 ? 32 * 1024 : 96 * 1024);
+    static constexpr int SLOT_BYTES = CHUNKS == 1 ? 128 * 1024 : (MODE == 0 ? 32 * 1024 : 128 * 1024);
     static constexpr int NS = SLOT_BYTES / SLOT > 4 ? 4 : SLOT_BYTES / SLOT;
     static_assert(NS >= 2, "at least two slots");
     static constexpr int OFF_A = 0;
@@ -152,7 +155,8 @@ __global__ void __launch_bounds__(RT_THREADS, 1)
 recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_constant__ CUtensorMap x_map,
                 const __grid_constant__ CUtensorMap mask_map, const ReconTcParams p) {
     using Cfg = RtCfg<CHUNKS, MODE, W>;
-    constexpr int A_BYTES = Cfg::A_BYTES, B_STAGE = Cfg::B_STAGE, NB = Cfg::NB, NS = Cfg::NS, SLOT = Cfg::SLOT, BOX = Cfg::BOX;
+    constexpr int A_BYTES = Cfg::A_BYTES, B_STAGE = Cfg::B_STAGE, NS = Cfg::NS, SLOT = Cfg::SLOT, BOX = Cfg::BOX;
+    constexpr int CPS = Cfg::CPS, NST = Cfg::NST, STEPS = CHUNKS / Cfg::CPS;
     constexpr int PC = 32 * W;                  // columns per epilogue part (TMA path)
     constexpr int OFF_A = Cfg::OFF_A, OFF_B = Cfg::OFF_B, OFF_STG = Cfg::OFF_SLOT, OFF_BAR = Cfg::OFF_BAR;
     extern __shared__ unsigned char rt_smem_raw[];
@@ -163,23 +167,21 @@ recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_consta
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* a_full = bars;            // 1
     uint64_t* a_empty = bars + 1;       // 1
-    uint64_t* b_full = bars + 2;        // 2
-    uint64_t* b_empty = bars + 4;       // 2
-    uint64_t* d_full = bars + 6;        // 2
-    uint64_t* d_empty = bars + 8;       // 2
-    uint64_t* slot_full = bars + 10;    // NS (<= 4)
-    uint64_t* slot_free = bars + 14;    // NS
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    uint64_t* b_full = bars + 2;        // NB (<= 4)
+    uint64_t* b_empty = bars + 6;       // NB
+    uint64_t* d_full = bars + 10;       // 2
+    uint64_t* d_empty = bars + 12;      // 2
+    uint64_t* slot_full = bars + 14;    // NS (<= 4)
+    uint64_t* slot_free = bars + 18;    // NS
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
     unsigned char* slots = smem + OFF_STG;
     __shared__ double red[2][4];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0 && lane == 0) {
         rt_mbar_init(a_full, 256); rt_mbar_init(a_empty, 1);
-        for (int i = 0; i < 2; ++i) {
-            rt_mbar_init(&b_full[i], 256); rt_mbar_init(&b_empty[i], 1);
-            rt_mbar_init(&d_full[i], 1); rt_mbar_init(&d_empty[i], 128);
-        }
+        for (int i = 0; i < 4; ++i) { rt_mbar_init(&b_full[i], 256); rt_mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { rt_mbar_init(&d_full[i], 1); rt_mbar_init(&d_empty[i], 128); }
         for (int i = 0; i < 4; ++i) { rt_mbar_init(&slot_full[i], 1); rt_mbar_init(&slot_free[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&out_map)) : "memory");
@@ -210,27 +212,35 @@ recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_consta
         for (int64_t t = t_begin; t < t_end; ++t, ++n) {
             const int64_t rt = t / p.col_tiles;
             const uint32_t s = n & 1u;                       // accumulator set
-            const uint32_t sb = n % NB;                      // Khatri-Rao stage
             if (rt != cur_rt) { rt_mbar_wait(a_full, a_gen & 1u); cur_rt = rt; }
-            rt_mbar_wait(&b_full[sb], (n / NB) & 1u);
             if (n >= 2) rt_mbar_wait(&d_empty[s], ((n >> 1) - 1) & 1u);
-            rt_fence_after();
             const bool last_of_row = t + 1 == t_end || (t + 1) / p.col_tiles != rt;
-            if (rt_elect_one()) {
-                const uint32_t d0 = tmem_base + s * 256;
+            const uint32_t d0 = tmem_base + s * 256;
 #pragma unroll
-                for (int ch = 0; ch < CHUNKS; ++ch)
+            for (int st = 0; st < STEPS; ++st) {
+                const uint32_t step = n * STEPS + st;        // Khatri-Rao stages turn over once per step (CPS chunks)
+                const uint32_t sb = step % NST;
+                rt_mbar_wait(&b_full[sb], (step / NST) & 1u);
+                rt_fence_after();
+                if (rt_elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t bd = rt_desc(b_addr + sb * B_STAGE + ch * 32768 + ks * 32);
-                        rt_mma_ss(d0, rt_desc(a_hi_addr + ch * 16384 + ks * 32), bd, idesc_wide, (ch | ks) ? 1u : 0u);
-                        rt_mma_ss(d0 + RT_N, rt_desc(a_lo_addr + ch * 16384 + ks * 32), bd, idesc_half, 1u);
+                    for (int c2 = 0; c2 < CPS; ++c2) {
+                        const int ch = st * CPS + c2;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t bd = rt_desc(b_addr + (sb * CPS + c2) * B_STAGE + ks * 32);
+                            rt_mma_ss(d0, rt_desc(a_hi_addr + ch * 16384 + ks * 32), bd, idesc_wide, (ch | ks) ? 1u : 0u);
+                            rt_mma_ss(d0 + RT_N, rt_desc(a_lo_addr + ch * 16384 + ks * 32), bd, idesc_half, 1u);
+                        }
                     }
-                rt_commit(&b_empty[sb]);
-                rt_commit(&d_full[s]);
-                if (last_of_row) rt_commit(a_empty);
+                    rt_commit(&b_empty[sb]);
+                    if (st == STEPS - 1) {
+                        rt_commit(&d_full[s]);
+                        if (last_of_row) rt_commit(a_empty);
+                    }
+                }
+                __syncwarp();
             }
-            __syncwarp();
             if (last_of_row) ++a_gen;
         }
     } else if (warp <= 8) {
@@ -293,21 +303,25 @@ recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_consta
                 cur_rt = rt;
                 ++a_gen;
             }
-            const uint32_t s = n % NB;
-            if (n >= NB) rt_mbar_wait(&b_empty[s], ((n / NB) - 1) & 1u);
-            unsigned char* stage = b_smem + s * B_STAGE;
+            // 2- and 3-way tensors: factor rows of this thread's four columns (32 apart): one division per tile, then an
+            // odometer — once per tile, not per chunk (the producers set the pace at rank 33..64)
+            const bool three = p.ndim == 3;
+            const float* r1[4] = {nullptr, nullptr, nullptr, nullptr};
+            const float* r2[4] = {nullptr, nullptr, nullptr, nullptr};
+            bool ok[4] = {false, false, false, false};
             if (p.ndim <= 3) {
-                // 2- and 3-way tensors: the 4 columns of this thread are 32 apart — one division per tile, then an
-                // odometer; all 8 factor-row loads are issued before the first product (two columns at a time was a
-                // chain of exposed L2 round trips: the producers, not HBM, set the pace)
-                const bool three = p.ndim == 3;
                 const int64_t I2 = three ? p.shape[2] : 1;
                 const int64_t gc0 = ct * RT_N + rr;
-                int64_t j = three ? gc0 / I2 : gc0;
-                int64_t k = three ? gc0 - j * I2 : 0;
-                const float* r1[4];
-                const float* r2[4];
-                bool ok[4];
+                int64_t j, k;
+                if (p.C < (1LL << 31)) {                  // 32-bit division: a fifth of the 64-bit one's instructions
+                    const uint32_t g32 = (uint32_t)gc0, i32 = (uint32_t)I2;
+                    const uint32_t q = three ? g32 / i32 : g32;
+                    j = q;
+                    k = three ? g32 - q * i32 : 0;
+                } else {
+                    j = three ? gc0 / I2 : gc0;
+                    k = three ? gc0 - j * I2 : 0;
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     ok[i] = j < p.shape[1];
@@ -315,8 +329,19 @@ recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_consta
                     r2[i] = three ? p.f[2] + k * p.rs[2] : p.f[1];
                     if (three) { k += 32; while (k >= I2) { k -= I2; ++j; } } else j += 32;
                 }
+            }
 #pragma unroll
-                for (int ch = 0; ch < CHUNKS; ++ch) {
+            for (int st = 0; st < STEPS; ++st) {
+            const uint32_t step = n * STEPS + st;            // one barrier step per CPS 32-wide chunks of the tile
+            const uint32_t s = step % NST;
+            if (step >= (uint32_t)NST) rt_mbar_wait(&b_empty[s], ((step / NST) - 1) & 1u);
+            if (p.ndim <= 3) {
+                // all 8 factor-row loads of a chunk are issued before the first product (two columns at a time was a
+                // chain of exposed L2 round trips)
+#pragma unroll
+                for (int c2 = 0; c2 < CPS; ++c2) {
+                    const int ch = st * CPS + c2;
+                    unsigned char* stage = b_smem + (s * CPS + c2) * B_STAGE;
                     const int r0 = ch * 32 + 4 * c;
                     float4 u1[4], u2[4];
 #pragma unroll
@@ -328,10 +353,14 @@ recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_consta
                     for (int i = 0; i < 4; ++i) {
                         float4 v = u1[i];
                         if (three) { v.x *= u2[i].x; v.y *= u2[i].y; v.z *= u2[i].z; v.w *= u2[i].w; }
-                        store_chunk(stage + ch * 32768, stage + ch * 32768 + 16384, rr + 32 * i, v);
+                        store_chunk(stage, stage + 16384, rr + 32 * i, v);
                     }
                 }
             } else {
+#pragma unroll
+            for (int c2 = 0; c2 < CPS; ++c2) {
+            const int ch = st * CPS + c2;
+            unsigned char* stage = b_smem + (s * CPS + c2) * B_STAGE;
 #pragma unroll 2
             for (int i = 0; i < 4; ++i) {
                 const int col = rr + 32 * i;
@@ -351,8 +380,7 @@ recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_consta
                     }
                     kp1 = p.f[1] + rem * p.rs[1];
                 }
-#pragma unroll
-                for (int ch = 0; ch < CHUNKS; ++ch) {
+                {
                     const int r0 = ch * 32 + 4 * c;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (gc < p.C) {
@@ -365,12 +393,14 @@ recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_consta
                             }
                         }
                     }
-                    store_chunk(stage + ch * 32768, stage + ch * 32768 + 16384, col, v);
+                    store_chunk(stage, stage + 16384, col, v);
                 }
+            }
             }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             rt_mbar_arrive(&b_full[s]);
+            }
         }
     } else if (warp == 13) {
         // ================= TMA loader of the x / mask boxes (imputation / masked variants, TMA epilogue only) ==========
@@ -682,10 +712,10 @@ int recon_tc_launch(const void* const* factors, const int64_t* shape, const int6
     p.use_tma = tc_available() && p.C % 4 == 0 && p.C < (1LL << 31) && p.I < (1LL << 31) &&
                 reinterpret_cast<uintptr_t>(out) % 16 == 0 && (!x || reinterpret_cast<uintptr_t>(x) % 16 == 0) &&
                 (!mask || reinterpret_cast<uintptr_t>(mask) % 16 == 0) && !getenv("TLB200_RECON_NO_TMA");
-    // two lines per row and box where the extents allow it (C % 32 == 0) and shared memory holds the slots (rank <= 32)
+    // two lines per row and box where the extents allow it (C % 32 == 0)
     static int w_cap = -1;
     if (w_cap < 0) { const char* e = getenv("TLB200_RECON_LINES"); w_cap = e ? atoi(e) : 2; }
-    const int W = (p.use_tma && p.C % 32 == 0 && rank <= 32 && w_cap >= 2) ? 2 : 1;
+    const int W = (p.use_tma && p.C % 32 == 0 && w_cap >= 2 && !(rank > 32 && mode == 0)) ? 2 : 1;
     if (p.use_tma) {
         int st;
         const void* bases[3] = {out, x, mask};
@@ -713,6 +743,10 @@ int recon_tc_launch(const void* const* factors, const int64_t* shape, const int6
         if (mode == 0) return launch_one<1, 0, 1>(p, maps, grid, stream);
         if (mode == 1) return launch_one<1, 1, 1>(p, maps, grid, stream);
         return launch_one<1, 2, 1>(p, maps, grid, stream);
+    }
+    if (Wk == 2) {
+        if (mode == 1) return launch_one<2, 1, 2>(p, maps, grid, stream);
+        return launch_one<2, 2, 2>(p, maps, grid, stream);
     }
     if (mode == 0) return launch_one<2, 0, 1>(p, maps, grid, stream);
     if (mode == 1) return launch_one<2, 1, 1>(p, maps, grid, stream);
