@@ -150,7 +150,9 @@ struct RtCfg {
     static_assert(SMEM <= 227 * 1024, "smem budget");
 };
 
-template <int CHUNKS, int MODE, int W>
+// ND4: the tensor is 4-way (its producers carry a two-level column odometer; a separate instance because the extra
+// registers cost the 2- / 3-way path 5-25 % when both live in one kernel)
+template <int CHUNKS, int MODE, int W, bool ND4>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_constant__ CUtensorMap x_map,
                 const __grid_constant__ CUtensorMap mask_map, const ReconTcParams p) {
@@ -309,7 +311,7 @@ recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_consta
             const float* r1[4] = {nullptr, nullptr, nullptr, nullptr};
             const float* r2[4] = {nullptr, nullptr, nullptr, nullptr};
             bool ok[4] = {false, false, false, false};
-            if (p.ndim <= 3) {
+            if (!ND4 && p.ndim <= 3) {
                 const int64_t I2 = three ? p.shape[2] : 1;
                 const int64_t gc0 = ct * RT_N + rr;
                 int64_t j, k;
@@ -330,29 +332,61 @@ recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_consta
                     if (three) { k += 32; while (k >= I2) { k -= I2; ++j; } } else j += 32;
                 }
             }
+            // 4-way tensors (ND4 instances): the same with a two-level odometer
+            const float* q3[4] = {nullptr, nullptr, nullptr, nullptr};
+            if constexpr (ND4) {
+                const int64_t I2 = p.shape[2], I3 = p.shape[3];
+                const int64_t gc0 = ct * RT_N + rr;
+                int64_t j, k, l;
+                if (p.C < (1LL << 31)) {
+                    const uint32_t g32 = (uint32_t)gc0, i2 = (uint32_t)I2, i3 = (uint32_t)I3;
+                    const uint32_t t = g32 / i3;
+                    l = g32 - t * i3;
+                    const uint32_t q = t / i2;
+                    k = t - q * i2;
+                    j = q;
+                } else {
+                    const int64_t t = gc0 / I3;
+                    l = gc0 - t * I3;
+                    j = t / I2;
+                    k = t - j * I2;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    ok[i] = j < p.shape[1];
+                    r1[i] = p.f[1] + (ok[i] ? j : 0) * p.rs[1];
+                    r2[i] = p.f[2] + k * p.rs[2];
+                    q3[i] = p.f[3] + l * p.rs[3];
+                    l += 32;
+                    while (l >= I3) { l -= I3; ++k; }
+                    while (k >= I2) { k -= I2; ++j; }
+                }
+            }
 #pragma unroll
             for (int st = 0; st < STEPS; ++st) {
             const uint32_t step = n * STEPS + st;            // one barrier step per CPS 32-wide chunks of the tile
             const uint32_t s = step % NST;
             if (step >= (uint32_t)NST) rt_mbar_wait(&b_empty[s], ((step / NST) - 1) & 1u);
-            if (p.ndim <= 3) {
-                // all 8 factor-row loads of a chunk are issued before the first product (two columns at a time was a
+            if (ND4 || p.ndim <= 3) {
+                // all factor-row loads of a chunk are issued before the first product (two columns at a time was a
                 // chain of exposed L2 round trips)
 #pragma unroll
                 for (int c2 = 0; c2 < CPS; ++c2) {
                     const int ch = st * CPS + c2;
                     unsigned char* stage = b_smem + (s * CPS + c2) * B_STAGE;
                     const int r0 = ch * 32 + 4 * c;
-                    float4 u1[4], u2[4];
+                    float4 u1[4], u2[4], u3[ND4 ? 4 : 1];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         u1[i] = ok[i] ? load4(r1[i], p.cs[1], r0, unit_cs) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (three) u2[i] = load4(r2[i], p.cs[2], r0, unit_cs);
+                        if (ND4 || three) u2[i] = load4(r2[i], p.cs[2], r0, unit_cs);
+                        if constexpr (ND4) u3[i] = load4(q3[i], p.cs[3], r0, unit_cs);
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        float4 v = u1[i];
-                        if (three) { v.x *= u2[i].x; v.y *= u2[i].y; v.z *= u2[i].z; v.w *= u2[i].w; }
+                        float4 v = u1[i];      // products left to right, like the reference's khatri_rao
+                        if (ND4 || three) { v.x *= u2[i].x; v.y *= u2[i].y; v.z *= u2[i].z; v.w *= u2[i].w; }
+                        if constexpr (ND4) { v.x *= u3[i].x; v.y *= u3[i].y; v.z *= u3[i].z; v.w *= u3[i].w; }
                         store_chunk(stage, stage + 16384, rr + 32 * i, v);
                     }
                 }
@@ -655,16 +689,22 @@ recon_tc_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_consta
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
-template <int CHUNKS, int MODE, int W>
-int launch_one(const ReconTcParams& p, const CUtensorMap* maps, int grid, cudaStream_t stream) {
+template <int CHUNKS, int MODE, int W, bool ND4>
+int launch_nd(const ReconTcParams& p, const CUtensorMap* maps, int grid, cudaStream_t stream) {
     // at least 120 KB: two of these CTAs must never share an SM (each allocates all 512 TMEM columns)
     constexpr int need = RtCfg<CHUNKS, MODE, W>::SMEM;
     constexpr int smem = need > 120 * 1024 ? need : 120 * 1024;
     static std::atomic<uint64_t> attr_done{0};
-    if (ensure_dynamic_smem(recon_tc_kernel<CHUNKS, MODE, W>, smem, attr_done)) return TLB200_ECUDA;
-    recon_tc_kernel<CHUNKS, MODE, W><<<grid, RT_THREADS, smem, stream>>>(maps[0], maps[1], maps[2], p);
+    if (ensure_dynamic_smem(recon_tc_kernel<CHUNKS, MODE, W, ND4>, smem, attr_done)) return TLB200_ECUDA;
+    recon_tc_kernel<CHUNKS, MODE, W, ND4><<<grid, RT_THREADS, smem, stream>>>(maps[0], maps[1], maps[2], p);
     TLB_CHECK_LAUNCH();
     return TLB200_OK;
+}
+
+template <int CHUNKS, int MODE, int W>
+int launch_one(const ReconTcParams& p, const CUtensorMap* maps, int grid, cudaStream_t stream) {
+    return p.ndim == 4 ? launch_nd<CHUNKS, MODE, W, true>(p, maps, grid, stream)
+                       : launch_nd<CHUNKS, MODE, W, false>(p, maps, grid, stream);
 }
 
 }  // namespace

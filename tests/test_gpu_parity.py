@@ -832,7 +832,9 @@ def test_cp_to_tensor_golden(golden):
                                         ((256, 96, 80), 32), ((200, 130, 52), 20), ((300, 77, 61), 64),
                                         ((64, 32, 24, 40), 48), ((2000, 1100), 7),
                                         # two contraction chunks through the TMA epilogue (one / two lines per box)
-                                        ((256, 64, 128), 64), ((192, 80, 96), 48), ((100, 90, 124), 40)])
+                                        ((256, 64, 128), 64), ((192, 80, 96), 48), ((100, 90, 124), 40),
+                                        # 4-way instances of the tensor-core kernel (two-level column odometer)
+                                        ((128, 32, 36, 28), 24), ((96, 20, 24, 32), 64)])
 def test_cp_to_tensor_and_impute_vs_oracle(shape, rank, dtype):
     rng = np.random.RandomState(17)
     fs = [(rng.random_sample((s, rank)) - 0.4).astype(dtype) for s in shape]
