@@ -53,10 +53,11 @@ for shape in [(64, 48, 96), (33, 47, 51)]:
         assert float(torch.linalg.norm(got - ref) / torch.linalg.norm(ref)) < 1e-12
 # reconstruction / imputation on the tensor cores: TMA epilogue with two-line and one-line boxes, two contraction chunks,
 # and the transposing epilogue for extents TMA cannot describe
-for shape, R in [((256, 64, 64), 32), ((256, 66, 62), 24), ((192, 64, 96), 48), ((192, 75, 73), 20)]:
+for shape, R in [((256, 64, 64), 32), ((256, 66, 62), 24), ((192, 64, 96), 48), ((192, 75, 73), 20), ((128, 16, 24, 32), 40)]:
     fs = [torch.randn(s, R, device="cuda") for s in shape]
     w = torch.rand(R, device="cuda") + 0.5
-    ref = torch.einsum("ir,jr,kr->ijk", fs[0].double() * w.double(), fs[1].double(), fs[2].double())
+    sub = ",".join(f"{'ijkl'[m]}r" for m in range(len(shape)))
+    ref = torch.einsum(sub + "->" + "ijkl"[:len(shape)], fs[0].double() * w.double(), *[f.double() for f in fs[1:]])
     rec = tb.cp_to_tensor((w, fs))
     paths.add("recon-" + tb.last_kernel_path())
     assert float(torch.linalg.norm(rec.double() - ref) / torch.linalg.norm(ref)) < 1e-5, shape
