@@ -26,7 +26,7 @@ for line in sass.splitlines():
         arch = m.group(1)
     if fn is None:
         continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+    m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
     if m:
         op = m.group(1)
         counts[fn]["total"] += 1
